@@ -1,0 +1,18 @@
+"""boss_runs_b200 — B200 (sm_100a) implementation of BOSS-RUNS' periodic strategy update.
+
+Layout:
+  csrc/            CUDA kernels + the C ABI of libbossgpu.so (declared in include/bossgpu.h)
+  build.py         nvcc recipe (in-tree build)
+  _lib.py          ctypes binding, error mapping
+  engine.py        `Engine`: one GPU shard behind the C ABI
+  priors.py        host constants of the scoring model (mirror of upstream `Priors`)
+  hostmodel.py     host mirrors: PafLine/parse_PAF, ReadlengthDist, ReadStartDist
+  runs.py          reference-facing API: Contig, Reference, CoverageConverter, BossRuns
+  dropin.py        the same engine underneath the upstream `BossRuns` / `BossRunsSim` classes
+  sharding.py      multi-GPU: genome-axis partition + NCCL exchange steps
+  synth.py         synthetic references / read batches of BASELINE.json's shapes (tests, bench)
+
+Importing the package never touches CUDA; the first `Engine` loads libbossgpu.so and fails loudly if it
+is missing or finds no device. There is no CPU fallback.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,1021 @@
+// bossgpu.cu — C ABI of libbossgpu.so (see include/bossgpu.h for the contract and the reference
+// file:line each entry point replaces). Host-side orchestration only; kernels live in the .cuh files.
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <thread>
+
+#include "common.cuh"
+#include "table.cuh"
+#include "scatter.cuh"
+#include "score_pass.cuh"
+#include "strategy.cuh"
+#include "synth.cuh"
+#include "tokenizer.h"
+
+namespace boss {
+thread_local std::string g_last_error;
+}
+using namespace boss;
+
+#define H_CHECK(h)                                                                 \
+    do {                                                                           \
+        if (!(h)) return fail(BOSSGPU_EINVAL, "null handle");                      \
+        BOSS_CUDA(cudaSetDevice((h)->device));                                     \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(T** p, size_t n, bool zero = true) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    if (zero) BOSS_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+    return 0;
+}
+#define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+extern "C" int bossgpu_abi_version(void) { return BOSSGPU_ABI_VERSION; }
+extern "C" const char* bossgpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" int bossgpu_device_count(int* n) {
+    if (!n) return fail(BOSSGPU_EINVAL, "null out pointer");
+    BOSS_CUDA(cudaGetDeviceCount(n));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch / staging buffers (grow on demand)
+// ------------------------------------------------------------------------------------------------
+static int ensure_scratch(bossgpu_handle* h, size_t bytes) {
+    if (bytes <= h->scratch_d_bytes) return 0;
+    if (h->scratch_d) cudaFree(h->scratch_d);
+    h->scratch_d = nullptr; h->scratch_d_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&h->scratch_d, want);
+    if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "scratch cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    h->scratch_d_bytes = want;
+    return 0;
+}
+static int ensure_stage(bossgpu_handle* h, size_t bytes) {
+    if (bytes > h->stage_d_bytes) {
+        if (h->stage_d) cudaFree(h->stage_d);
+        h->stage_d = nullptr; h->stage_d_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&h->stage_d, want);
+        if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "stage cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        h->stage_d_bytes = want;
+    }
+    if (bytes > h->stage_h_bytes) {
+        if (h->stage_h) cudaFreeHost(h->stage_h);
+        h->stage_h = nullptr; h->stage_h_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMallocHost(&h->stage_h, want);
+        if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        h->stage_h_bytes = want;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
+    if (!cfg || !out) return fail(BOSSGPU_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != BOSSGPU_ABI_VERSION)
+        return fail(BOSSGPU_EINVAL, "ABI version mismatch: caller %d, library %d", cfg->abi_version, BOSSGPU_ABI_VERSION);
+    if (cfg->n_segments <= 0 || cfg->n_barcodes <= 0 || !cfg->segments || !cfg->ref_codes || !cfg->contig_len_all ||
+        cfg->n_contigs_total <= 0)
+        return fail(BOSSGPU_EINVAL, "empty geometry");
+    if (cfg->len_g != 5 && cfg->len_g != 15) return fail(BOSSGPU_EINVAL, "len_g must be 5 (haploid) or 15 (diploid)");
+    if (!cfg->phi || !cfg->priors || !cfg->phi_pow) return fail(BOSSGPU_EINVAL, "missing scoring constants");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev <= 0)
+        return fail(BOSSGPU_ECUDA, "no usable CUDA device (%s); libbossgpu has no CPU fallback",
+                    e0 == cudaSuccess ? "device count is 0" : cudaGetErrorString(e0));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(BOSSGPU_EINVAL, "device %d out of range [0,%d)", cfg->device, ndev);
+    BOSS_CUDA(cudaSetDevice(cfg->device));
+
+    bossgpu_handle* h = new bossgpu_handle();
+    h->device = cfg->device;
+    h->stream = (cudaStream_t)cfg->stream;
+    h->nb = cfg->n_barcodes;
+    h->len_g = cfg->len_g;
+    h->n_seg = cfg->n_segments;
+    h->n_contigs_total = cfg->n_contigs_total;
+    h->halo_bins = cfg->halo_bins;
+    h->n_sites_total = cfg->n_sites_total;
+    h->n_windows_total = cfg->n_windows_total;
+    h->score0 = cfg->score0_contig;
+    h->ent0 = cfg->entropy0_contig;
+    h->contig_len_all.assign(cfg->contig_len_all, cfg->contig_len_all + cfg->n_contigs_total);
+    {   // fhat * 2^shift summed over everything must stay below 2^63: sum(fhat) ~ nb (+ tail copies)
+        int lg = 0;
+        while ((1 << lg) < h->nb) ++lg;
+        h->fhat_shift = 60 - lg;
+    }
+
+    // ---- global axes --------------------------------------------------------------------------
+    std::vector<int64_t> o_row(h->n_contigs_total + 1, 0), o_srow(h->n_contigs_total + 1, 0);
+    int64_t sumL = 0;
+    for (int k = 0; k < h->n_contigs_total; ++k) {
+        int64_t L = h->contig_len_all[k];
+        if (L < BUCKET) { delete h; return fail(BOSSGPU_EINVAL, "contig %d shorter than one bucket (%lld)", k, (long long)L); }
+        o_row[k + 1] = o_row[k] + L / BIN + 1;
+        o_srow[k + 1] = o_srow[k] + L / BIN;
+        sumL += L;
+    }
+    h->M_rows = o_row[h->n_contigs_total];
+    h->target_rows = h->n_sites_total / BIN;
+    h->Tf_rows = sumL / BIN;
+    if (h->target_rows < o_srow[h->n_contigs_total] || h->target_rows - h->M_rows > h->M_rows) {
+        delete h;
+        return fail(BOSSGPU_EINVAL, "n_sites_total inconsistent with contig lengths");
+    }
+
+    // ---- segments -----------------------------------------------------------------------------
+    h->segs.resize(h->n_seg);
+    int64_t P = 0, tiles = 0, ds = 0, rows = 0, srows = 0, sw = 0;
+    for (int s = 0; s < h->n_seg; ++s) {
+        const bossgpu_segment& in = cfg->segments[s];
+        SegDev& S = h->segs[s];
+        if (in.contig < 0 || in.contig >= h->n_contigs_total || in.contig_len != h->contig_len_all[in.contig] ||
+            in.start < 0 || in.len <= 0 || in.start % BUCKET != 0 || in.start + in.len > in.contig_len ||
+            (in.start + in.len != in.contig_len && (in.start + in.len) % BUCKET != 0)) {
+            delete h;
+            return fail(BOSSGPU_EINVAL, "segment %d is not a bucket-aligned range of its contig", s);
+        }
+        if (s > 0) {
+            const SegDev& Pv = h->segs[s - 1];
+            bool contiguous = (in.contig == Pv.contig && in.start == Pv.start + Pv.len) ||
+                              (in.contig == Pv.contig + 1 && in.start == 0 && Pv.is_tail);
+            if (!contiguous) { delete h; return fail(BOSSGPU_EINVAL, "segments must be a contiguous range of the genome axis"); }
+        }
+        S.contig = in.contig;
+        S.contig_len = in.contig_len;
+        S.start = in.start;
+        S.len = in.len;
+        S.is_tail = (in.start + in.len == in.contig_len) ? 1 : 0;
+        S.site_off = P;
+        P += round_up(S.len, SITE_ALIGN);
+        S.n_bins = S.is_tail ? (S.contig_len / BIN + 1 - S.start / BIN) : S.len / BIN;
+        S.halo_l = (S.start > 0) ? h->halo_bins : 0;
+        S.halo_r = (!S.is_tail) ? h->halo_bins : 0;
+        S.ds_off = ds + S.halo_l;
+        ds += S.halo_l + S.n_bins + S.halo_r;
+        S.row_off = rows;
+        rows += S.n_bins;
+        S.n_srows = S.is_tail ? (S.contig_len / BIN - S.start / BIN) : S.len / BIN;
+        S.srow_off = srows;
+        srows += S.n_srows;
+        S.n_full_buckets = S.is_tail ? (S.contig_len / BUCKET - S.start / BUCKET) : S.len / BUCKET;
+        S.n_sw = S.n_full_buckets + (S.is_tail ? 1 : 0);
+        if (S.is_tail && S.n_full_buckets < 1) {
+            delete h;
+            return fail(BOSSGPU_EINVAL, "tail segment %d must hold at least one complete bucket", s);
+        }
+        S.sw_off = sw;
+        sw += S.n_sw;
+        S.tile_off = tiles;
+        S.n_tiles = ceil_div(S.n_bins * BIN, TILE);
+        tiles += S.n_tiles;
+    }
+    h->P = P; h->n_tiles = tiles; h->ds_len = ds; h->n_rows = rows; h->n_srows = srows; h->n_sw = sw;
+    h->R0 = o_row[h->segs[0].contig] + h->segs[0].start / BIN;
+    h->D0 = o_srow[h->segs[0].contig] + h->segs[0].start / BIN;
+
+    // ---- device memory ------------------------------------------------------------------------
+    int rc = 0;
+    auto A = [&](int r) { if (rc == 0) rc = r; };
+    A(dev_alloc(&h->d_segs, h->n_seg));
+    A(dev_alloc(&h->d_tile_start, h->n_seg + 1));
+    A(dev_alloc(&h->d_row_start, h->n_seg + 1));
+    A(dev_alloc(&h->d_srow_start, h->n_seg + 1));
+    A(dev_alloc(&h->d_ref, (size_t)P));
+    A(dev_alloc(&h->d_cov, (size_t)h->nb * 5 * P));
+    if (h->nb > 1) A(dev_alloc(&h->d_rowflag, (size_t)P));
+    A(dev_alloc(&h->d_table, (size_t)NPAT * 4));
+    A(dev_alloc(&h->d_etable, (size_t)NPAT * 4));
+    A(dev_alloc(&h->d_phi, (size_t)5 * h->len_g));
+    A(dev_alloc(&h->d_priors, (size_t)4 * h->len_g));
+    A(dev_alloc(&h->d_phi_pow, (size_t)5 * h->len_g * FREEZE));
+    A(dev_alloc(&h->d_cov_total, (size_t)h->n_contigs_total));
+    A(dev_alloc(&h->d_drop_thr, (size_t)h->n_contigs_total));
+    A(dev_alloc(&h->d_ds, (size_t)h->nb * ds));
+    A(dev_alloc(&h->d_benefit, (size_t)h->nb * rows));
+    A(dev_alloc(&h->d_bucket_sum, (size_t)sw * h->nb));
+    A(dev_alloc(&h->d_bucket_sw, (size_t)sw * h->nb));
+    A(dev_alloc(&h->d_fhat_w, (size_t)h->n_windows_total * 2));
+    A(dev_alloc(&h->d_hist, (size_t)3 * HBINS + 4));
+    A(dev_alloc(&h->d_strat, (size_t)srows * 2 * h->nb));
+    A(dev_alloc(&h->d_upd, 1));
+    A(dev_alloc(&h->d_ingest_err, 1));
+    A(dev_alloc((int64_t**)&h->scratch_d, 1));   // placeholder so scratch is never null
+    h->scratch_d_bytes = sizeof(int64_t);
+    if (rc != 0) { bossgpu_destroy(h); return rc; }
+    BOSS_CUDA(cudaMallocHost((void**)&h->h_upd, sizeof(UpdateDev)));
+    BOSS_CUDA(cudaMallocHost((void**)&h->h_ingest_err, sizeof(int32_t)));
+    for (auto& ev : h->ev) BOSS_CUDA(cudaEventCreate(&ev));
+
+    // geometry tables
+    {
+        std::vector<int64_t> ts(h->n_seg + 1), rs(h->n_seg + 1), ss(h->n_seg + 1);
+        for (int s = 0; s < h->n_seg; ++s) { ts[s] = h->segs[s].tile_off; rs[s] = h->segs[s].row_off; ss[s] = h->segs[s].srow_off; }
+        ts[h->n_seg] = tiles; rs[h->n_seg] = rows; ss[h->n_seg] = srows;
+        BOSS_CUDA(cudaMemcpy(h->d_segs, h->segs.data(), sizeof(SegDev) * h->n_seg, cudaMemcpyHostToDevice));
+        BOSS_CUDA(cudaMemcpy(h->d_tile_start, ts.data(), sizeof(int64_t) * ts.size(), cudaMemcpyHostToDevice));
+        BOSS_CUDA(cudaMemcpy(h->d_row_start, rs.data(), sizeof(int64_t) * rs.size(), cudaMemcpyHostToDevice));
+        BOSS_CUDA(cudaMemcpy(h->d_srow_start, ss.data(), sizeof(int64_t) * ss.size(), cudaMemcpyHostToDevice));
+    }
+    // reference bases, segment by segment onto the padded axis
+    {
+        const uint8_t* src = cfg->ref_codes;
+        for (int s = 0; s < h->n_seg; ++s) {
+            BOSS_CUDA(cudaMemcpy(h->d_ref + h->segs[s].site_off, src, (size_t)h->segs[s].len, cudaMemcpyHostToDevice));
+            src += h->segs[s].len;
+        }
+    }
+    // Contig.strat starts all-accept (reference.py:118)
+    BOSS_CUDA(cudaMemset(h->d_strat, 1, (size_t)srows * 2 * h->nb));
+    BOSS_CUDA(cudaMemset(h->d_drop_thr, 0xFF, sizeof(int32_t) * h->n_contigs_total));
+    // scoring constants + dense table
+    BOSS_CUDA(cudaMemcpy(h->d_phi, cfg->phi, sizeof(double) * 5 * h->len_g, cudaMemcpyHostToDevice));
+    BOSS_CUDA(cudaMemcpy(h->d_priors, cfg->priors, sizeof(double) * 4 * h->len_g, cudaMemcpyHostToDevice));
+    BOSS_CUDA(cudaMemcpy(h->d_phi_pow, cfg->phi_pow, sizeof(double) * 5 * h->len_g * FREEZE, cudaMemcpyHostToDevice));
+    k_build_table<<<(unsigned)ceil_div(NPAT, 128), 128, 0, h->stream>>>(h->len_g, h->d_phi, h->d_priors, h->d_phi_pow,
+                                                                       h->d_table, h->d_etable);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+extern "C" int bossgpu_destroy(bossgpu_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {h->d_segs, h->d_tile_start, h->d_row_start, h->d_srow_start, h->d_ref, h->d_cov, h->d_rowflag,
+                    h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
+                    h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
+                    h->d_hist, h->d_strat, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all,
+                    h->d_shard_row_start, h->d_halo};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_upd) cudaFreeHost(h->h_upd);
+    if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
+    if (h->stage_h) cudaFreeHost(h->stage_h);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    delete h;
+    return 0;
+}
+
+extern "C" int bossgpu_synchronize(bossgpu_handle* h) {
+    H_CHECK(h);
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest
+// ------------------------------------------------------------------------------------------------
+static int launch_scatter(bossgpu_handle* h, int64_t n_reads, const int32_t* d_seg, const int64_t* d_tstart,
+                          const int32_t* d_bc, const int64_t* d_cig_off, const uint32_t* d_cig,
+                          const int64_t* d_base_off, const uint8_t* d_bases, int ascii, bool count_totals) {
+    BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    k_check_spans<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_cig_off, d_cig, d_base_off, h->d_ingest_err);
+    BOSS_KERNEL_CHECK();
+    unsigned grid = (unsigned)std::min<int64_t>(n_reads, 1 << 20);
+    k_scatter<<<grid, SC_THREADS, 0, h->stream>>>(n_reads, d_seg, d_tstart, d_bc, d_cig_off, d_cig, d_base_off, d_bases,
+                                                  ascii, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
+                                                  count_totals ? 1 : 0, h->d_ingest_err);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    h->ev_valid[0] = true;
+    h->launches += 2;
+    return 0;
+}
+
+static int add_contig_totals(bossgpu_handle* h, const int64_t* contig_cov_add) {
+    // tiny: n_contigs values; done with a device-side add so it stays ordered on the stream
+    size_t bytes = sizeof(int64_t) * h->n_contigs_total;
+    TRY(ensure_scratch(h, bytes));
+    BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, contig_cov_add, bytes, cudaMemcpyHostToDevice, h->stream));
+    k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total,
+                                                                                 (const unsigned long long*)h->scratch_d,
+                                                                                 h->n_contigs_total);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));   // scratch is reused by later calls
+    return 0;
+}
+
+static int check_ingest_error(bossgpu_handle* h) {
+    BOSS_CUDA(cudaMemcpyAsync(h->h_ingest_err, h->d_ingest_err, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    int32_t e = *h->h_ingest_err;
+    if (e != 0) {
+        BOSS_CUDA(cudaMemsetAsync(h->d_ingest_err, 0, sizeof(int32_t), h->stream));
+        if (e == BOSSGPU_EBASE)
+            return fail(BOSSGPU_EBASE, "a read base outside ACGT reached the coverage scatter (index out of bounds upstream)");
+        if (e == BOSSGPU_ESHAPE)
+            return fail(BOSSGPU_ESHAPE, "CIGAR does not consume exactly the aligned read slice");
+        return fail(e, "device-side ingest error %d", e);
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const int32_t* seg, const int64_t* tstart,
+                                     const int32_t* barcode, const int64_t* cig_off, const uint32_t* cigar,
+                                     const int64_t* base_off, const uint8_t* bases, int base_is_ascii, int on_device,
+                                     const int64_t* contig_cov_add) {
+    H_CHECK(h);
+    if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
+    if (contig_cov_add) TRY(add_contig_totals(h, contig_cov_add));
+    if (n_reads == 0) return 0;
+    if (!seg || !tstart || !barcode || !cig_off || !cigar || !base_off || !bases) return fail(BOSSGPU_EINVAL, "null batch array");
+    if (on_device) {
+        TRY(launch_scatter(h, n_reads, seg, tstart, barcode, cig_off, cigar, base_off, bases, base_is_ascii, contig_cov_add == nullptr));
+        return 0;   // errors surface at the next update / synchronize-checked call
+    }
+    const int64_t n_ops = cig_off[n_reads], n_bases = base_off[n_reads];
+    if (cig_off[0] != 0 || base_off[0] != 0 || n_ops < 0 || n_bases < 0) return fail(BOSSGPU_EINVAL, "offset arrays must start at 0");
+    // one staging blob: [seg | barcode | tstart | cig_off | base_off | cigar | bases]
+    size_t o_seg = 0;
+    size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
+    size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_cg = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(n_ops, 1), 16);
+    size_t total = o_bs + round_up(std::max<int64_t>(n_bases, 1), 16);
+    TRY(ensure_stage(h, total));
+    char* hs = (char*)h->stage_h;
+    memcpy(hs + o_seg, seg, sizeof(int32_t) * n_reads);
+    memcpy(hs + o_bc, barcode, sizeof(int32_t) * n_reads);
+    memcpy(hs + o_ts, tstart, sizeof(int64_t) * n_reads);
+    memcpy(hs + o_co, cig_off, sizeof(int64_t) * (n_reads + 1));
+    memcpy(hs + o_bo, base_off, sizeof(int64_t) * (n_reads + 1));
+    memcpy(hs + o_cg, cigar, sizeof(uint32_t) * n_ops);
+    memcpy(hs + o_bs, bases, (size_t)n_bases);
+    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
+    char* ds = (char*)h->stage_d;
+    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
+                       (const uint8_t*)(ds + o_bs), base_is_ascii, contig_cov_add == nullptr));
+    return check_ingest_error(h);
+}
+
+extern "C" int64_t bossgpu_tokenize_cigar(const char* text, int64_t len, uint32_t* out, int64_t cap, int64_t* ref_span,
+                                          int64_t* query_span) {
+    if (!text || len < 0 || (!out && cap > 0)) return fail(BOSSGPU_EINVAL, "bad tokenizer arguments");
+    int64_t r = 0, q = 0;
+    int64_t n = tokenize_cigar(text, len, out, cap, &r, &q);
+    if (n < 0) return fail(BOSSGPU_EINVAL, "CIGAR tokenizer: output capacity %lld too small", (long long)cap);
+    if (ref_span) *ref_span = r;
+    if (query_span) *query_span = q;
+    return n;
+}
+
+extern "C" int bossgpu_ingest_records(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+                                      const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
+                                      const int64_t* cig_off, const char* cigar_text, const int64_t* seq_off,
+                                      const char* seq_text, int n_threads) {
+    H_CHECK(h);
+    if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
+    if (n_reads == 0) return 0;
+    if (!contig || !tstart || !tend || !barcode || !rev || !cig_off || !cigar_text || !seq_off || !seq_text)
+        return fail(BOSSGPU_EINVAL, "null batch array");
+    if (cig_off[0] != 0 || seq_off[0] != 0) return fail(BOSSGPU_EINVAL, "offset arrays must start at 0");
+    // map global contig -> local segment (records API is for whole-contig shards; split shards use ingest_packed)
+    std::vector<int32_t> seg_of_contig(h->n_contigs_total, -1);
+    for (int s = 0; s < h->n_seg; ++s) {
+        if (h->segs[s].start != 0 || !h->segs[s].is_tail)
+            return fail(BOSSGPU_ESTATE, "bossgpu_ingest_records needs whole-contig segments");
+        seg_of_contig[h->segs[s].contig] = s;
+    }
+    // upper bound on ops: every op needs at least 2 characters
+    const int64_t cig_chars = cig_off[n_reads], n_bases = seq_off[n_reads];
+    const int64_t ops_cap = cig_chars / 2 + n_reads;
+    size_t o_seg = 0;
+    size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
+    size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_bs = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_cg = o_bs + round_up(std::max<int64_t>(n_bases, 1), 16);
+    size_t total = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
+    TRY(ensure_stage(h, total));
+    char* hs = (char*)h->stage_h;
+    int32_t* s_seg = (int32_t*)(hs + o_seg);
+    int32_t* s_bc = (int32_t*)(hs + o_bc);
+    int64_t* s_ts = (int64_t*)(hs + o_ts);
+    int64_t* s_co = (int64_t*)(hs + o_co);
+    int64_t* s_bo = (int64_t*)(hs + o_bo);
+    uint8_t* s_bs = (uint8_t*)(hs + o_bs);
+    uint32_t* s_cg = (uint32_t*)(hs + o_cg);
+
+    // ---- tokenise in parallel: each read writes at its worst-case op offset, compacted afterwards ----
+    std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads), cap_off(n_reads + 1);
+    cap_off[0] = 0;
+    for (int64_t i = 0; i < n_reads; ++i) cap_off[i + 1] = cap_off[i] + (cig_off[i + 1] - cig_off[i]) / 2 + 1;
+    int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (n_reads < 64) T = 1;
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            n_ops[i] = tokenize_cigar(cigar_text + cig_off[i], cig_off[i + 1] - cig_off[i], s_cg + cap_off[i],
+                                      cap_off[i + 1] - cap_off[i], &rspan[i], &qspan[i]);
+            const int64_t a = seq_off[i], b = seq_off[i + 1];
+            if (rev[i]) revcomp_copy(seq_text + a, b - a, (char*)s_bs + a);       // boss/utils.py:85-95
+            else memcpy(s_bs + a, seq_text + a, (size_t)(b - a));
+        }
+    };
+    if (T == 1) work(0, n_reads);
+    else {
+        std::vector<std::thread> pool;
+        // split by bases so long reads do not pile up in one thread
+        int64_t per = n_bases / T + 1, lo = 0;
+        for (int t = 0; t < T && lo < n_reads; ++t) {
+            int64_t hi = lo;
+            int64_t lim = seq_off[lo] + per;
+            while (hi < n_reads && (seq_off[hi] < lim || hi == lo)) ++hi;
+            if (t == T - 1) hi = n_reads;
+            pool.emplace_back(work, lo, hi);
+            lo = hi;
+        }
+        for (auto& th : pool) th.join();
+    }
+    // validate like upstream, then compact the ops
+    int64_t w = 0;
+    s_co[0] = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        if (n_ops[i] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
+        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
+        if (qspan[i] != seq_off[i + 1] - seq_off[i])
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
+                        (long long)i, (long long)qspan[i], (long long)(seq_off[i + 1] - seq_off[i]));
+        if (rspan[i] != t1 - t0)
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
+                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
+        if (contig[i] < 0 || contig[i] >= h->n_contigs_total) return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
+        s_seg[i] = seg_of_contig[contig[i]];
+        s_bc[i] = barcode[i];
+        s_ts[i] = t0;
+        s_bo[i] = seq_off[i];
+        if (w != cap_off[i]) memmove(s_cg + w, s_cg + cap_off[i], sizeof(uint32_t) * n_ops[i]);
+        w += n_ops[i];
+        s_co[i + 1] = w;
+    }
+    s_bo[n_reads] = n_bases;
+    size_t used = o_cg + sizeof(uint32_t) * std::max<int64_t>(w, 1);
+    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, used, cudaMemcpyHostToDevice, h->stream));
+    char* ds = (char*)h->stage_d;
+    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
+                       (const uint8_t*)(ds + o_bs), /*ascii=*/1, /*count_totals=*/true));
+    return check_ingest_error(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// update
+// ------------------------------------------------------------------------------------------------
+static int validate_params(const bossgpu_update_params* p) {
+    if (!p) return fail(BOSSGPU_EINVAL, "null update params");
+    for (int i = 0; i < NSTEPS; ++i) {
+        // bn.move_sum raises for window < 1 (reference.py:259-260 with approx_ccl < 100)
+        if (p->w[i] < 1) return fail(BOSSGPU_EINVAL, "staircase window %d is %d bins; Bottleneck's move_sum rejects windows < 1", i, p->w[i]);
+        if (i > 0 && p->w[i] < p->w[i - 1]) return fail(BOSSGPU_EINVAL, "staircase windows must be non-decreasing");
+        if (p->w[i] > 20000) return fail(BOSSGPU_EINVAL, "staircase window %d exceeds the supported 20000 bins", i);
+    }
+    return 0;
+}
+
+#define EV_BEGIN(i) BOSS_CUDA(cudaEventRecord(h->ev[2 * (i)], h->stream))
+#define EV_END(i)   do { BOSS_CUDA(cudaEventRecord(h->ev[2 * (i) + 1], h->stream)); h->ev_valid[i] = true; } while (0)
+
+static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
+    // reset per-update device scalars (keeps `error`)
+    BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
+    BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
+    EV_BEGIN(1);
+    {
+        // contig lengths live at the front of scratch for the threshold kernel
+        size_t bytes = sizeof(int64_t) * h->n_contigs_total;
+        TRY(ensure_scratch(h, bytes));
+        BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, h->contig_len_all.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+        k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
+            h->n_contigs_total, (const int64_t*)h->scratch_d, h->nb, h->d_cov_total, h->d_drop_thr);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
+    ScoreArgs a;
+    a.segs = h->d_segs; a.tile_start = h->d_tile_start; a.n_seg = h->n_seg; a.nb = h->nb; a.P = h->P;
+    a.ref = h->d_ref; a.cov = h->d_cov; a.rowflag = h->d_rowflag; a.table = h->d_table; a.drop_thr = h->d_drop_thr;
+    a.score0 = h->score0; a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
+    a.n_dropout = &h->d_upd->n_dropout;
+    dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
+    if (h->nb > 1) {
+        k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
+        BOSS_KERNEL_CHECK();
+        k_score_bin<true><<<grid, TILE_THREADS, 0, h->stream>>>(a);
+        h->launches += 2;
+    } else {
+        k_score_bin<false><<<grid, TILE_THREADS, 0, h->stream>>>(a);
+        h->launches++;
+    }
+    BOSS_KERNEL_CHECK();
+    EV_END(1);
+    EV_BEGIN(2);
+    int64_t max_sw = 0;
+    for (auto& S : h->segs) max_sw = std::max(max_sw, S.n_sw);
+    dim3 gb((unsigned)ceil_div(max_sw * h->nb, 128), (unsigned)h->n_seg);
+    k_buckets<<<gb, 128, 0, h->stream>>>(h->d_segs, h->n_seg, h->nb, p->bucket_threshold, h->d_bucket_sum, h->d_bucket_sw,
+                                         &h->d_upd->switched_on);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    EV_END(2);
+    return 0;
+}
+
+static int ensure_debug(bossgpu_handle* h) {
+    if (h->debug_bufs) return 0;
+    TRY(dev_alloc(&h->d_smu, (size_t)h->nb * h->n_rows));
+    TRY(dev_alloc(&h->d_expected, (size_t)h->nb * h->n_rows));
+    h->debug_bufs = true;
+    return 0;
+}
+
+static int phase1_smooth(bossgpu_handle* h, const bossgpu_update_params* p) {
+    if (p->write_debug) TRY(ensure_debug(h));
+    EV_BEGIN(3);
+    // per-segment tile table for the smoothing kernel (host-built, tiny)
+    std::vector<int64_t> st(h->n_seg + 1);
+    int64_t t = 0;
+    for (int s = 0; s < h->n_seg; ++s) { st[s] = t; t += ceil_div(h->segs[s].n_bins, SM_TILE); }
+    st[h->n_seg] = t;
+    size_t bytes = sizeof(int64_t) * st.size();
+    TRY(ensure_scratch(h, bytes + 64));
+    BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, st.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));      // st is a stack vector; cheap (tiny copy) and keeps lifetime simple
+    SmoothArgs a;
+    a.segs = h->d_segs; a.row_start = h->d_row_start; a.n_seg = h->n_seg; a.nb = h->nb; a.ds = h->d_ds; a.ds_len = h->ds_len;
+    a.benefit = h->d_benefit;
+    a.smu = p->write_debug ? h->d_smu : nullptr;
+    a.expected = p->write_debug ? h->d_expected : nullptr;
+    a.n_rows = h->n_rows;
+    int wmax = 4;
+    for (int i = 0; i < NSTEPS; ++i) { a.w[i] = p->w[i]; a.mult[i] = p->mult[i]; wmax = std::max(wmax, p->w[i]); }
+    a.wmax = wmax;
+    a.R0 = h->R0; a.target_rows = h->target_rows; a.upd = h->d_upd;
+    size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)(wmax - 1));
+    if (smem > 200 * 1024) return fail(BOSSGPU_EINVAL, "staircase window of %d bins needs %zu B of shared memory", wmax, smem);
+    dim3 grid((unsigned)t, (unsigned)h->nb);
+    k_smooth<<<grid, SM_TILE, smem, h->stream>>>(a, (const int64_t*)h->scratch_d);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    EV_END(3);
+    return 0;
+}
+
+static int upload_fhat(bossgpu_handle* h, const bossgpu_update_params* p) {
+    if (p->fhat_windows) {
+        size_t bytes = sizeof(double) * 2 * h->n_windows_total;
+        TRY(ensure_stage(h, bytes));
+        memcpy(h->stage_h, p->fhat_windows, bytes);
+        BOSS_CUDA(cudaMemcpyAsync(h->d_fhat_w, h->stage_h, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->have_fhat = true;
+    }
+    if (!h->have_fhat) return fail(BOSSGPU_ESTATE, "no F-hat uploaded yet");
+    return 0;
+}
+
+static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
+    EV_BEGIN(4);
+    FhatGeom fg{h->n_windows_total, h->Tf_rows, h->target_rows};
+    const int fsum_shift = 50;
+    k_fhat_sum<<<(unsigned)ceil_div(h->n_windows_total, 256), 256, 0, h->stream>>>(fg, h->d_fhat_w, fsum_shift, h->d_upd);
+    BOSS_KERNEL_CHECK();
+    k_fhat_finish<<<1, 1, 0, h->stream>>>(fsum_shift, h->d_upd);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned long long) * (3 * HBINS + 4), h->stream));
+    HistArgs a;
+    a.benefit = h->d_benefit; a.n_rows = h->n_rows; a.nb = h->nb; a.R0 = h->R0; a.M = h->M_rows; a.target = h->target_rows;
+    a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.hist = h->d_hist; a.upd = h->d_upd;
+    unsigned gx = (unsigned)std::min<int64_t>(ceil_div(h->n_rows, 256), 148 * 8);
+    k_hist<<<dim3(gx, (unsigned)h->nb), 256, 0, h->stream>>>(a);
+    BOSS_KERNEL_CHECK();
+    h->launches += 3;
+    EV_END(4);
+    return 0;
+}
+
+static int phase3_threshold(bossgpu_handle* h, const bossgpu_update_params* p) {
+    EV_BEGIN(5);
+    k_threshold<<<1, 32, 0, h->stream>>>(h->d_hist, h->fhat_shift, p->tc, h->d_upd);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    EV_END(5);
+    return 0;
+}
+
+static int phase4_distribute(bossgpu_handle* h, const uint8_t* merged_mask) {
+    EV_BEGIN(6);
+    DistArgs a;
+    a.segs = h->d_segs; a.srow_start = h->d_srow_start; a.n_seg = h->n_seg; a.nb = h->nb; a.benefit = h->d_benefit;
+    a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.merged_mask = merged_mask; a.bucket_sw = h->d_bucket_sw;
+    a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards; a.mask_stride = h->mask_stride;
+    a.strat = h->d_strat; a.n_srows = h->n_srows; a.upd = h->d_upd; a.n_accept = h->d_upd->n_accept;
+    int64_t total = h->n_srows * 2 * h->nb;
+    unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+    k_distribute<<<grid, 256, 0, h->stream>>>(a);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    EV_END(6);
+    return 0;
+}
+
+static int fetch_result(bossgpu_handle* h, bossgpu_update_result* r) {
+    BOSS_CUDA(cudaMemcpyAsync(h->h_upd, h->d_upd, sizeof(UpdateDev), cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    h->last = *h->h_upd;
+    for (int i = 0; i < BOSSGPU_N_TIMERS; ++i)
+        if (h->ev_valid[i]) cudaEventElapsedTime(&h->ms[i], h->ev[2 * i], h->ev[2 * i + 1]);
+    if (r) {
+        memset(r, 0, sizeof *r);
+        r->switched_on = h->last.switched_on;
+        r->strat_size = h->last.strat_size;
+        r->threshold = h->last.threshold;
+        r->normaliser = h->last.normaliser;
+        r->ubar0 = h->last.ubar0;
+        r->fhat_sum = h->last.fhat_sum;
+        r->n_nonzero = (int64_t)h->last.n_nonzero;
+        r->n_dropout = (int64_t)h->last.n_dropout;
+        r->n_accept[0] = (int64_t)h->last.n_accept[0];
+        r->n_accept[1] = (int64_t)h->last.n_accept[1];
+    }
+    TRY(check_ingest_error(h));
+    return 0;
+}
+
+extern "C" int bossgpu_update(bossgpu_handle* h, const bossgpu_update_params* p, bossgpu_update_result* r) {
+    H_CHECK(h);
+    TRY(validate_params(p));
+    for (const auto& S : h->segs)
+        if (S.start != 0 || !S.is_tail) return fail(BOSSGPU_ESTATE, "bossgpu_update needs whole-contig segments; use the phase API");
+    EV_BEGIN(7);
+    TRY(phase0_scores(h, p));
+    // The strategy half only runs once some bucket is on (core.py:172). The switch lives on the device;
+    // reading it costs one small sync, which also bounds how much work is queued behind an idle update.
+    BOSS_CUDA(cudaMemcpyAsync(&h->h_upd->switched_on, &h->d_upd->switched_on, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_upd->switched_on) {
+        TRY(upload_fhat(h, p));
+        TRY(phase1_smooth(h, p));
+        TRY(phase2_hist(h, p));
+        TRY(phase3_threshold(h, p));
+        // upstream raises on an all-zero benefit before touching any strategy (sequences.py:588)
+        BOSS_CUDA(cudaMemcpyAsync(&h->h_upd->empty, &h->d_upd->empty, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->h_upd->empty) {
+            EV_END(7);
+            fetch_result(h, r);
+            return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
+        }
+        TRY(phase4_distribute(h, nullptr));
+    }
+    EV_END(7);
+    return fetch_result(h, r);
+}
+
+static int pack_own_mask(bossgpu_handle* h);
+
+extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_params* p, bossgpu_update_result* r) {
+    H_CHECK(h);
+    TRY(validate_params(p));
+    if (phase != 0 && phase != h->phase_done + 1) return fail(BOSSGPU_ESTATE, "phase %d after phase %d", phase, h->phase_done);
+    switch (phase) {
+        case 0: EV_BEGIN(7); TRY(phase0_scores(h, p)); break;
+        case 1: TRY(upload_fhat(h, p)); TRY(phase1_smooth(h, p)); break;
+        case 2: TRY(phase2_hist(h, p)); break;
+        case 3: TRY(phase3_threshold(h, p)); TRY(pack_own_mask(h)); break;
+        case 4: TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_all : nullptr)); EV_END(7); TRY(fetch_result(h, r)); break;
+        default: return fail(BOSSGPU_EINVAL, "unknown phase %d", phase);
+    }
+    h->phase_done = phase == 4 ? -1 : phase;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-shard support: exchange buffers
+// ------------------------------------------------------------------------------------------------
+extern "C" int bossgpu_set_shards(bossgpu_handle* h, int32_t n_shards, int32_t shard_index, const int64_t* row_start) {
+    H_CHECK(h);
+    if (n_shards < 1 || shard_index < 0 || shard_index >= n_shards || !row_start) return fail(BOSSGPU_EINVAL, "bad shard description");
+    if (row_start[shard_index] != h->R0 || row_start[shard_index + 1] != h->R0 + h->n_rows)
+        return fail(BOSSGPU_EINVAL, "shard row table disagrees with this handle's segments");
+    h->n_shards = n_shards;
+    h->shard_index = shard_index;
+    h->shard_row_start.assign(row_start, row_start + n_shards + 1);
+    int64_t max_rows = 0;
+    for (int i = 0; i < n_shards; ++i) max_rows = std::max(max_rows, row_start[i + 1] - row_start[i]);
+    h->mask_stride = round_up(ceil_div(max_rows * 2 * h->nb, 8), 16);
+    if (h->d_mask_all) cudaFree(h->d_mask_all);
+    if (h->d_shard_row_start) cudaFree(h->d_shard_row_start);
+    TRY(dev_alloc(&h->d_mask_all, (size_t)h->mask_stride * n_shards));
+    TRY(dev_alloc(&h->d_shard_row_start, (size_t)n_shards + 1));
+    BOSS_CUDA(cudaMemcpy(h->d_shard_row_start, row_start, sizeof(int64_t) * (n_shards + 1), cudaMemcpyHostToDevice));
+    // halo staging: [left send | right send | left recv | right recv], each halo_bins * nb doubles
+    if (h->d_halo) cudaFree(h->d_halo);
+    TRY(dev_alloc(&h->d_halo, (size_t)4 * std::max(1, h->halo_bins) * h->nb));
+    return 0;
+}
+
+static int pack_own_mask(bossgpu_handle* h) {
+    if (h->n_shards <= 1) return 0;
+    int64_t n_bits = h->n_rows * 2 * h->nb;
+    k_pack_mask<<<(unsigned)ceil_div(ceil_div(n_bits, 8), 256), 256, 0, h->stream>>>(
+        h->d_benefit, h->n_rows, h->nb, h->R0, h->target_rows, h->d_upd, h->d_mask_all + (size_t)h->shard_index * h->mask_stride, n_bits);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    return 0;
+}
+
+// copy the edge bins of split contigs into / out of the halo staging buffers
+extern "C" int bossgpu_halo_pack(bossgpu_handle* h) {
+    H_CHECK(h);
+    if (h->halo_bins <= 0 || !h->d_halo) return 0;
+    const SegDev& F = h->segs.front();
+    const SegDev& L = h->segs.back();
+    const int hb = h->halo_bins;
+    BOSS_CUDA(cudaMemsetAsync(h->d_halo, 0, sizeof(double) * 2 * hb * h->nb, h->stream));
+    for (int b = 0; b < h->nb; ++b) {
+        if (F.start > 0) {      // my first bins go to the left neighbour (its right halo)
+            int64_t n = std::min<int64_t>(hb, F.n_bins);
+            BOSS_CUDA(cudaMemcpyAsync(h->d_halo + (size_t)b * hb, h->d_ds + (size_t)b * h->ds_len + F.ds_off, sizeof(double) * n,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+        }
+        if (!L.is_tail) {       // my last bins go to the right neighbour (its left halo), right-aligned
+            int64_t n = std::min<int64_t>(hb, L.n_bins);
+            BOSS_CUDA(cudaMemcpyAsync(h->d_halo + (size_t)(h->nb + b) * hb + (hb - n),
+                                      h->d_ds + (size_t)b * h->ds_len + L.ds_off + L.n_bins - n, sizeof(double) * n,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_halo_unpack(bossgpu_handle* h) {
+    H_CHECK(h);
+    if (h->halo_bins <= 0 || !h->d_halo) return 0;
+    const SegDev& F = h->segs.front();
+    const SegDev& L = h->segs.back();
+    const int hb = h->halo_bins;
+    double* recv_l = h->d_halo + (size_t)2 * hb * h->nb;     // from the left neighbour: its last bins, right-aligned
+    double* recv_r = recv_l + (size_t)hb * h->nb;            // from the right neighbour: its first bins
+    for (int b = 0; b < h->nb; ++b) {
+        if (F.start > 0)
+            BOSS_CUDA(cudaMemcpyAsync(h->d_ds + (size_t)b * h->ds_len + F.ds_off - hb, recv_l + (size_t)b * hb, sizeof(double) * hb,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+        if (!L.is_tail)
+            BOSS_CUDA(cudaMemcpyAsync(h->d_ds + (size_t)b * h->ds_len + L.ds_off + L.n_bins, recv_r + (size_t)b * hb, sizeof(double) * hb,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_ptr, size_t* bytes) {
+    H_CHECK(h);
+    if (!dev_ptr || !bytes) return fail(BOSSGPU_EINVAL, "null out pointer");
+    const size_t hb = (size_t)std::max(1, h->halo_bins) * h->nb * sizeof(double);
+    switch (which) {
+        case BOSSGPU_BUF_SWITCH: *dev_ptr = &h->d_upd->switched_on; *bytes = sizeof(int32_t); break;
+        case BOSSGPU_BUF_NORM: *dev_ptr = &h->d_upd->norm_bits; *bytes = sizeof(unsigned long long); break;
+        case BOSSGPU_BUF_HIST: *dev_ptr = h->d_hist; *bytes = sizeof(unsigned long long) * (3 * HBINS + 4); break;
+        case BOSSGPU_BUF_MASK:
+            if (!h->d_mask_all) return fail(BOSSGPU_ESTATE, "bossgpu_set_shards not called");
+            *dev_ptr = h->d_mask_all; *bytes = (size_t)h->mask_stride * h->n_shards; break;
+        case BOSSGPU_BUF_HALO_SEND:
+            if (!h->d_halo) return fail(BOSSGPU_ESTATE, "bossgpu_set_shards not called");
+            *dev_ptr = h->d_halo; *bytes = 2 * hb; break;
+        case BOSSGPU_BUF_HALO_RECV:
+            if (!h->d_halo) return fail(BOSSGPU_ESTATE, "bossgpu_set_shards not called");
+            *dev_ptr = (char*)h->d_halo + 2 * hb; *bytes = 2 * hb; break;
+        default: return fail(BOSSGPU_EINVAL, "unknown exchange buffer %d", which);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// getters / setters
+// ------------------------------------------------------------------------------------------------
+#define SEG_CHECK(h, seg)                                                                         \
+    do {                                                                                          \
+        if ((seg) < 0 || (seg) >= (h)->n_seg) return fail(BOSSGPU_EINVAL, "segment %d out of range", (int)(seg)); \
+    } while (0)
+
+extern "C" int64_t bossgpu_strat_rows(bossgpu_handle* h, int32_t seg) {
+    if (!h) return -1;
+    if (seg < 0) return h->n_srows;
+    if (seg >= h->n_seg) return -1;
+    return h->segs[seg].n_srows;
+}
+
+extern "C" int bossgpu_get_strat(bossgpu_handle* h, int32_t seg, uint8_t* out, int64_t out_bytes) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.n_srows * 2 * h->nb;
+    if (!out || out_bytes != n) return fail(BOSSGPU_EINVAL, "strat buffer must hold %lld bytes", (long long)n);
+    BOSS_CUDA(cudaMemcpyAsync(out, h->d_strat + (size_t)S.srow_off * 2 * h->nb, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_strat_all(bossgpu_handle* h, uint8_t* out, int64_t out_bytes) {
+    H_CHECK(h);
+    int64_t n = h->n_srows * 2 * h->nb;
+    if (!out || out_bytes != n) return fail(BOSSGPU_EINVAL, "strat buffer must hold %lld bytes", (long long)n);
+    BOSS_CUDA(cudaMemcpyAsync(out, h->d_strat, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_strat_packed(bossgpu_handle* h, uint8_t* out, int64_t out_bytes) {
+    H_CHECK(h);
+    int64_t n = h->n_srows * 2 * h->nb;
+    int64_t nbytes = ceil_div(n, 8);
+    if (!out || out_bytes != nbytes) return fail(BOSSGPU_EINVAL, "packed strat buffer must hold %lld bytes", (long long)nbytes);
+    TRY(ensure_scratch(h, (size_t)nbytes));
+    k_pack_strat<<<(unsigned)ceil_div(nbytes, 256), 256, 0, h->stream>>>(h->d_strat, n, (uint8_t*)h->scratch_d);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaMemcpyAsync(out, h->scratch_d, (size_t)nbytes, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_coverage(bossgpu_handle* h, int32_t seg, uint16_t* out, int64_t out_elems) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.len * 5 * h->nb;
+    if (!out || out_elems != n) return fail(BOSSGPU_EINVAL, "coverage buffer must hold %lld elements", (long long)n);
+    TRY(ensure_scratch(h, sizeof(uint16_t) * (size_t)n));
+    k_cov_to_ref_layout<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(S, h->nb, h->P, h->d_cov, (uint16_t*)h->scratch_d);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaMemcpyAsync(out, h->scratch_d, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_set_coverage(bossgpu_handle* h, int32_t seg, const uint16_t* in, int64_t in_elems) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.len * 5 * h->nb;
+    if (!in || in_elems != n) return fail(BOSSGPU_EINVAL, "coverage buffer must hold %lld elements", (long long)n);
+    TRY(ensure_scratch(h, sizeof(uint16_t) * (size_t)n + 16));
+    BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, in, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    k_cov_from_ref_layout<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(S, h->nb, h->P, (const uint16_t*)h->scratch_d, h->d_cov);
+    BOSS_KERNEL_CHECK();
+    // the contig depth total is state derived from the counters: recompute it for every contig of this shard
+    BOSS_CUDA(cudaMemsetAsync(h->d_cov_total, 0, sizeof(unsigned long long) * h->n_contigs_total, h->stream));
+    for (const auto& T : h->segs) {
+        k_depth_total<<<(unsigned)std::min<int64_t>(ceil_div(T.len, 256), 148 * 8), 256, 0, h->stream>>>(T, h->nb, h->P, h->d_cov, h->d_cov_total);
+        BOSS_KERNEL_CHECK();
+    }
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_scores(bossgpu_handle* h, int32_t seg, double* scores, double* entropy, int64_t out_elems) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.len * h->nb;
+    if (out_elems != n) return fail(BOSSGPU_EINVAL, "score buffers must hold %lld elements", (long long)n);
+    TRY(ensure_scratch(h, sizeof(double) * (size_t)n * 2));
+    double* ds = (double*)h->scratch_d;
+    double* de = ds + n;
+    k_materialise_scores<<<(unsigned)ceil_div(S.len, 256), 256, 0, h->stream>>>(S, h->nb, h->P, h->d_ref, h->d_cov, h->d_table, h->d_etable,
+                                                                                 h->d_drop_thr, h->score0, h->ent0, ds, de);
+    BOSS_KERNEL_CHECK();
+    if (scores) BOSS_CUDA(cudaMemcpyAsync(scores, ds, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (entropy) BOSS_CUDA(cudaMemcpyAsync(entropy, de, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_scores_ds(bossgpu_handle* h, int32_t seg, double* out, int64_t out_elems) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.n_bins * h->nb;
+    if (!out || out_elems != n) return fail(BOSSGPU_EINVAL, "scores_ds buffer must hold %lld elements", (long long)n);
+    TRY(ensure_scratch(h, sizeof(double) * (size_t)n));
+    k_gather_bins<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(h->d_ds, h->ds_len, S.ds_off, S.n_bins, h->nb, 1, (double*)h->scratch_d);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaMemcpyAsync(out, h->scratch_d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_benefit(bossgpu_handle* h, int32_t seg, double* additional, double* smu, double* expected, int64_t out_elems) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    int64_t n = S.n_bins * 2 * h->nb;
+    if (out_elems != n) return fail(BOSSGPU_EINVAL, "benefit buffers must hold %lld elements", (long long)n);
+    if ((smu || expected) && !h->debug_bufs) return fail(BOSSGPU_ESTATE, "smu/expected need write_debug in the last update");
+    TRY(ensure_scratch(h, sizeof(double) * (size_t)n));
+    const double2* srcs[3] = {h->d_benefit, h->d_smu, h->d_expected};
+    double* dsts[3] = {additional, smu, expected};
+    for (int i = 0; i < 3; ++i) {
+        if (!dsts[i]) continue;
+        k_gather_bins<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>((const double*)srcs[i], h->n_rows * 2, S.row_off * 2, S.n_bins * 2,
+                                                                         h->nb, 2, (double*)h->scratch_d);
+        BOSS_KERNEL_CHECK();
+        BOSS_CUDA(cudaMemcpyAsync(dsts[i], h->scratch_d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_get_buckets(bossgpu_handle* h, int32_t seg, uint8_t* switches, int64_t n, uint8_t* switched_on) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    if (n != S.n_sw * h->nb) return fail(BOSSGPU_EINVAL, "bucket buffer must hold %lld entries", (long long)(S.n_sw * h->nb));
+    std::vector<uint8_t> tmp((size_t)n);
+    BOSS_CUDA(cudaMemcpyAsync(tmp.data(), h->d_bucket_sw + (size_t)S.sw_off * h->nb, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    if (switches) memcpy(switches, tmp.data(), (size_t)n);
+    if (switched_on) {
+        // reference.py:203-207: once any bucket of any barcode is on, the whole contig is flagged
+        bool any = false;
+        for (uint8_t v : tmp) any |= v != 0;
+        for (int b = 0; b < h->nb; ++b) switched_on[b] = any ? 1 : 0;
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_set_buckets(bossgpu_handle* h, int32_t seg, const uint8_t* switches, int64_t n) {
+    H_CHECK(h);
+    SEG_CHECK(h, seg);
+    const SegDev& S = h->segs[seg];
+    if (!switches || n != S.n_sw * h->nb) return fail(BOSSGPU_EINVAL, "bucket buffer must hold %lld entries", (long long)(S.n_sw * h->nb));
+    BOSS_CUDA(cudaMemcpyAsync(h->d_bucket_sw + (size_t)S.sw_off * h->nb, switches, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_grid) {
+    H_CHECK(h);
+    std::vector<unsigned long long> tmp(3 * HBINS + 4);
+    BOSS_CUDA(cudaMemcpyAsync(tmp.data(), h->d_hist, sizeof(unsigned long long) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    for (int e = 0; e < HBINS; ++e) {
+        if (counts) counts[e] = (int64_t)tmp[e];
+        if (f_grid) f_grid[e] = from_limbs(tmp[HBINS + e], tmp[2 * HBINS + e], h->fhat_shift);
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_get_score_table(bossgpu_handle* h, double* scores, double* entropies) {
+    H_CHECK(h);
+    if (scores) BOSS_CUDA(cudaMemcpy(scores, h->d_table, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
+    if (entropies) BOSS_CUDA(cudaMemcpy(entropies, h->d_etable, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int64_t bossgpu_pattern_rank(const uint16_t c[5]) {
+    if (!c) return -1;
+    uint32_t s = (uint32_t)c[0] + c[1] + c[2] + c[3] + c[4];
+    if (s >= (uint32_t)FREEZE) return -1;
+    return pattern_rank(c[0], c[1], c[2], c[3], c[4]);
+}
+
+extern "C" int bossgpu_timing(bossgpu_handle* h, float ms[BOSSGPU_N_TIMERS]) {
+    if (!h || !ms) return fail(BOSSGPU_EINVAL, "null argument");
+    BOSS_CUDA(cudaSetDevice(h->device));
+    if (h->ev_valid[0]) { BOSS_CUDA(cudaEventSynchronize(h->ev[1])); cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]); }
+    for (int i = 0; i < BOSSGPU_N_TIMERS; ++i) ms[i] = h->ev_valid[i] ? h->ms[i] : -1.0f;
+    return 0;
+}
+
+extern "C" int64_t bossgpu_launch_count(bossgpu_handle* h) { return h ? h->launches : -1; }
+
+extern "C" int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double mean_depth, double p_ref, double p_del,
+                                      double frac_dropout, double frac_deep) {
+    H_CHECK(h);
+    BOSS_CUDA(cudaMemsetAsync(h->d_cov_total, 0, sizeof(unsigned long long) * h->n_contigs_total, h->stream));
+    for (const auto& S : h->segs) {
+        unsigned grid = (unsigned)std::min<int64_t>(ceil_div(S.len, 256), 148 * 32);
+        k_synth_coverage<<<grid, 256, 0, h->stream>>>(S, h->nb, h->P, h->d_ref, h->d_cov, h->d_cov_total, seed, mean_depth, p_ref, p_del,
+                                                      frac_dropout, frac_deep);
+        BOSS_KERNEL_CHECK();
+    }
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}

@@ -1,0 +1,173 @@
+// common.cuh — handle layout, error plumbing and small device helpers for libbossgpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bossgpu.h"
+
+namespace boss {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: no exception crosses the C ABI
+// ------------------------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+
+inline int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define BOSS_CUDA(expr)                                                                            \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::boss::fail(BOSSGPU_ECUDA, "%s failed: %s (%s:%d)", #expr,                     \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    } while (0)
+
+#define BOSS_KERNEL_CHECK() BOSS_CUDA(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+constexpr int      BIN       = BOSSGPU_BIN;
+constexpr int      BUCKET    = BOSSGPU_BUCKET;
+constexpr int      FREEZE    = BOSSGPU_FREEZE;
+constexpr int      NPAT      = BOSSGPU_N_PATTERNS;
+constexpr int      HBINS     = BOSSGPU_HIST_BINS;
+constexpr int      NSTEPS    = BOSSGPU_N_STEPS;
+constexpr int      TILE      = 2000;          // sites per CTA in the score+bin pass: 20 bins, 1/10 bucket
+constexpr int      TILE_THREADS = 512;        // 500 active threads x 4 sites
+constexpr int64_t  SITE_ALIGN = 256;          // segment starts on the padded site axis
+constexpr double   TINY      = 2.2250738585072014e-308;   // np.finfo(float).tiny (sequences.py:430)
+
+// per-segment geometry, device-visible
+struct SegDev {
+    int32_t contig;         // global index in contigs_filt order
+    int32_t is_tail;        // segment contains the contig's last site
+    int64_t contig_len;
+    int64_t start;          // first site within the contig (multiple of BUCKET)
+    int64_t len;            // sites
+    int64_t site_off;       // offset on the padded site axis
+    int64_t n_bins;         // bins owned (tail: includes the L//100 + 1 - th bin)
+    int64_t ds_off;         // index of local bin 0 in the scores_ds arrays (after the left halo)
+    int32_t halo_l, halo_r; // halo capacity available in scores_ds on each side
+    int64_t row_off;        // merged-row index of local bin 0, relative to the shard's first merged row
+    int64_t n_srows;        // strategy rows owned
+    int64_t srow_off;       // strategy-row offset within the shard
+    int64_t n_full_buckets; // complete 20 kb buckets in this segment
+    int64_t n_sw;           // bucket switch entries owned (tail: n_full_buckets + 1)
+    int64_t sw_off;         // offset into bucket arrays
+    int64_t tile_off;       // first tile id of this segment
+    int64_t n_tiles;
+};
+
+// device-side scalars shared between kernels of one update
+struct UpdateDev {
+    unsigned long long norm_bits;    // max benefit as raw double bits (non-negative => order preserving)
+    int32_t  switched_on;
+    int32_t  strat_size;
+    double   threshold;
+    double   normaliser;
+    double   ubar0;
+    double   fhat_sum;
+    double   fhat_scale;             // 1 / fhat_sum (or 1 when the sum is 0)
+    unsigned long long n_nonzero;
+    unsigned long long n_dropout;
+    unsigned long long n_accept[2];
+    unsigned long long fsum_hi, fsum_lo;   // exact limbs of sum(fhat_exp)
+    int32_t  error;                  // BOSSGPU_E* raised on the device
+    int32_t  empty;
+};
+
+struct Timers {
+    cudaEvent_t ev[16];
+};
+
+}  // namespace boss
+
+struct bossgpu_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nb = 1;
+    int len_g = 5;
+    int n_seg = 0;
+    int n_contigs_total = 0;
+    int halo_bins = 0;
+    int64_t n_sites_total = 0;
+    int64_t n_windows_total = 0;
+    // derived global geometry
+    int64_t M_rows = 0;        // sum over contigs of L//100 + 1   (rows of the merged benefit array)
+    int64_t target_rows = 0;   // n_sites_total // 100             (core.py:179)
+    int64_t Tf_rows = 0;       // sum(L) // 100                    (readstartdist.py:29)
+    int64_t R0 = 0;            // first merged row of this shard
+    int64_t D0 = 0;            // first strategy row (distribution axis) of this shard
+    int fhat_shift = 55;
+    // shard totals
+    int64_t P = 0;             // padded sites
+    int64_t n_tiles = 0;
+    int64_t ds_len = 0;        // scores_ds slots incl. halos
+    int64_t n_rows = 0;        // merged rows owned
+    int64_t n_srows = 0;       // strategy rows owned
+    int64_t n_sw = 0;          // bucket switch entries owned
+    std::vector<boss::SegDev> segs;
+    std::vector<int64_t> contig_len_all;
+    // device memory
+    boss::SegDev* d_segs = nullptr;
+    int64_t*  d_tile_start = nullptr;   // [n_seg+1]
+    int64_t*  d_row_start = nullptr;    // [n_seg+1]
+    int64_t*  d_srow_start = nullptr;   // [n_seg+1]
+    uint8_t*  d_ref = nullptr;          // [P]
+    uint16_t* d_cov = nullptr;          // [nb][5][P]
+    uint32_t* d_rowflag = nullptr;      // [P] (nb > 1 only)
+    double*   d_table = nullptr;        // [NPAT][4] scores
+    double*   d_etable = nullptr;       // [NPAT][4] entropies
+    double*   d_phi = nullptr;          // [5][len_g]
+    double*   d_priors = nullptr;       // [4][len_g]
+    double*   d_phi_pow = nullptr;      // [5][len_g][30]
+    double    score0 = 0, ent0 = 0;
+    unsigned long long* d_cov_total = nullptr;   // [n_contigs_total]
+    int32_t*  d_drop_thr = nullptr;              // [n_contigs_total]  -1 = dropout rule inactive
+    double*   d_ds = nullptr;                    // [nb][ds_len]
+    double2*  d_benefit = nullptr;               // [nb][n_rows]  (.x forward, .y reverse)
+    double2*  d_smu = nullptr;                   // debug
+    double2*  d_expected = nullptr;              // debug
+    unsigned long long* d_bucket_sum = nullptr;  // [n_sw][nb]
+    uint8_t*  d_bucket_sw = nullptr;             // [n_sw][nb]
+    double*   d_fhat_w = nullptr;                // [n_windows_total][2]
+    unsigned long long* d_hist = nullptr;        // [3*HBINS + 4]
+    uint8_t*  d_strat = nullptr;                 // [n_srows][2][nb]
+    boss::UpdateDev* d_upd = nullptr;
+    boss::UpdateDev* h_upd = nullptr;            // pinned
+    // staging for ingest
+    void*  stage_h = nullptr;  size_t stage_h_bytes = 0;   // pinned
+    void*  stage_d = nullptr;  size_t stage_d_bytes = 0;
+    void*  scratch_d = nullptr; size_t scratch_d_bytes = 0;
+    int32_t* d_ingest_err = nullptr;
+    int32_t* h_ingest_err = nullptr;
+    // timing
+    cudaEvent_t ev[2 * BOSSGPU_N_TIMERS];
+    float ms[BOSSGPU_N_TIMERS] = {0};
+    bool  ev_valid[BOSSGPU_N_TIMERS] = {false};
+    int64_t launches = 0;
+    int phase_done = -1;
+    // multi-shard exchange state (bossgpu_set_shards)
+    int n_shards = 1, shard_index = 0;
+    std::vector<int64_t> shard_row_start;
+    int64_t mask_stride = 0;
+    uint8_t* d_mask_all = nullptr;           // [n_shards][mask_stride] packed masks of every shard's merged rows
+    int64_t* d_shard_row_start = nullptr;    // [n_shards+1]
+    double*  d_halo = nullptr;               // [send L | send R | recv L | recv R] x halo_bins x nb
+    bool have_fhat = false;
+    bool debug_bufs = false;
+    boss::UpdateDev last;
+};

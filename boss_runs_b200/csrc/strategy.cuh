@@ -1,0 +1,384 @@
+// strategy.cuh — benefit smoothing on the binned scores and strategy derivation.
+//
+// Replaces Contig.calc_smu / calc_u (boss/runs/reference.py:215-269; bn.move_sum box sums),
+// ReadStartDist._expand_fhat (boss/runs/readstartdist.py:121-152), Scoring.merge_benefit +
+// adjust_length (boss/runs/sequences.py:553-560, boss/utils.py:206-226), Scoring.find_strat_thread
+// (sequences.py:566-649) and BossRuns._distribute_strategy (boss/runs/core.py:125-155).
+//
+// Axes.  "merged row" r: row of the concatenated per-contig benefit arrays (L_c//100 + 1 rows per
+// contig).  "strategy row" d: row of the concatenated Contig.strat arrays (L_c//100 rows per contig).
+// Upstream slices the merged mask with strategy-row offsets (core.py:141,155), so strategy row d is
+// simply merged row d (parity quirk Q2) — contig k's mask is shifted by k bins.
+//
+// Determinism: every cross-thread floating-point sum that feeds the threshold is accumulated in exact
+// integer limbs (value * 2^shift split into a 64-bit integer part and 32 fractional bits), so the
+// histogram, ubar0 and the F-hat normaliser do not depend on thread order, grid size or shard count.
+#pragma once
+#include "common.cuh"
+#include "score_pass.cuh"
+
+namespace boss {
+
+constexpr int SM_TILE = 256;   // output bins per CTA in the smoothing kernel
+
+struct SmoothArgs {
+    const SegDev* segs;
+    const int64_t* row_start;     // [n_seg+1] merged rows (local)
+    int n_seg, nb;
+    const double* ds;
+    int64_t ds_len;
+    double2* benefit;             // [nb][n_rows]
+    double2* smu;                 // optional
+    double2* expected;            // optional
+    int64_t n_rows;
+    int32_t w[NSTEPS];            // non-decreasing
+    double mult[NSTEPS];
+    int32_t wmax;                 // max(w[9], 4)
+    int64_t R0, target_rows;      // rows >= target are cut by adjust_length (core.py:179-181)
+    UpdateDev* upd;
+};
+
+// grid = (ceil(bins/SM_TILE) per segment flattened, nb). Dynamic smem: (SM_TILE + 2*(wmax-1)) doubles.
+__global__ void __launch_bounds__(SM_TILE)
+k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
+    extern __shared__ double s_ds[];
+    __shared__ unsigned long long s_max;
+    const int b = blockIdx.y;
+    const int sg = find_segment(sm_tile_start, a.n_seg, blockIdx.x);
+    const SegDev S = a.segs[sg];
+    const int64_t j0 = (blockIdx.x - sm_tile_start[sg]) * SM_TILE;
+    const int halo = a.wmax - 1;
+    const int span = SM_TILE + 2 * halo;
+    const double* src = a.ds + (size_t)b * a.ds_len + S.ds_off;
+    if (threadIdx.x == 0) s_max = 0ull;
+    // stage ds[j0-halo, j0+SM_TILE+halo); outside the contig (or the exchanged halo) the box sums see 0,
+    // which is what min_count=1 partial windows amount to
+    for (int i = threadIdx.x; i < span; i += SM_TILE) {
+        int64_t j = j0 - halo + i;
+        double v = 0.0;
+        if (j >= -(int64_t)S.halo_l && j < S.n_bins + S.halo_r) v = src[j];
+        s_ds[i] = v;
+    }
+    __syncthreads();
+    const int64_t j = j0 + threadIdx.x;
+    unsigned long long mybits = 0ull;
+    if (j < S.n_bins) {
+        const double* c = s_ds + halo + threadIdx.x;
+        // S_mu: 4-bin forward / backward box (reference.py:233-237)
+        const double smu_f = ((c[0] + c[1]) + c[2]) + c[3];
+        const double smu_r = ((c[0] + c[-1]) + c[-2]) + c[-3];
+        // staircase: sum_i mult_i * box_{w_i}; the boxes are nested, so one running sum per strand
+        double run_f = 0.0, run_r = 0.0, eb_f = 0.0, eb_r = 0.0;
+        int k = 0;
+#pragma unroll 1
+        for (int i = 0; i < NSTEPS; ++i) {
+            const int wi = a.w[i];
+            for (; k < wi; ++k) { run_f += c[k]; run_r += c[-k]; }
+            eb_f += run_f * a.mult[i];
+            eb_r += run_r * a.mult[i];
+        }
+        double ad_f = eb_f - smu_f, ad_r = eb_r - smu_r;
+        if (ad_f < 0.0) ad_f = 0.0;                   // reference.py:267-269
+        if (ad_r < 0.0) ad_r = 0.0;
+        const size_t o = (size_t)b * a.n_rows + S.row_off + j;
+        a.benefit[o] = make_double2(ad_f, ad_r);
+        if (a.smu) a.smu[o] = make_double2(smu_f, smu_r);
+        if (a.expected) a.expected[o] = make_double2(eb_f, eb_r);
+        if (a.R0 + S.row_off + j < a.target_rows) {
+            // non-negative doubles order like their bit patterns; NaN would sort above everything
+            unsigned long long bf = (unsigned long long)__double_as_longlong(ad_f);
+            unsigned long long br = (unsigned long long)__double_as_longlong(ad_r);
+            mybits = bf > br ? bf : br;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xFFFFFFFFu, mybits, o);
+        mybits = other > mybits ? other : mybits;
+    }
+    if ((threadIdx.x & 31) == 0 && mybits) atomicMax(&s_max, mybits);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(&a.upd->norm_bits, s_max);
+}
+
+// ---- exact limb arithmetic ---------------------------------------------------------------------------
+// v >= 0 and v < 2^63: hi = floor(v), lo = floor(frac(v) * 2^32)
+__device__ __forceinline__ void to_limbs(double v, unsigned long long& hi, unsigned long long& lo) {
+    hi = (unsigned long long)v;
+    lo = (unsigned long long)((v - (double)hi) * 4294967296.0);
+}
+__host__ __device__ inline double from_limbs(unsigned long long hi, unsigned long long lo, int shift) {
+    // hi + lo*2^-32, scaled back by 2^-shift
+    double v = (double)hi + (double)lo * (1.0 / 4294967296.0);
+    return ldexp(v, -shift);
+}
+
+// F-hat geometry (all global): W windows, expanded x20, tail-fixed to Tf rows (readstartdist.py:129-140),
+// then tail-fixed again to `target` rows by adjust_length (core.py:184-185)
+struct FhatGeom {
+    int64_t W, Tf, target;
+};
+__device__ __forceinline__ int64_t fhat_window_of_row(const FhatGeom& g, int64_t r) {
+    if (r >= g.Tf) r -= (g.target - g.Tf);              // appended copy of the last target-Tf rows
+    const int64_t e = 20 * g.W;
+    if (r >= e) r -= (g.Tf - e);                        // appended copy of the last Tf-20W rows
+    return r / 20;
+}
+
+// exact sum of the expanded, tail-fixed F-hat (before normalisation): one thread per window
+__global__ void k_fhat_sum(FhatGeom g, const double* __restrict__ fw, int shift, UpdateDev* upd) {
+    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long hi = 0, lo = 0;
+    if (w < g.W) {
+        const int64_t e = 20 * g.W;
+        const int64_t lim = g.Tf < e ? g.Tf : e;
+        // rows of the plain expansion that survive truncation
+        int64_t m = 0;
+        int64_t a0 = 20 * w, a1 = 20 * w + 20;
+        if (a1 > lim) a1 = lim;
+        if (a1 > a0) m += a1 - a0;
+        // rows appended from the tail [e-d, e)
+        if (g.Tf > e) {
+            int64_t d = g.Tf - e;
+            int64_t s0 = e - d > 20 * w ? e - d : 20 * w, s1 = 20 * w + 20;
+            if (s1 > s0) m += s1 - s0;
+        }
+        if (m > 0) {
+            for (int s = 0; s < 2; ++s) {
+                unsigned long long h, l;
+                to_limbs(ldexp(fw[2 * w + s], shift), h, l);
+                hi += h * (unsigned long long)m;
+                lo += l * (unsigned long long)m;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        hi += __shfl_down_sync(0xFFFFFFFFu, hi, o);
+        lo += __shfl_down_sync(0xFFFFFFFFu, lo, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (hi | lo)) {
+        atomicAdd(&upd->fsum_hi, hi);
+        atomicAdd(&upd->fsum_lo, lo);
+    }
+}
+
+__global__ void k_fhat_finish(int shift, UpdateDev* upd) {
+    double s = from_limbs(upd->fsum_hi, upd->fsum_lo, shift);
+    upd->fhat_sum = s;
+    upd->fhat_scale = s != 0.0 ? 1.0 / s : 1.0;        // readstartdist.py:145-150, on_target = 1
+}
+
+// ---- exponent histogram (sequences.py:584-624) -----------------------------------------------------------
+struct HistArgs {
+    const double2* benefit;       // [nb][n_rows]
+    int64_t n_rows;               // merged rows owned by this shard
+    int nb;
+    int64_t R0, M, target;        // global: first row here, total merged rows, rows after adjust_length
+    FhatGeom fg;
+    const double* fw;             // [W][2]
+    int shift;                    // limbs hold fhat * 2^shift
+    unsigned long long* hist;     // [3*HBINS + 4]: counts | hi | lo | ubar_hi, ubar_lo, n_nonzero, -
+    UpdateDev* upd;
+};
+
+__device__ __forceinline__ int abs_frexp_exponent(double x) {
+    // |e| with x = m * 2^e, 0.5 <= m < 1 (np.frexp + np.abs, sequences.py:590-593), x > 0 finite
+    int e;
+    frexp(x, &e);
+    return e < 0 ? -e : e;
+}
+
+__global__ void __launch_bounds__(256)
+k_hist(HistArgs a) {
+    __shared__ unsigned s_cnt[HBINS];
+    __shared__ unsigned long long s_hi[HBINS];
+    __shared__ unsigned long long s_lo[HBINS];
+    __shared__ unsigned long long s_u[3];
+    for (int i = threadIdx.x; i < HBINS; i += blockDim.x) { s_cnt[i] = 0; s_hi[i] = 0; s_lo[i] = 0; }
+    if (threadIdx.x < 3) s_u[threadIdx.x] = 0;
+    __syncthreads();
+
+    const double norm = __longlong_as_double((long long)a.upd->norm_bits);
+    const double scale = a.upd->fhat_scale;
+    int norm_e;
+    frexp(norm, &norm_e);                       // norm < 2^norm_e  =>  fhat*b*2^(shift-norm_e) < fhat*2^shift
+    const int b = blockIdx.y;
+    const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail
+    unsigned long long u_hi = 0, u_lo = 0, nnz = 0;
+
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = a.R0 + i;
+        const double2 v = a.benefit[(size_t)b * a.n_rows + i];
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            int64_t rr = r;
+            if (rep == 0) { if (r >= a.target) continue; }
+            else { if (!(extra > 0 && r >= a.M - extra)) continue; rr = r + extra; }
+            const int64_t win = fhat_window_of_row(a.fg, rr);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const double x = s == 0 ? v.x : v.y;
+                if (x == 0.0) continue;                                   // np.nonzero (sequences.py:585)
+                const double f = a.fw[2 * win + s] * scale;               // np.multiply(fhat_exp, normalizer)
+                const int e = abs_frexp_exponent(x / norm);
+                unsigned long long h, l;
+                to_limbs(ldexp(f, a.shift), h, l);
+                atomicAdd(&s_cnt[e], 1u);
+                atomicAdd(&s_hi[e], h);
+                atomicAdd(&s_lo[e], l);
+                to_limbs(ldexp(f * x, a.shift - norm_e), h, l);           // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
+                u_hi += h; u_lo += l; nnz++;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        u_hi += __shfl_down_sync(0xFFFFFFFFu, u_hi, o);
+        u_lo += __shfl_down_sync(0xFFFFFFFFu, u_lo, o);
+        nnz += __shfl_down_sync(0xFFFFFFFFu, nnz, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_u[0], u_hi); atomicAdd(&s_u[1], u_lo); atomicAdd(&s_u[2], nnz); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HBINS; i += blockDim.x) {
+        if (s_cnt[i]) {
+            atomicAdd(&a.hist[i], (unsigned long long)s_cnt[i]);
+            atomicAdd(&a.hist[HBINS + i], s_hi[i]);
+            atomicAdd(&a.hist[2 * HBINS + i], s_lo[i]);
+        }
+    }
+    if (threadIdx.x < 3 && s_u[threadIdx.x]) atomicAdd(&a.hist[3 * HBINS + threadIdx.x], s_u[threadIdx.x]);
+}
+
+// ---- threshold from the histogram: two cumulative sums and an argmax (sequences.py:607-646) ----------------
+// One thread: at most 1076 occupied bins, and the cumulative sums are sequential by definition.
+__global__ void k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, UpdateDev* upd) {
+    __shared__ int s_exp[HBINS];
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double norm = __longlong_as_double((long long)upd->norm_bits);
+    upd->normaliser = norm;
+    upd->n_nonzero = hist[3 * HBINS + 2];
+    if (upd->norm_bits == 0ull || hist[3 * HBINS + 2] == 0ull) {       // np.max of an empty array upstream
+        upd->empty = 1;
+        upd->threshold = 0.0;
+        upd->strat_size = 0;
+        return;
+    }
+    int norm_e;
+    frexp(norm, &norm_e);
+    const double ubar0 = from_limbs(hist[3 * HBINS], hist[3 * HBINS + 1], shift - norm_e);
+    upd->ubar0 = ubar0;
+    const double tbar0 = 3.0 + 3.0 + 4.0;                               // alpha + rho + mu in bins (sequences.py:578-580,630)
+    double cs_u = 0.0, cs_t = 0.0, best = 0.0;
+    int best_i = -1, n_occ = 0;
+    for (int e = 0; e < HBINS; ++e) {
+        const unsigned long long cnt = hist[e];
+        if (!cnt) continue;                                             // np.nonzero(bincounts) (sequences.py:607)
+        s_exp[n_occ] = e;
+        const double counts = (double)(long long)cnt;
+        const double f_grid = from_limbs(hist[HBINS + e], hist[2 * HBINS + e], shift);
+        const double f_mean = f_grid / counts;
+        const double bin = ldexp(1.0, -e) * norm;                       // np.power(2.0, -e) * normaliser
+        cs_u += (bin * f_mean) * counts;                                // np.cumsum(benefit_bin * f_grid_mean * counts)
+        cs_t += (tc * counts) * f_mean;                                 // np.cumsum(tc * counts * f_grid_mean)
+        const double peak = (cs_u + ubar0) / (cs_t + tbar0);
+        // np.argmax: first maximum, and the first NaN beats everything
+        const bool best_nan = best != best;
+        if (best_i < 0 || (!best_nan && (peak > best || peak != peak))) { best = peak; best_i = n_occ; }
+        ++n_occ;
+    }
+    // threshold = bin[argmax + 1], or the last bin when argmax is the last (sequences.py:643-646)
+    const int k = best_i + 1;
+    const int e_thr = k < n_occ ? s_exp[k] : s_exp[n_occ - 1];
+    upd->strat_size = k;
+    upd->threshold = ldexp(1.0, -e_thr) * norm;
+}
+
+// ---- mask + bucket-gated distribution (sequences.py:648, core.py:125-155) ---------------------------------
+struct DistArgs {
+    const SegDev* segs;
+    const int64_t* srow_start;    // [n_seg+1]
+    int n_seg, nb;
+    const double2* benefit;       // [nb][n_rows], local merged rows
+    int64_t n_rows;
+    int64_t R0, D0;
+    const uint8_t* merged_mask;   // multi-shard: [n_shards][mask_stride] packed masks, bit (i*2+s)*nb+b for the
+                                  // shard-local merged row i; NULL: single shard, benefit is compared directly
+    const int64_t* shard_row_start;
+    int n_shards;
+    int64_t mask_stride;
+    const uint8_t* bucket_sw;     // [n_sw][nb]
+    uint8_t* strat;               // [n_srows][2][nb]
+    int64_t n_srows;
+    const UpdateDev* upd;
+    unsigned long long* n_accept; // [2]
+};
+
+__global__ void __launch_bounds__(256)
+k_distribute(DistArgs a) {
+    const int64_t total = a.n_srows * 2 * a.nb;
+    const double thr = a.upd->threshold;
+    unsigned acc0 = 0, acc1 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i % a.nb);
+        const int s = (int)((i / a.nb) & 1);
+        const int64_t dl = i / (2 * a.nb);                 // local strategy row
+        const int sg = find_segment(a.srow_start, a.n_seg, dl);
+        const SegDev S = a.segs[sg];
+        const int64_t j = dl - S.srow_off;                 // row within the segment
+        uint8_t cur = a.strat[i];
+        if (a.bucket_sw[(size_t)(S.sw_off + j / (BUCKET / BIN)) * a.nb + b]) {
+            const int64_t r = a.D0 + dl;                   // Q2: strategy row d reads merged row d
+            bool m;
+            if (a.merged_mask) {
+                const int sh = find_segment(a.shard_row_start, a.n_shards, r);
+                const int64_t bit = ((r - a.shard_row_start[sh]) * 2 + s) * a.nb + b;
+                m = (a.merged_mask[(size_t)sh * a.mask_stride + (bit >> 3)] >> (bit & 7)) & 1;
+            } else {
+                const double2 v = a.benefit[(size_t)b * a.n_rows + (r - a.R0)];
+                m = (s == 0 ? v.x : v.y) >= thr;
+            }
+            cur = m ? 1 : 0;
+            a.strat[i] = cur;
+        }
+        if (s == 0) acc0 += cur; else acc1 += cur;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_down_sync(0xFFFFFFFFu, acc0, o);
+        acc1 += __shfl_down_sync(0xFFFFFFFFu, acc1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (acc0) atomicAdd(&a.n_accept[0], (unsigned long long)acc0);
+        if (acc1) atomicAdd(&a.n_accept[1], (unsigned long long)acc1);
+    }
+}
+
+// packed mask of this shard's merged rows: bit (i*2+s)*nb+b for local row i (rows cut by adjust_length are 0)
+__global__ void k_pack_mask(const double2* __restrict__ benefit, int64_t n_rows, int nb, int64_t R0, int64_t target,
+                            const UpdateDev* upd, uint8_t* __restrict__ out_bits, int64_t n_bits) {
+    int64_t byte = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (byte * 8 >= n_bits) return;
+    const double thr = upd->threshold;
+    unsigned v = 0;
+    for (int k = 0; k < 8; ++k) {
+        int64_t bit = byte * 8 + k;
+        if (bit >= n_bits) break;
+        int b = (int)(bit % nb);
+        int s = (int)((bit / nb) & 1);
+        int64_t i = bit / (2 * nb);
+        if (R0 + i >= target) continue;
+        double2 x = benefit[(size_t)b * n_rows + i];
+        if ((s == 0 ? x.x : x.y) >= thr) v |= 1u << k;
+    }
+    out_bits[byte] = (uint8_t)v;
+}
+
+__global__ void k_pack_strat(const uint8_t* __restrict__ strat, int64_t n, uint8_t* __restrict__ out) {
+    int64_t byte = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (byte * 8 >= n) return;
+    unsigned v = 0;
+    for (int k = 0; k < 8; ++k) {
+        int64_t i = byte * 8 + k;
+        if (i < n && strat[i]) v |= 1u << k;
+    }
+    out[byte] = (uint8_t)v;
+}
+
+}  // namespace boss

@@ -1,0 +1,294 @@
+"""`Engine`: thin object wrapper over one libbossgpu handle (one GPU shard of the genome).
+
+All numerics run in the CUDA kernels of libbossgpu.so; this file only marshals NumPy arrays across the
+C ABI (include/bossgpu.h). The reference-facing classes in `boss_runs_b200.runs` sit on top of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import BIN, BUCKET, RSD_WINDOW, HIST_BINS, N_PATTERNS, N_STEPS, N_TIMERS, check, ptr, as_c
+from .priors import Priors, Scoring
+
+
+@dataclass
+class SegmentSpec:
+    contig: int        # index in contigs_filt order
+    start: int
+    length: int
+
+
+@dataclass
+class UpdateOutcome:
+    switched_on: bool
+    threshold: float
+    strat_size: int
+    normaliser: float
+    ubar0: float
+    fhat_sum: float
+    n_nonzero: int
+    n_dropout: int
+    n_accept: tuple[int, int]
+
+
+def staircase_mult() -> np.ndarray:
+    """Weights of the ten read-length steps, computed with upstream's own expression (reference.py:253)."""
+    return np.arange(0.05, 1, 0.1)[::-1].copy()
+
+
+class Engine:
+    """One shard: an ordered list of contig segments with their counters, switches and strategy on a GPU."""
+
+    def __init__(self, contig_lengths, ref_codes, n_barcodes: int = 1, ploidy: int = 1, n_sites_total: int | None = None,
+                 device: int = 0, stream: int | None = None, segments: list[SegmentSpec] | None = None,
+                 halo_bins: int = 0):
+        """
+        :param contig_lengths: lengths of ALL non-rejected contigs, in contigs_filt order
+        :param ref_codes: per segment (or per contig when `segments` is None) uint8 arrays of seq_int (0..3)
+        :param n_sites_total: `Reference.n_sites` (adds 4 per reject ref); defaults to sum(contig_lengths)
+        :param stream: raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = default stream
+        """
+        self.lib = _lib.load()
+        self.contig_lengths = np.asarray(contig_lengths, dtype=np.int64)
+        self.nb = int(n_barcodes)
+        self.ploidy = int(ploidy)
+        if segments is None:
+            segments = [SegmentSpec(k, 0, int(L)) for k, L in enumerate(self.contig_lengths)]
+        self.segments = segments
+        if len(ref_codes) != len(segments):
+            raise ValueError("one reference array per segment expected")
+        for seg, rc in zip(segments, ref_codes):
+            assert len(rc) == seg.length, "reference array length does not match its segment"
+        self.n_sites_total = int(n_sites_total if n_sites_total is not None else self.contig_lengths.sum())
+        self.n_windows_total = int(sum(int(L / RSD_WINDOW) for L in self.contig_lengths))
+        # scoring constants: model of the configured ploidy; unobserved-site constant of the HAPLOID model (Q5)
+        self.model = Priors(ploidy=self.ploidy)
+        hap = Scoring(ploidy=1)
+        self.score0_contig, self.ent0_contig = float(hap.score0[0]), float(hap.ent0[0])
+
+        segs = (_lib.Segment * len(segments))()
+        for i, s in enumerate(segments):
+            segs[i].contig, segs[i].contig_len = s.contig, int(self.contig_lengths[s.contig])
+            segs[i].start, segs[i].len = s.start, s.length
+        ref_all = as_c(np.concatenate([np.asarray(r, dtype=np.uint8) for r in ref_codes]), np.uint8)
+        phi = as_c(self.model.phi, np.float64)
+        pri = as_c(self.model.priors, np.float64)
+        ppow = as_c(self.model.phi_stored[:, :, :_lib.FREEZE], np.float64)
+        cfg = _lib.Config()
+        cfg.abi_version, cfg.device, cfg.stream = _lib.ABI_VERSION, int(device), stream
+        cfg.n_segments, cfg.n_barcodes = len(segments), self.nb
+        cfg.segments, cfg.ref_codes = segs, ptr(ref_all)
+        cfg.n_contigs_total, cfg.halo_bins = len(self.contig_lengths), int(halo_bins)
+        cfg.contig_len_all = ptr(self.contig_lengths)
+        cfg.n_sites_total, cfg.n_windows_total = self.n_sites_total, self.n_windows_total
+        cfg.len_g = self.model.len_g
+        cfg.phi, cfg.priors, cfg.phi_pow = ptr(phi), ptr(pri), ptr(ppow)
+        cfg.score0_contig, cfg.entropy0_contig = self.score0_contig, self.ent0_contig
+        h = C.c_void_p()
+        check(self.lib.bossgpu_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.halo_bins = int(halo_bins)
+        self._mult = staircase_mult()
+
+    # -- lifetime --------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.bossgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self) -> None:
+        check(self.lib.bossgpu_synchronize(self.h))
+
+    # -- geometry --------------------------------------------------------------------------------
+    def seg_len(self, seg: int) -> int:
+        return self.segments[seg].length
+
+    def seg_is_tail(self, seg: int) -> bool:
+        s = self.segments[seg]
+        return s.start + s.length == int(self.contig_lengths[s.contig])
+
+    def seg_bins(self, seg: int) -> int:
+        s = self.segments[seg]
+        L = int(self.contig_lengths[s.contig])
+        return (L // BIN + 1 - s.start // BIN) if self.seg_is_tail(seg) else s.length // BIN
+
+    def seg_strat_rows(self, seg: int) -> int:
+        return int(self.lib.bossgpu_strat_rows(self.h, seg))
+
+    def seg_switches(self, seg: int) -> int:
+        s = self.segments[seg]
+        L = int(self.contig_lengths[s.contig])
+        return (L // BUCKET - s.start // BUCKET + 1) if self.seg_is_tail(seg) else s.length // BUCKET
+
+    # -- coverage update -------------------------------------------------------------------------
+    def ingest_packed(self, seg, tstart, barcode, cig_off, cigar, base_off, bases, ascii_bases: bool = False,
+                      contig_cov_add=None) -> None:
+        seg = as_c(seg, np.int32); tstart = as_c(tstart, np.int64); barcode = as_c(barcode, np.int32)
+        cig_off = as_c(cig_off, np.int64); cigar = as_c(cigar, np.uint32)
+        base_off = as_c(base_off, np.int64); bases = as_c(bases, np.uint8)
+        n = len(seg)
+        assert len(tstart) == n and len(barcode) == n and len(cig_off) == n + 1 and len(base_off) == n + 1
+        add = None if contig_cov_add is None else as_c(contig_cov_add, np.int64)
+        check(self.lib.bossgpu_ingest_packed(self.h, n, ptr(seg), ptr(tstart), ptr(barcode), ptr(cig_off), ptr(cigar),
+                                             ptr(base_off), ptr(bases), int(ascii_bases), 0, ptr(add)))
+
+    def ingest_packed_device(self, n, seg, tstart, barcode, cig_off, cigar, base_off, bases, ascii_bases=False) -> None:
+        """Same with raw device pointers (ints); nothing is copied and the call does not synchronise."""
+        check(self.lib.bossgpu_ingest_packed(self.h, int(n), seg, tstart, barcode, cig_off, cigar, base_off, bases,
+                                             int(ascii_bases), 1, None))
+
+    def ingest_records(self, contig, tstart, tend, barcode, rev, cig_off, cigar_text: bytes, seq_off, seq_text: bytes,
+                       n_threads: int = 0) -> None:
+        contig = as_c(contig, np.int32); tstart = as_c(tstart, np.int64); tend = as_c(tend, np.int64)
+        barcode = as_c(barcode, np.int32); rev = as_c(rev, np.uint8)
+        cig_off = as_c(cig_off, np.int64); seq_off = as_c(seq_off, np.int64)
+        n = len(contig)
+        assert len(cig_off) == n + 1 and len(seq_off) == n + 1
+        assert cig_off[-1] == len(cigar_text) and seq_off[-1] == len(seq_text)
+        check(self.lib.bossgpu_ingest_records(self.h, n, ptr(contig), ptr(tstart), ptr(tend), ptr(barcode), ptr(rev),
+                                              ptr(cig_off), C.cast(C.c_char_p(cigar_text), C.c_void_p), ptr(seq_off),
+                                              C.cast(C.c_char_p(seq_text), C.c_void_p), int(n_threads)))
+
+    # -- strategy update -------------------------------------------------------------------------
+    def _params(self, approx_ccl, time_cost, bucket_threshold, fhat_windows, debug) -> tuple:
+        p = _lib.UpdateParams()
+        w = np.asarray(approx_ccl) // BIN                       # reference.py:252
+        assert w.shape == (N_STEPS,)
+        for i in range(N_STEPS):
+            p.w[i] = int(w[i])
+            p.mult[i] = float(self._mult[i])
+        p.tc = float(time_cost // BIN)                          # sequences.py:581
+        p.bucket_threshold = float(bucket_threshold)
+        keep = None
+        if fhat_windows is not None:
+            keep = as_c(fhat_windows, np.float64)
+            assert keep.shape == (self.n_windows_total, 2), "fhat_windows must be [sum int(L/2000)][2]"
+            p.fhat_windows = keep.ctypes.data
+        p.write_debug = int(bool(debug))
+        return p, keep
+
+    @staticmethod
+    def _outcome(r) -> UpdateOutcome:
+        return UpdateOutcome(bool(r.switched_on), r.threshold, r.strat_size, r.normaliser, r.ubar0, r.fhat_sum,
+                             r.n_nonzero, r.n_dropout, (r.n_accept[0], r.n_accept[1]))
+
+    def update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None, debug: bool = False) -> UpdateOutcome:
+        p, _keep = self._params(approx_ccl, time_cost, bucket_threshold, fhat_windows, debug)
+        r = _lib.UpdateResult()
+        check(self.lib.bossgpu_update(self.h, C.byref(p), C.byref(r)))
+        return self._outcome(r)
+
+    def update_phase(self, phase: int, params) -> UpdateOutcome | None:
+        r = _lib.UpdateResult()
+        check(self.lib.bossgpu_update_phase(self.h, phase, C.byref(params), C.byref(r)))
+        return self._outcome(r) if phase == 4 else None
+
+    def exchange_buffer(self, which: int) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self.lib.bossgpu_exchange_buffer(self.h, which, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    # -- results / state -------------------------------------------------------------------------
+    def strat(self, seg: int, out: np.ndarray | None = None) -> np.ndarray:
+        """Contig.strat of segment `seg`: bool [rows][2][nb] (reference.py:118)."""
+        rows = self.seg_strat_rows(seg)
+        if out is None:
+            out = np.empty((rows, 2, self.nb), dtype=np.bool_)
+        assert out.shape == (rows, 2, self.nb) and out.dtype == np.bool_ and out.flags.c_contiguous
+        check(self.lib.bossgpu_get_strat(self.h, seg, ptr(out), out.size))
+        return out
+
+    def strat_all(self, out: np.ndarray | None = None) -> np.ndarray:
+        rows = self.seg_strat_rows(-1)
+        if out is None:
+            out = np.empty((rows, 2, self.nb), dtype=np.bool_)
+        check(self.lib.bossgpu_get_strat_all(self.h, ptr(out), out.size))
+        return out
+
+    def strat_packed(self) -> np.ndarray:
+        n = self.seg_strat_rows(-1) * 2 * self.nb
+        out = np.empty((n + 7) // 8, dtype=np.uint8)
+        check(self.lib.bossgpu_get_strat_packed(self.h, ptr(out), out.size))
+        return out
+
+    def coverage(self, seg: int) -> np.ndarray:
+        out = np.empty((self.seg_len(seg), 5, self.nb), dtype=np.uint16)
+        check(self.lib.bossgpu_get_coverage(self.h, seg, ptr(out), out.size))
+        return out
+
+    def set_coverage(self, seg: int, cov: np.ndarray) -> None:
+        cov = as_c(cov, np.uint16)
+        assert cov.shape == (self.seg_len(seg), 5, self.nb)
+        check(self.lib.bossgpu_set_coverage(self.h, seg, ptr(cov), cov.size))
+
+    def scores(self, seg: int, entropy: bool = False):
+        s = np.empty((self.seg_len(seg), self.nb))
+        e = np.empty_like(s) if entropy else None
+        check(self.lib.bossgpu_get_scores(self.h, seg, ptr(s), ptr(e), s.size))
+        return (s, e) if entropy else s
+
+    def scores_ds(self, seg: int) -> np.ndarray:
+        out = np.empty((self.seg_bins(seg), self.nb))
+        check(self.lib.bossgpu_get_scores_ds(self.h, seg, ptr(out), out.size))
+        return out
+
+    def benefit(self, seg: int, debug: bool = False):
+        shape = (self.seg_bins(seg), 2, self.nb)
+        ad = np.empty(shape)
+        if not debug:
+            check(self.lib.bossgpu_get_benefit(self.h, seg, ptr(ad), None, None, ad.size))
+            return ad
+        smu, eb = np.empty(shape), np.empty(shape)
+        check(self.lib.bossgpu_get_benefit(self.h, seg, ptr(ad), ptr(smu), ptr(eb), ad.size))
+        return ad, smu, eb
+
+    def buckets(self, seg: int) -> tuple[np.ndarray, np.ndarray]:
+        sw = np.empty((self.seg_switches(seg), self.nb), dtype=np.bool_)
+        on = np.empty(self.nb, dtype=np.bool_)
+        check(self.lib.bossgpu_get_buckets(self.h, seg, ptr(sw), sw.size, ptr(on)))
+        return sw, on
+
+    def set_buckets(self, seg: int, sw: np.ndarray) -> None:
+        sw = as_c(sw, np.bool_)
+        assert sw.shape == (self.seg_switches(seg), self.nb)
+        check(self.lib.bossgpu_set_buckets(self.h, seg, ptr(sw), sw.size))
+
+    def hist(self) -> tuple[np.ndarray, np.ndarray]:
+        counts = np.empty(HIST_BINS, dtype=np.int64)
+        f_grid = np.empty(HIST_BINS)
+        check(self.lib.bossgpu_get_hist(self.h, ptr(counts), ptr(f_grid)))
+        return counts, f_grid
+
+    def score_table(self) -> tuple[np.ndarray, np.ndarray]:
+        s = np.empty((N_PATTERNS, 4))
+        e = np.empty((N_PATTERNS, 4))
+        check(self.lib.bossgpu_get_score_table(self.h, ptr(s), ptr(e)))
+        return s, e
+
+    def pattern_rank(self, counts) -> int:
+        c = as_c(counts, np.uint16)
+        assert c.shape == (5,)
+        return int(self.lib.bossgpu_pattern_rank(ptr(c)))
+
+    def timing(self) -> dict[str, float]:
+        ms = np.empty(N_TIMERS, dtype=np.float32)
+        check(self.lib.bossgpu_timing(self.h, ptr(ms)))
+        names = ("scatter", "score_bin", "buckets", "smooth", "hist", "threshold", "distribute", "update")
+        return {k: float(v) for k, v in zip(names, ms)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.bossgpu_launch_count(self.h))
+
+    def synth_coverage(self, seed: int = 11, mean_depth: float = 8.0, p_ref: float = 0.90, p_del: float = 0.04,
+                       frac_dropout: float = 0.02, frac_deep: float = 0.01) -> None:
+        check(self.lib.bossgpu_synth_coverage(self.h, seed, mean_depth, p_ref, p_del, frac_dropout, frac_deep))

@@ -1,0 +1,210 @@
+"""Host-side mirrors of the small reference classes that feed the strategy update.
+
+Same names, arguments and error behaviour as upstream so callers (and our parity tests) read like the
+reference's own; the heavy arrays they used to produce now live on the GPU.
+
+  PafLine, parse_PAF, choose_best_mapper .... boss/paf.py:12-74, 640-672, 710-722
+  ReadlengthDist ............................. boss/readlengthdist.py:7-97
+  ReadStartDist .............................. boss/runs/readstartdist.py:11-152 (expansion moved to the GPU)
+  adjust_length, window helpers .............. boss/utils.py:192-226
+"""
+from __future__ import annotations
+
+import logging
+from collections import defaultdict
+from io import StringIO
+from pathlib import Path
+
+import numpy as np
+from scipy.special import betaln
+
+from ._lib import RSD_WINDOW
+
+_PAF_FIELDS = ("qname", "qlen", "qstart", "qend", "strand", "tname", "tlen", "tstart", "tend",
+               "num_matches", "alignment_block_length", "mapq")
+_TAG_TYPES = {"i": int, "A": str, "f": float, "Z": str}
+
+
+def _conv(s: str, typ):
+    try:
+        return typ(s)
+    except ValueError:
+        return s
+
+
+class PafLine:
+    """One PAF alignment: 12 core columns + AS/cg/s1/tp tags (boss/paf.py:18-74)."""
+
+    __slots__ = (*_PAF_FIELDS, "line", "rev", "align_score", "cigar", "s1", "primary", "barcode", "c")
+
+    def __init__(self, line: str, tags: bool = True):
+        self.line = line
+        cols = line.strip().split("\t")
+        for name, raw in zip(_PAF_FIELDS, cols[:12]):
+            setattr(self, name, _conv(raw, int))
+        self.qname, self.tname = str(self.qname), str(self.tname)
+        self.rev = 0 if self.strand == "+" else 1
+        self.c = -1
+        self.barcode = None
+        if tags:
+            parsed = {}
+            for t in cols[12:]:
+                key, typ, val = t.split(":")          # upstream splits on every ':' the same way
+                parsed[key] = _conv(val, _TAG_TYPES[typ])
+            self.align_score = int(parsed.get("AS", 0))
+            self.cigar = parsed.get("cg", None)
+            self.s1 = parsed.get("s1", 0)
+            self.primary = 1 if parsed.get("tp", None) == "P" else 0
+
+
+def parse_PAF(paf_file, min_len: int = 1) -> dict[str, list[PafLine]]:
+    """`Paf.parse_PAF`: path or StringIO -> {qname: [primary records with block length >= min_len]}."""
+    if isinstance(paf_file, str) and Path(paf_file).is_file():
+        fh = open(paf_file, "r")
+    elif isinstance(paf_file, StringIO):
+        fh = paf_file
+    else:
+        print("need file path or StringIO")
+        return dict()
+    out = defaultdict(list)
+    with fh:
+        for rec in fh:
+            p = PafLine(rec)
+            if p.alignment_block_length < min_len or not p.primary:
+                continue
+            out[str(p.qname)].append(p)
+    return out
+
+
+def choose_best_mapper(records: list) -> list:
+    """Last element of an argsort by (mapq, alignment score) (boss/paf.py:710-722)."""
+    keys = np.array([(r.mapq, r.align_score) for r in records], dtype=[("q", int), ("dp", int)])
+    return [records[np.argsort(keys, order=["q", "dp"])[-1]]]
+
+
+def best_record(recs):
+    return recs[0] if len(recs) == 1 else choose_best_mapper(recs)[0]
+
+
+def adjust_length(original_size: int, expanded: np.ndarray) -> np.ndarray:
+    """Pad with a copy of the tail / truncate to `original_size` rows (boss/utils.py:206-226)."""
+    d = original_size - expanded.shape[0]
+    if d > 0:
+        out = np.append(expanded, expanded[-d:], axis=0)
+    elif d < 0:
+        out = expanded[:-abs(d)]
+    else:
+        out = expanded
+    assert out.shape[0] == original_size
+    return out
+
+
+class ReadlengthDist:
+    """Histogram of accepted read lengths -> lambda, time_cost and the 10-step staircase approx_ccl."""
+
+    def __init__(self, mu: int = 400, sd: int = 4000, lam: int = 6000, eta: int = 11):
+        self.sd, self.lam, self.eta, self.mu = sd, lam, eta, mu
+        self.read_lengths = np.zeros(shape=int(1e6), dtype="uint16")
+        x = np.arange(int(lam + 10 * sd), dtype="int")
+        L = np.exp(-((x - lam + 1) ** 2) / (2 * (sd ** 2))) / (sd * np.sqrt(2 * np.pi))
+        L /= sum(L)
+        self.L = L
+        self.approx_ccl = self.ccl_approx_constant()
+
+    def update(self, read_lengths: dict) -> None:
+        lens = np.fromiter(read_lengths.values(), dtype=np.int64, count=len(read_lengths))
+        lens = lens[lens > self.mu * 2]                       # rejected (truncated) reads are ignored
+        lens = np.minimum(lens, int(1e6) - 1)                 # whales count as 1M - 1
+        np.add.at(self.read_lengths, lens, np.uint16(1))      # uint16 counters, as upstream
+        seen = np.nonzero(self.read_lengths)
+        if len(seen[0]) == 0:
+            logging.info("Attempted update of read lengths before observing any reads")
+            return
+        self.lam = np.sum(seen * self.read_lengths[seen]) / np.sum(self.read_lengths[seen])
+        self.longest_read = np.max(np.where(self.read_lengths))
+        self.L = np.copy(self.read_lengths[: self.longest_read + 1]).astype("float64")
+        self.L /= sum(self.L)
+        self.approx_ccl = self.ccl_approx_constant()
+        logging.info(f"rld: {self.approx_ccl}")
+        self.time_cost = self.lam - 400 - 300                 # lambda - mu - rho; absent before the first update
+
+    def ccl_approx_constant(self) -> np.ndarray:
+        ccl = np.zeros(len(self.L) + 1)
+        ccl[0] = 1
+        ccl[1:] = 1 - np.concatenate((self.L[1:].cumsum(), np.ones(1)))
+        ccl[ccl < 1e-6] = 0
+        ccl = np.concatenate((np.trim_zeros(ccl, trim="b"), np.zeros(1)))
+        self.ccl = ccl
+        steps = np.zeros(self.eta - 1, dtype="int32")
+        i = 0
+        for part in range(self.eta - 1):
+            prob = 1 - (part + 0.5) / (self.eta - 1)
+            while (ccl[i] > prob) and (len(ccl) > i):
+                i += 1
+            steps[part] = i
+        return steps
+
+
+class ReadStartDist:
+    """Read-start counts per 2 kb window and strand, and the Bayesian point-mass estimate F-hat.
+
+    `update_f_pointmass()` returns the COMPACT estimate (one row per window); expansion x20, the two tail
+    fixes and the normalisation (readstartdist.py:121-152, core.py:184-185) run on the GPU inside the
+    strategy update. `expand()` reproduces the upstream array on the host for tests and small genomes.
+    """
+
+    def __init__(self, contigs: dict, window_size: int = RSD_WINDOW, alpha: float = 1.0, p0: float = 0.1,
+                 strict: bool = True):
+        self.alpha, self.p0, self.window_size = alpha, p0, window_size
+        self.read_starts = {name: np.zeros(shape=(int(c.length / window_size), 2)) for name, c in contigs.items()}
+        self.total_len = np.sum([a.shape[0] for a in self.read_starts.values()])
+        self.target_size = int(np.sum([c.length for c in contigs.values()]) // 100)
+        self.on_target = 1
+        lendiff = self.target_size - int(self.total_len) * (window_size // 100)
+        if strict:
+            # upstream asserts this inside _expand_fhat (readstartdist.py:131); it fails for references of
+            # more than ~100-200 contigs. strict=False lifts the limit (the GPU expansion handles any tail).
+            assert lendiff < self.window_size
+
+    def merge(self) -> np.ndarray:
+        return np.concatenate(list(self.read_starts.values()))
+
+    def count_read_starts(self, paf_dict: dict) -> None:
+        fwd, rev = defaultdict(list), defaultdict(list)
+        for recs in paf_dict.values():
+            rec = best_record(recs)
+            (rev if rec.rev else fwd)[rec.tname].append(rec.tend if rec.rev else rec.tstart)
+        for name, arr in self.read_starts.items():
+            nw = int(arr.shape[0])
+            span = (0, self.window_size * nw)
+            arr[:, 0] += np.histogram(fwd[name], bins=nw, range=span)[0].astype(dtype="float")
+            arr[:, 1] += np.histogram(rev[name], bins=nw, range=span)[0].astype(dtype="float")
+
+    def update_f_pointmass(self) -> np.ndarray:
+        merged = self.merge()
+        nw = merged.shape[0]
+        fhat = np.zeros(shape=merged.shape)
+        nzi = np.nonzero(merged)
+        nz = merged[nzi]
+        csum = np.sum(nz)
+        fhat[nzi] = np.divide(np.add(self.alpha, nz), 2 * nw * self.alpha + csum)
+        rhs = self.alpha / (2 * nw * self.alpha + csum)
+        beta_num = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha + csum)))
+        beta_denom = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha))) or 1e-20
+        p0_bit = self.p0 / (self.p0 + (1 - self.p0))
+        zero = np.ones(shape=fhat.shape, dtype="bool")
+        zero[nzi] = 0
+        fhat[zero] = (1 - p0_bit * (beta_num / beta_denom)) * rhs
+        return fhat
+
+    def expand(self, fhat_windows: np.ndarray, downsample_window: int = 100) -> np.ndarray:
+        f = np.repeat(fhat_windows, int(self.window_size // downsample_window), axis=0)
+        d = self.target_size - f.shape[0]
+        if d > 0:
+            f = np.append(f, f[-d:], axis=0)
+        elif d < 0:
+            f = f[:-abs(d)]
+        s = np.sum(f)
+        if s != 0:
+            f = np.multiply(f, self.on_target / s)
+        return f

@@ -1,0 +1,336 @@
+"""Reference-facing host API of the B200 strategy update.
+
+Mirrors the operator interface of the reference for this path — `Contig`, `Reference`,
+`CoverageConverter`, `BossRuns` (boss/runs/reference.py, boss/runs/sequences.py:657-794,
+boss/runs/core.py:20-224) — with the same method names, argument meaning and error behaviour, while
+every array operation runs in libbossgpu's CUDA kernels. Mapping (minimap2/mappy), MinKNOW/readfish
+I/O and the simulator's sampling stay on the host and are not part of this module.
+
+Standalone use (no upstream checkout needed)::
+
+    run = BossRuns(contigs={"chr1": "ACGT...", ...}, ploidy=1, bucket_threshold=5)
+    run.rl_dist.update(read_lengths)                      # host, as upstream
+    run.process_batch_runs(paf_dict, seqs)                # convert -> scatter -> read starts -> update
+    run.contigs["chr1"].strat                             # bool (L//100, 2, nb), refreshed by the update
+
+`boss_runs_b200.dropin` wires the same engine underneath the upstream `BossRuns` / `BossRunsSim` classes.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from ._lib import BIN, BUCKET
+from .engine import Engine, UpdateOutcome
+from .hostmodel import ReadlengthDist, ReadStartDist, best_record
+from .priors import Scoring
+
+_SEQ_LUT = np.zeros(256, dtype=np.uint8)
+for _ch, _v in zip("ACGT", range(4)):
+    _SEQ_LUT[ord(_ch)] = _v
+
+
+def seq_to_int(seq: str) -> np.ndarray:
+    """`Contig._seq2int`: ACGT -> 0..3, every other letter -> 0 (reference.py:46-68)."""
+    return _SEQ_LUT[np.frombuffer(seq.upper().encode(), dtype=np.uint8)]
+
+
+@dataclass
+class PackedBatch:
+    """What `CoverageConverter.convert_records` hands to `_effect_increments`: the batch as flat arrays,
+    still as text (the library tokenises CIGARs and reverse-complements in C++ threads)."""
+    contig: np.ndarray      # int32 index into contigs_filt order
+    tstart: np.ndarray      # int64
+    tend: np.ndarray        # int64
+    barcode: np.ndarray     # int32
+    rev: np.ndarray         # uint8
+    cig_off: np.ndarray     # int64 [n+1]
+    cigar_text: bytes
+    seq_off: np.ndarray     # int64 [n+1]
+    seq_text: bytes
+    n_skipped: int = 0      # reads whose target is not a tracked contig
+
+    def __len__(self) -> int:
+        return int(self.contig.shape[0])
+
+
+class CoverageConverter:
+    """Host half of the coverage update (sequences.py:657-739): picks each read's record, slices the
+    aligned part of the read and flattens the batch. CIGAR expansion and counting happen on the GPU."""
+
+    def __init__(self, contig_index: dict[str, int], qt: int = 0):
+        if qt != 0:
+            raise NotImplementedError("upstream fixes the quality threshold at 0 (sequences.py:659)")
+        self.contig_index = contig_index
+        self.qt = qt
+
+    def convert_records(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
+                        barcodes: dict[str, int] | None = None) -> PackedBatch:
+        contig, tstart, tend, bc, rev, cig, sl = [], [], [], [], [], [], []
+        skipped = 0
+        for rid in list(paf_dict.keys()):
+            rec = best_record(paf_dict[rid])
+            k = self.contig_index.get(rec.tname)
+            if k is None:
+                skipped += 1          # upstream collects these under a key nobody reads (core.py:83-86)
+                continue
+            s = seqs[rec.qname]
+            n = len(s)
+            if rec.rev:
+                # upstream slices the reverse complement of the WHOLE string with qlen-based coordinates
+                # (sequences.py:707-711; Q12): rc[a:b] == revcomp(s[n-b:n-a])
+                a, b = rec.qlen - rec.qend, rec.qlen - rec.qstart
+                piece = s[max(n - b, 0): max(n - a, 0)]
+            else:
+                piece = s[rec.qstart: rec.qend]
+            assert rec.cigar is not None
+            contig.append(k)
+            tstart.append(rec.tstart)
+            tend.append(rec.tend)
+            bc.append(0 if rec.barcode is None else rec.barcode)
+            rev.append(1 if rec.rev else 0)
+            cig.append(rec.cigar)
+            sl.append(piece)
+        n = len(contig)
+        cig_off = np.zeros(n + 1, dtype=np.int64)
+        seq_off = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(c) for c in cig], out=cig_off[1:])
+            np.cumsum([len(p) for p in sl], out=seq_off[1:])
+        return PackedBatch(np.asarray(contig, dtype=np.int32), np.asarray(tstart, dtype=np.int64),
+                           np.asarray(tend, dtype=np.int64), np.asarray(bc, dtype=np.int32),
+                           np.asarray(rev, dtype=np.uint8), cig_off, "".join(cig).encode("ascii", "replace"),
+                           seq_off, "".join(sl).encode("ascii", "replace"), skipped)
+
+
+class Contig:
+    """View of one reference sequence. Small state (`strat`, switches) is mirrored on the host after every
+    update; the per-site arrays are fetched from the GPU on access (tests / debugging)."""
+
+    def __init__(self, name: str, seq: str, ploidy: int = 1, rej: bool = False, barcodes: list | None = None):
+        self.name = name.strip().split(" ")[0]
+        self.length = len(seq)
+        self.rej = rej
+        self.barcodes = barcodes
+        self.nbarcodes = len(barcodes) if barcodes is not None else 1
+        self.seq_int = seq_to_int(seq)
+        assert len(set(self.seq_int[:100]) | {0, 1, 2, 3}) == 4
+        self.bucket_size = BUCKET
+        self.bucket_switches = np.zeros(shape=(int(self.length // BUCKET) + 1, self.nbarcodes), dtype="bool")
+        self.switched_on = np.zeros(shape=(self.nbarcodes), dtype="bool")
+        self.scoring = Scoring(ploidy=ploidy)
+        self.len_b = self.scoring.priors.len_b
+        self.score0, self.ent0 = self.scoring.score0, self.scoring.ent0
+        if self.rej:
+            self.strat = np.zeros(dtype="bool", shape=1)
+        else:
+            self.strat = np.ones(dtype="bool", shape=(self.length // BIN, 2, self.nbarcodes))
+        self._engine: Engine | None = None
+        self._seg = -1
+
+    def _bind(self, engine: Engine, seg: int) -> None:
+        self._engine, self._seg = engine, seg
+
+    def _need(self) -> Engine:
+        if self._engine is None:
+            raise RuntimeError("contig is not bound to a GPU engine (reject refs carry no state)")
+        return self._engine
+
+    # per-site / per-bin state lives on the GPU
+    @property
+    def coverage(self) -> np.ndarray:
+        return self._need().coverage(self._seg)
+
+    @property
+    def scores(self) -> np.ndarray:
+        return self._need().scores(self._seg)
+
+    @property
+    def entropy(self) -> np.ndarray:
+        return self._need().scores(self._seg, entropy=True)[1]
+
+    @property
+    def scores_ds(self) -> np.ndarray:
+        return self._need().scores_ds(self._seg)
+
+    @property
+    def additional_benefit(self) -> np.ndarray:
+        return self._need().benefit(self._seg)
+
+    @property
+    def smu(self) -> np.ndarray:
+        return self._need().benefit(self._seg, debug=True)[1]
+
+    @property
+    def expected_benefit(self) -> np.ndarray:
+        return self._need().benefit(self._seg, debug=True)[2]
+
+
+class Reference:
+    """Contig table with upstream's filtering rules (reference.py:274-373): contigs under 1e5 are dropped,
+    `reject_refs` become 4-bp placeholders whose strategy is a single False."""
+
+    def __init__(self, ref: str | None = None, mmi: str | None = None, reject_refs: str | None = None,
+                 barcodes: list | None = None, records=None):
+        self.ref, self.mmi, self.barcodes = ref, mmi, barcodes
+        if records is None:
+            if ref is None or not Path(ref).is_file():
+                raise FileNotFoundError("Reference file not found")
+            if not any(r in {".fa", ".fasta"} for r in Path(ref).suffixes):
+                raise ValueError("Reference needs to be either .fa or .fasta (optionally gzipped).")
+            records = read_fasta(ref)
+        self.reject_refs = set(reject_refs.split(",")) if reject_refs else set()
+        logging.info("Reading reference file")
+        self.contigs = self._load_contigs(records)
+        self.n_sites = self._total_sites()
+
+    def _load_contigs(self, records, min_len: int = int(1e5), ploidy: int = 1) -> dict[str, Contig]:
+        contigs = {}
+        for cname, cseq in records:
+            if len(cseq) < min_len:
+                continue
+            if cname not in self.reject_refs:
+                contigs[cname] = Contig(name=cname, seq=cseq, ploidy=ploidy, barcodes=self.barcodes)
+            else:
+                contigs[cname] = Contig(name=cname, seq="ACGT", ploidy=ploidy, rej=True)
+        return contigs
+
+    def _total_sites(self) -> int:
+        return np.sum(list(self.contig_lengths().values()))
+
+    def contig_lengths(self) -> dict[str, int]:
+        return {c.name: c.length for c in self.contigs.values()}
+
+    def get_strategy_dict(self) -> dict[str, np.ndarray]:
+        return {cname: cont.strat for cname, cont in self.contigs.items()}
+
+
+def read_fasta(path: str):
+    """Minimal FASTA reader (plain or gzip) yielding (name up to the first blank, sequence)."""
+    import gzip
+    opener = gzip.open if str(path).endswith(".gz") else open
+    name, chunks = None, []
+    with opener(path, "rt") as fh:
+        for line in fh:
+            if line.startswith(">"):
+                if name is not None:
+                    yield name, "".join(chunks)
+                head = line[1:].split()
+                name, chunks = (head[0] if head else ""), []
+            else:
+                chunks.append(line.strip())
+    if name is not None:
+        yield name, "".join(chunks)
+
+
+class BossRuns:
+    """The strategy-update half of `boss.runs.core.BossRuns`, GPU-backed.
+
+    Constructor arguments replace the TOML fields the path reads (`general.ref/barcodes`,
+    `optional.ploidy/reject_refs/bucket_threshold`); `out_dir` enables the boss.npz hand-over to readfish.
+    """
+
+    def __init__(self, ref: str | None = None, contigs=None, ploidy: int = 1, barcodes: list[str] | None = None,
+                 reject_refs: str | None = None, bucket_threshold: float = 5, out_dir: str | None = None,
+                 device: int = 0, stream: int | None = None, strict_upstream_asserts: bool = True,
+                 write_debug: bool = False):
+        if not barcodes:
+            self.barcodes_index = {"": 0}
+        else:
+            self.barcodes_index = {int(bc.split("barcode")[1]): i for i, bc in enumerate(barcodes)}
+        self.barcodes = barcodes
+        self.nbarcodes = len(self.barcodes_index)
+        self.bucket_threshold = bucket_threshold
+        self.out_dir = out_dir
+        self.write_debug = write_debug
+        records = None
+        if contigs is not None:
+            records = list(contigs.items()) if isinstance(contigs, dict) else list(contigs)
+        self.ref = Reference(ref=ref, reject_refs=reject_refs, barcodes=barcodes, records=records)
+        self.contigs = self.ref.contigs
+        self.contigs_filt = {n: c for n, c in self.contigs.items() if not c.rej}
+        if not self.contigs_filt:
+            raise ValueError("no contig of at least 100 kb left to track")
+        self.scoring = Scoring(ploidy=ploidy)      # validates ploidy like upstream (ValueError)
+        self.rl_dist = ReadlengthDist()
+        self.read_starts = ReadStartDist(contigs=self.contigs_filt, strict=strict_upstream_asserts)
+        self._names = list(self.contigs_filt.keys())
+        self.cc = CoverageConverter({n: i for i, n in enumerate(self._names)})
+        self.engine = Engine(contig_lengths=[c.length for c in self.contigs_filt.values()],
+                             ref_codes=[c.seq_int for c in self.contigs_filt.values()],
+                             n_barcodes=self.nbarcodes, ploidy=ploidy, n_sites_total=int(self.ref.n_sites),
+                             device=device, stream=stream)
+        for i, c in enumerate(self.contigs_filt.values()):
+            c._bind(self.engine, i)
+        self.batch = 0
+        self.threshold: float | None = None
+        self.last: UpdateOutcome | None = None
+        if self.out_dir is not None:
+            Path(self.out_dir, "masks").mkdir(parents=True, exist_ok=True)
+            self._write_contig_strategies(self.ref.get_strategy_dict())
+
+    # -- output (core.py:59-69) ----------------------------------------------------------------------
+    def _write_contig_strategies(self, contig_strats: dict[str, np.ndarray]) -> None:
+        if self.out_dir is None:
+            return
+        tmp = f"{self.out_dir}/masks/boss_tmp.npz"
+        np.savez(tmp, **contig_strats)
+        Path(tmp).rename(f"{self.out_dir}/masks/boss.npz")
+
+    # -- coverage (core.py:77-86) ----------------------------------------------------------------------
+    def _effect_increments(self, increments: PackedBatch) -> None:
+        b = increments
+        self.engine.ingest_records(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cig_off, b.cigar_text,
+                                   b.seq_off, b.seq_text)
+
+    # -- update (core.py:160-198) ----------------------------------------------------------------------
+    def update_wrapper(self) -> None:
+        fhat_w = self.read_starts.update_f_pointmass()
+        # `time_cost` does not exist before the first successful read-length update (Q14). Upstream only
+        # reads it once some bucket is on (core.py:172,192), so the AttributeError is raised at that point.
+        time_cost = getattr(self.rl_dist, "time_cost", None)
+        out = self.engine.update(approx_ccl=self.rl_dist.approx_ccl,
+                                 time_cost=np.float64("nan") if time_cost is None else time_cost,
+                                 bucket_threshold=self.bucket_threshold, fhat_windows=fhat_w,
+                                 debug=self.write_debug)
+        self.last = out
+        self._pull_switches()
+        if out.switched_on:
+            if time_cost is None:
+                self.rl_dist.time_cost      # AttributeError, as upstream
+            self.threshold = out.threshold
+            self._pull_strategies()
+            self._write_contig_strategies(self.ref.get_strategy_dict())
+
+    def _pull_switches(self) -> None:
+        for i, c in enumerate(self.contigs_filt.values()):
+            sw, on = self.engine.buckets(i)
+            c.bucket_switches[...] = sw
+            c.switched_on[...] = on
+
+    def _pull_strategies(self) -> None:
+        """One device->host copy of every contig's mask, then per-contig views (no per-contig round trips)."""
+        flat = self.engine.strat_all()
+        row = 0
+        for c in self.contigs_filt.values():
+            n = c.length // BIN
+            c.strat = flat[row: row + n]
+            row += n
+            f_perc = np.count_nonzero(c.strat[:, 0]) / c.strat.shape[0]
+            r_perc = np.count_nonzero(c.strat[:, 1]) / c.strat.shape[0]
+            logging.info(f"{c.name}: {f_perc}, {r_perc}")
+
+    # -- one batch (core.py:202-224, minus the mapping call) -------------------------------------------
+    def process_batch_runs(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
+                           barcodes: dict[str, int] | None = None, paf_dict_starts=None) -> None:
+        """`paf_dict` = mappings of the batch ({read id: [PafLine]}); `paf_dict_starts` (default: the same)
+        is the subset that feeds the read-start distribution — the simulator passes accepted reads only
+        (simulation.py:171)."""
+        increments = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
+        self._effect_increments(increments=increments)
+        self.read_starts.count_read_starts(paf_dict=paf_dict if paf_dict_starts is None else paf_dict_starts)
+        self.update_wrapper()
+        self.batch += 1

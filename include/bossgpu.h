@@ -1,0 +1,250 @@
+/*
+ * bossgpu.h — C ABI of libbossgpu.so: the B200 (sm_100a) implementation of BOSS-RUNS' periodic
+ * strategy update (coverage update -> site scoring -> benefit smoothing -> strategy derivation).
+ *
+ * Every entry point below replaces a piece of the reference's NumPy hot path; the citation after
+ * "replaces:" is file:line in the upstream repository (goldman-gp-ebi/BOSS-RUNS @ a5b6af8).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only; no C++/torch types cross this boundary.
+ *   - every function returns 0 on success and a negative BOSSGPU_E* code on failure; the message
+ *     is available from bossgpu_last_error() (thread-local). Nothing throws across the boundary.
+ *   - the caller owns every host buffer; the library owns all device memory inside the handle.
+ *   - a handle is bound to one CUDA device and one stream and is not thread-safe.
+ *   - there is no CPU fallback: without a usable CUDA device bossgpu_create() fails.
+ *
+ * Vocabulary (the reference's): contig, site, barcode, bucket (20 000 sites), bin (100 sites),
+ * window (2 000 sites, read-start distribution), strand 0 = forward, 1 = reverse.
+ */
+#ifndef BOSSGPU_H
+#define BOSSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOSSGPU_ABI_VERSION 1
+
+/* error codes */
+#define BOSSGPU_OK            0
+#define BOSSGPU_EINVAL       -1   /* bad argument (mirrors the reference's AssertionError / ValueError sites) */
+#define BOSSGPU_ECUDA        -2   /* CUDA runtime failure (message holds cudaGetErrorString) */
+#define BOSSGPU_ENOMEM       -3
+#define BOSSGPU_EBASE        -4   /* a read base outside ACGT reached the scatter: IndexError upstream
+                                     (boss/runs/reference.py:138-140 with codes from sequences.py:762-763) */
+#define BOSSGPU_ESHAPE       -5   /* CIGAR does not span tend-tstart / qend-qstart: upstream AssertionError
+                                     (sequences.py:732-733) or NumPy shape ValueError (sequences.py:785) */
+#define BOSSGPU_ESTATE       -6   /* call sequence violated (e.g. update phases out of order) */
+#define BOSSGPU_EEMPTY       -7   /* all benefits are zero: upstream `np.max` of an empty array raises
+                                     ValueError (sequences.py:588) */
+
+/* model constants of the reference (function defaults upstream, fixed here) */
+#define BOSSGPU_BIN          100     /* downsampling window: reference.py:109,215 ; sequences.py:577 */
+#define BOSSGPU_BUCKET       20000   /* reference.py:83 */
+#define BOSSGPU_RSD_WINDOW   2000    /* readstartdist.py:13 */
+#define BOSSGPU_FREEZE       30      /* sequences.py:419 */
+#define BOSSGPU_N_PATTERNS   278256  /* C(34,5): count patterns with sum <= 29 */
+#define BOSSGPU_N_STEPS      10      /* eta-1 pieces of the read-length staircase: readlengthdist.py:9,86 */
+#define BOSSGPU_HIST_BINS    1088    /* |binary exponent| of benefit/max lies in [0,1075] */
+
+typedef struct bossgpu_handle bossgpu_handle;
+
+/* ---------------------------------------------------------------------------------------------
+ * Construction. Replaces: Contig.__init__ state allocation (boss/runs/reference.py:71-118),
+ * Scoring.__init__/init_score_array (boss/runs/sequences.py:335-393) and the per-contig wiring of
+ * BossRuns.init (boss/runs/core.py:23-55).
+ *
+ * A handle holds one *shard*: an ordered list of segments, each a position range of one
+ * non-rejected contig, in `contigs_filt` order. With one GPU every segment is a whole contig.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bossgpu_segment {
+    int32_t contig;        /* index into the GLOBAL contigs_filt order */
+    int32_t reserved;
+    int64_t contig_len;    /* full length of that contig */
+    int64_t start;         /* first site of this segment within the contig; multiple of BOSSGPU_BUCKET */
+    int64_t len;           /* sites in this segment; start+len == contig_len or a multiple of BOSSGPU_BUCKET */
+} bossgpu_segment;
+
+typedef struct bossgpu_config {
+    int32_t abi_version;        /* BOSSGPU_ABI_VERSION */
+    int32_t device;             /* CUDA device ordinal */
+    void*   stream;             /* cudaStream_t to launch on (NULL = the legacy default stream) */
+    int32_t n_segments;
+    int32_t n_barcodes;         /* 1 when the run is not barcoded (core.py:31-35) */
+    const bossgpu_segment* segments;
+    const uint8_t* ref_codes;   /* seq_int of each segment, concatenated (0..3; reference.py:46-68) */
+    /* global geometry, identical on every shard */
+    int32_t n_contigs_total;    /* len(contigs_filt) */
+    int32_t halo_bins;          /* capacity of the bin halo kept on split contig edges (0 = none) */
+    const int64_t* contig_len_all;  /* [n_contigs_total] */
+    int64_t n_sites_total;      /* Reference.n_sites: includes 4 per reject ref (reference.py:337,343-347) */
+    int64_t n_windows_total;    /* sum over contigs_filt of int(L/2000) (readstartdist.py:26-28) */
+    /* scoring constants, computed by the host mirror of `Priors` so they are bit-identical */
+    int32_t len_g;              /* 5 haploid / 15 diploid genotypes */
+    int32_t reserved2;
+    const double* phi;          /* [5][len_g]          sequences.py:39-155 */
+    const double* priors;       /* [4][len_g]          sequences.py:186-313 */
+    const double* phi_pow;      /* [5][len_g][30]      phi**k, sequences.py:159-168 */
+    double score0_contig;       /* score of a never-observed site: the HAPLOID score0 whatever the ploidy
+                                   (Reference._load_contigs builds Contig(ploidy=1): reference.py:319,334) */
+    double entropy0_contig;
+} bossgpu_config;
+
+int  bossgpu_abi_version(void);
+const char* bossgpu_last_error(void);
+int  bossgpu_device_count(int* n);
+int  bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out);
+int  bossgpu_destroy(bossgpu_handle* h);
+int  bossgpu_synchronize(bossgpu_handle* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coverage update. Replaces: CoverageConverter.convert_records/_parse_cigar
+ * (boss/runs/sequences.py:678-794) + Contig.increment_coverage (boss/runs/reference.py:122-144)
+ * + BossRuns._effect_increments (boss/runs/core.py:77-86).
+ *
+ * ingest_packed: the batch is already tokenised. Read i maps to segment seg[i] starting at
+ *   contig coordinate tstart[i] (= min(tstart,tend)); its CIGAR is cigar[cig_off[i]..cig_off[i+1])
+ *   with each op packed as (len << 4) | class, class 0 = consumes read+reference (M,=,X and every
+ *   other letter the reference does not special-case), 1 = insertion (read only), 2 = deletion
+ *   (reference only; counted as base 4). bases[base_off[i]..base_off[i+1]) are the read bases of
+ *   the aligned slice in ALIGNMENT orientation: ASCII if base_is_ascii, else codes 0..3.
+ *   ASCII is translated like upstream: ACGT -> 0..3, anything else -> ord-48 (-> BOSSGPU_EBASE).
+ *   Positions outside the segment are clipped (a read spanning a shard edge is given to both shards).
+ *   All pointers are HOST pointers unless on_device != 0 (then they are device pointers on the
+ *   handle's device and no copy is made).
+ * ingest_records: text form, tokenised by the library's C++ tokenizer (regex + translate upstream:
+ *   sequences.py:672,762-776). seq slices are given in ORIGINAL read orientation together with
+ *   rev[i]; the library reverse-complements (boss/utils.py:85-95: ATGC<->TACG only).
+ * contig_cov_add[k] (may be NULL): number of reference positions this batch adds to GLOBAL contig k
+ *   over all shards — needed by the dropout rule (reference.py:158,175-177) when a contig is split;
+ *   NULL means "this shard sees every read of its contigs" and the library counts by itself.
+ * ------------------------------------------------------------------------------------------- */
+int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads,
+                          const int32_t* seg, const int64_t* tstart, const int32_t* barcode,
+                          const int64_t* cig_off, const uint32_t* cigar,
+                          const int64_t* base_off, const uint8_t* bases,
+                          int base_is_ascii, int on_device, const int64_t* contig_cov_add);
+
+int bossgpu_ingest_records(bossgpu_handle* h, int64_t n_reads,
+                           const int32_t* contig, const int64_t* tstart, const int64_t* tend,
+                           const int32_t* barcode, const uint8_t* rev,
+                           const int64_t* cig_off, const char* cigar_text,
+                           const int64_t* seq_off, const char* seq_text,
+                           int n_threads);
+
+/* Host tokenizer on its own (no device work): CIGAR text -> packed ops. Returns the number of ops
+ * written (<= cap) or a negative error; ref_span/query_span receive the spans the ops consume. */
+int64_t bossgpu_tokenize_cigar(const char* text, int64_t len, uint32_t* out, int64_t cap,
+                               int64_t* ref_span, int64_t* query_span);
+
+/* ---------------------------------------------------------------------------------------------
+ * Strategy update. Replaces BossRuns.update_wrapper (boss/runs/core.py:160-198):
+ *   Scoring.update_scores (sequences.py:398-455) + Contig.modify_scores (reference.py:148-179)
+ *   + Contig.check_buckets (reference.py:183-211) + ReadStartDist._expand_fhat
+ *   (readstartdist.py:121-152) + Contig.calc_smu/calc_u (reference.py:215-269)
+ *   + Scoring.merge_benefit/adjust_length (sequences.py:553-560, utils.py:206-226)
+ *   + Scoring.find_strat_thread (sequences.py:566-649) + BossRuns._distribute_strategy
+ *   (core.py:125-155).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bossgpu_update_params {
+    int32_t w[BOSSGPU_N_STEPS];       /* approx_ccl // 100 (reference.py:252); each must be >= 1 */
+    double  mult[BOSSGPU_N_STEPS];    /* np.arange(0.05, 1, 0.1)[::-1] (reference.py:253) */
+    double  tc;                       /* time_cost // 100 (sequences.py:581) */
+    double  bucket_threshold;         /* optional.bucket_threshold (core.py:108) */
+    const double* fhat_windows;       /* HOST [n_windows_total][2]: F-hat per 2 kb window before expansion
+                                         (readstartdist.py:86-115); NULL keeps the previous upload */
+    int32_t write_debug;              /* != 0: also keep S_mu and expected benefit for the getters */
+    int32_t reserved;
+} bossgpu_update_params;
+
+typedef struct bossgpu_update_result {
+    int32_t switched_on;      /* any bucket of any contig on (core.py:110-111); 0 => strategy left as is */
+    int32_t strat_size;       /* argmax+1 over the exponent bins (sequences.py:636) */
+    double  threshold;        /* acceptance threshold (sequences.py:643-646) */
+    double  normaliser;       /* max non-zero benefit (sequences.py:588) */
+    double  ubar0;            /* sum(fhat * smu) with smu := benefit, as upstream (core.py:182-183) */
+    double  fhat_sum;         /* sum of the expanded F-hat before normalisation (readstartdist.py:144) */
+    int64_t n_nonzero;        /* benefit entries entering the histogram */
+    int64_t n_dropout;        /* site rows zeroed by the dropout rule (reference.py:160) */
+    int64_t n_accept[2];      /* accepted bins per strand over all contigs (core.py:152-153 log) */
+} bossgpu_update_result;
+
+/* single-shard update: all phases back to back on the handle's stream, one host sync at the end */
+int bossgpu_update(bossgpu_handle* h, const bossgpu_update_params* p, bossgpu_update_result* r);
+
+/* Multi-shard update = the same kernels split where the path has an exchange step. The caller
+ * (one process per GPU) performs the exchanges on the exposed device buffers with NCCL:
+ *   phase 0  score+bin pass, bucket switches         -> exchange: scores_ds halos of split contigs,
+ *                                                        allreduce(max) of the switch flag
+ *   phase 1  S_mu / staircase benefit, local max     -> allreduce(max) of the normaliser word
+ *   phase 2  exponent histogram                      -> allreduce(sum) of the integer histogram
+ *   phase 3  threshold, mask of own merged rows      -> allgather of the packed merged mask
+ *   phase 4  bucket-gated distribution into the persistent strategy */
+int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_params* p,
+                         bossgpu_update_result* r);
+
+#define BOSSGPU_BUF_SWITCH     0   /* int32[1]                          allreduce max */
+#define BOSSGPU_BUF_NORM       1   /* uint64[1] (double bits, >= 0)     allreduce max */
+#define BOSSGPU_BUF_HIST       2   /* uint64[3*HIST_BINS + 4]           allreduce sum */
+#define BOSSGPU_BUF_MASK       3   /* uint8[...] merged mask, all shards allgather    */
+#define BOSSGPU_BUF_HALO_SEND  4
+#define BOSSGPU_BUF_HALO_RECV  5
+int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_ptr, size_t* bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * Results and state access (host buffers, reference layouts).
+ * ------------------------------------------------------------------------------------------- */
+/* Contig.strat of the part of segment `seg` in this shard: bool [len//100 rows][2][n_barcodes]
+ * (reference.py:118; read by simulation.py:79-80 and written to boss.npz by core.py:59-69). */
+int bossgpu_get_strat(bossgpu_handle* h, int32_t seg, uint8_t* out, int64_t out_bytes);
+/* every segment back to back, same layout, one copy */
+int bossgpu_get_strat_all(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
+/* same bits packed little-endian, 8 per byte, over the flattened [row][strand][barcode] order */
+int bossgpu_get_strat_packed(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
+int64_t bossgpu_strat_rows(bossgpu_handle* h, int32_t seg);   /* seg = -1: all segments */
+
+/* Contig.coverage uint16 [len][5][n_barcodes] (reference.py:77) */
+int bossgpu_get_coverage(bossgpu_handle* h, int32_t seg, uint16_t* out, int64_t out_elems);
+int bossgpu_set_coverage(bossgpu_handle* h, int32_t seg, const uint16_t* in, int64_t in_elems);
+/* Contig.scores / Contig.entropy float64 [len][n_barcodes] as they stand after the last update
+ * (materialised on demand from the counts; entropy of frozen sites is the table value, see Q7) */
+int bossgpu_get_scores(bossgpu_handle* h, int32_t seg, double* scores, double* entropy, int64_t out_elems);
+/* Contig.scores_ds float64 [bins][n_barcodes] (reference.py:227) */
+int bossgpu_get_scores_ds(bossgpu_handle* h, int32_t seg, double* out, int64_t out_elems);
+/* Contig.additional_benefit / smu / expected_benefit float64 [bins][2][n_barcodes]
+ * (reference.py:225,254,267); smu and expected need write_debug in the last update */
+int bossgpu_get_benefit(bossgpu_handle* h, int32_t seg, double* additional, double* smu,
+                        double* expected, int64_t out_elems);
+/* Contig.bucket_switches bool [len//20000+1][n_barcodes] and switched_on bool [n_barcodes] */
+int bossgpu_get_buckets(bossgpu_handle* h, int32_t seg, uint8_t* switches, int64_t n, uint8_t* switched_on);
+int bossgpu_set_buckets(bossgpu_handle* h, int32_t seg, const uint8_t* switches, int64_t n);
+/* exponent histogram of the last update: counts int64[HIST_BINS], f_grid float64[HIST_BINS]
+ * (sequences.py:593-624, before the empty bins are dropped) */
+int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_grid);
+/* the dense score table: float64 [N_PATTERNS][4] (replaces score_arr / entropy_arr, sequences.py:387-388) */
+int bossgpu_get_score_table(bossgpu_handle* h, double* scores, double* entropies);
+/* rank of a count pattern (c0..c4, sum <= 29) in that table; -1 if out of range */
+int64_t bossgpu_pattern_rank(const uint16_t c[5]);
+
+/* per-kernel device times of the last update in ms (CUDA events on the handle's stream):
+ * [0] scatter (last ingest) [1] score+bin pass [2] buckets [3] smoothing [4] histogram
+ * [5] threshold [6] mask+distribute [7] whole update */
+#define BOSSGPU_N_TIMERS 8
+int bossgpu_timing(bossgpu_handle* h, float ms[BOSSGPU_N_TIMERS]);
+/* algorithmic launches issued so far (kernels of this library only) */
+int64_t bossgpu_launch_count(bossgpu_handle* h);
+
+/* Bench/test support: fill the coverage of every segment with a synthetic sequencing state on the
+ * device (depth ~ Poisson(mean_depth) split over bases with p_ref, uniform errors, p_del; a fraction
+ * of 20 kb regions with zero depth and a fraction with depth >= 30), deterministic in `seed`.
+ * Not part of the reference; used for BASELINE.json config 3 whose state cannot be built on a host. */
+int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double mean_depth, double p_ref,
+                           double p_del, double frac_dropout, double frac_deep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSSGPU_H */
