@@ -1,0 +1,88 @@
+"""Shared drivers for the parity tests: run the same batches through the oracle and through the product."""
+from __future__ import annotations
+
+import io
+
+import numpy as np
+
+from oracle import boss_oracle as bo
+from boss_runs_b200.hostmodel import parse_PAF
+import tolerances as tol
+
+
+def parse_batch(paf_text, bcs, barcoded):
+    pd = parse_PAF(io.StringIO(paf_text))
+    for rid, recs in pd.items():
+        for r in recs:
+            r.barcode = bcs.get(rid) if barcoded else None
+    return pd
+
+
+def oracle_run(records, ploidy, reject_refs, barcodes, bucket_threshold, strict=True):
+    return bo.OracleRun(records, ploidy=ploidy, reject_refs=reject_refs, barcodes=barcodes, bucket_threshold=bucket_threshold)
+
+
+def oracle_step(run, pd, seqs):
+    run.rl.update({rid: recs[0].qlen for rid, recs in pd.items()})
+    run.ingest(pd, seqs)
+    run.read_starts.count(pd)
+    return run.update()
+
+
+def product_run(records, ploidy, reject_refs, barcodes, bucket_threshold, **kw):
+    from boss_runs_b200.runs import BossRuns
+    return BossRuns(contigs=records, ploidy=ploidy, barcodes=barcodes,
+                    reject_refs=",".join(reject_refs) if reject_refs else None, bucket_threshold=bucket_threshold,
+                    write_debug=True, **kw)
+
+
+def product_step(run, pd, seqs):
+    run.rl_dist.update({rid: recs[0].qlen for rid, recs in pd.items()})
+    run.process_batch_runs(pd, seqs)
+    return bool(run.last.switched_on)
+
+
+def assert_close_smooth(got, want, what):
+    atol = tol.SMOOTH_ATOL_FRAC * float(np.max(np.abs(want))) if want.size else 0.0
+    err = np.abs(got - want)
+    bad = err > (tol.SMOOTH_RTOL * np.abs(want) + atol)
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst abs err {err.max():.3e} (atol {atol:.3e})"
+
+
+def assert_masks_match(got, want, benefit, thr, what):
+    """Masks must agree everywhere except where the benefit is within MASK_REL of the threshold."""
+    diff = got != want
+    if diff.any():
+        near = np.abs(benefit - thr) <= tol.MASK_REL * abs(thr)
+        assert not (diff & ~near).any(), f"{what}: {(diff & ~near).sum()} mask bits differ away from the threshold"
+
+
+def compare_state(prod, orc, updated: bool, tag: str):
+    """Product (GPU) vs oracle after one update."""
+    for (name, pc), (oname, oc) in zip(prod.contigs.items(), orc.contigs.items()):
+        assert name == oname
+        if oc.rej:
+            assert pc.strat.shape == (1,) and not pc.strat.any()
+            continue
+        t = f"{tag}/{name}"
+        assert np.array_equal(pc.coverage, oc.coverage), f"{t}: coverage differs"
+        s = pc.scores
+        np.testing.assert_allclose(s, oc.scores, rtol=tol.SCORE_RTOL, atol=0, err_msg=f"{t}: scores")
+        assert np.array_equal(s == 0.0, oc.scores == 0.0), f"{t}: dropout zeros differ"
+        assert np.array_equal(pc.bucket_switches, oc.bucket_switches), f"{t}: bucket switches"
+        assert np.array_equal(pc.switched_on, oc.switched_on), f"{t}: switched_on"
+        if updated:
+            np.testing.assert_allclose(pc.scores_ds, oc.scores_ds, rtol=tol.SCORE_RTOL, atol=0, err_msg=f"{t}: scores_ds")
+            assert_close_smooth(pc.smu, oc.smu, f"{t}: smu")
+            assert_close_smooth(pc.expected_benefit, oc.expected_benefit, f"{t}: expected_benefit")
+            assert_close_smooth(pc.additional_benefit, oc.additional_benefit, f"{t}: additional_benefit")
+    if updated:
+        assert abs(prod.threshold - orc.threshold) <= tol.THRESHOLD_RTOL * abs(orc.threshold), \
+            f"{tag}: threshold {prod.threshold!r} vs oracle {orc.threshold!r}"
+        # strategies: Q2 means contig k reads merged rows shifted by k bins; check against the oracle's own arrays
+        i = 0
+        for (name, pc), oc in zip(prod.contigs_filt.items(), orc.contigs_filt.values()):
+            n = oc.length // 100
+            ben = orc.benefit_adj[i: i + n]
+            assert_masks_match(pc.strat, oc.strat, ben, orc.threshold, f"{tag}/{name}: strat")
+            i += n
