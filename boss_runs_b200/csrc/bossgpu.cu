@@ -499,7 +499,6 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     // reset per-update device scalars (keeps `error`)
     BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
     BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
-    EV_BEGIN(1);
     {
         // contig lengths live at the front of scratch for the threshold kernel
         size_t bytes = sizeof(int64_t) * h->n_contigs_total;
@@ -516,6 +515,7 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     a.score0 = h->score0; a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
     a.n_dropout = &h->d_upd->n_dropout;
     dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
+    EV_BEGIN(1);
     if (h->nb > 1) {
         k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
         BOSS_KERNEL_CHECK();

@@ -116,7 +116,8 @@ class Contig:
         self.rej = rej
         self.barcodes = barcodes
         self.nbarcodes = len(barcodes) if barcodes is not None else 1
-        self.seq_int = seq_to_int(seq)
+        # `seq` may also be given already integerised (uint8 codes 0..3) — large synthetic references
+        self.seq_int = seq_to_int(seq) if isinstance(seq, str) else np.asarray(seq, dtype=np.uint8)
         assert len(set(self.seq_int[:100]) | {0, 1, 2, 3}) == 4
         self.bucket_size = BUCKET
         self.bucket_switches = np.zeros(shape=(int(self.length // BUCKET) + 1, self.nbarcodes), dtype="bool")
@@ -334,3 +335,51 @@ class BossRuns:
         self.read_starts.count_read_starts(paf_dict=paf_dict if paf_dict_starts is None else paf_dict_starts)
         self.update_wrapper()
         self.batch += 1
+
+    # -- device-resident variants (bench.py `value` leg, pipelined callers) ----------------------------
+    def local_sites(self) -> int:
+        """Sites held by this process' GPU."""
+        return int(sum(s.length for s in self.engine.segments))
+
+    def pack_for_device(self, batch: PackedBatch) -> dict:
+        """Tokenise a batch on the host into libbossgpu's packed arrays (what `bossgpu_ingest_packed` takes),
+        e.g. to upload it ahead of time and ingest with `ingest_device`."""
+        import ctypes as C
+        lib = self.engine.lib
+        n = len(batch)
+        cig_off = np.zeros(n + 1, dtype=np.int64)
+        ops = np.empty(len(batch.cigar_text) // 2 + n + 1, dtype=np.uint32)
+        text = np.frombuffer(batch.cigar_text, dtype=np.uint8)
+        seq = np.frombuffer(batch.seq_text, dtype=np.uint8)
+        bases = np.empty(len(seq), dtype=np.uint8)
+        comp = np.arange(256, dtype=np.uint8)
+        for a, b in zip(b"ATGC", b"TACG"):
+            comp[a] = b
+        r, q = C.c_int64(), C.c_int64()
+        w = 0
+        for i in range(n):
+            a, b = int(batch.cig_off[i]), int(batch.cig_off[i + 1])
+            k = lib.bossgpu_tokenize_cigar(text[a:b].tobytes(), b - a, ops[w:].ctypes.data, len(ops) - w, C.byref(r), C.byref(q))
+            if k < 0:
+                raise ValueError("CIGAR tokenizer failed")
+            w += k
+            cig_off[i + 1] = w
+            sa, sb = int(batch.seq_off[i]), int(batch.seq_off[i + 1])
+            if q.value != sb - sa or r.value != abs(int(batch.tend[i]) - int(batch.tstart[i])):
+                raise AssertionError(f"read {i}: CIGAR does not span the aligned slice / target interval")
+            bases[sa:sb] = comp[seq[sa:sb][::-1]] if batch.rev[i] else seq[sa:sb]
+        return dict(n=n, seg=batch.contig.astype(np.int32), tstart=np.minimum(batch.tstart, batch.tend).astype(np.int64),
+                    barcode=batch.barcode.astype(np.int32), cig_off=cig_off, cigar=ops[:max(w, 1)].copy(),
+                    base_off=batch.seq_off.astype(np.int64), bases=bases if len(bases) else np.zeros(1, np.uint8))
+
+    def ingest_device(self, d: dict) -> None:
+        """`d`: the dict of `pack_for_device` with every array replaced by a CUDA tensor on this device."""
+        self.engine.ingest_packed_device(d["n"], d["seg"].data_ptr(), d["tstart"].data_ptr(), d["barcode"].data_ptr(),
+                                         d["cig_off"].data_ptr(), d["cigar"].data_ptr(), d["base_off"].data_ptr(),
+                                         d["bases"].data_ptr(), ascii_bases=True)
+
+    def device_update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None) -> UpdateOutcome:
+        """The strategy update without the device->host copy of the masks."""
+        self.last = self.engine.update(approx_ccl=approx_ccl, time_cost=time_cost, bucket_threshold=bucket_threshold,
+                                       fhat_windows=fhat_windows)
+        return self.last

@@ -103,7 +103,9 @@ def read_batch(contigs: dict[str, str], n_reads: int, seed: int, mean_len: float
     if codes is None:
         lut = np.zeros(256, dtype=np.uint8)
         lut[ACGT] = np.arange(4, dtype=np.uint8)
-        codes = {n: lut[np.frombuffer(contigs[n].encode(), dtype=np.uint8)] for n in names}
+        # contigs may be strings or already-integerised uint8 arrays
+        codes = {n: (lut[np.frombuffer(contigs[n].encode(), dtype=np.uint8)] if isinstance(contigs[n], str)
+                     else np.asarray(contigs[n], dtype=np.uint8)) for n in names}
     lens = np.array([len(contigs[n]) for n in names], dtype=np.float64)
     which = rng.choice(len(names), size=n_reads, p=lens / lens.sum())
     lines, seqs, bcs = [], {}, {}
@@ -145,10 +147,11 @@ def read_batch(contigs: dict[str, str], n_reads: int, seed: int, mean_len: float
     return ReadBatch("\n".join(lines) + "\n", seqs, bcs, total_ref)
 
 
-def packed_batch(contig_lengths, ref_codes, n_reads: int, seed: int, mean_len: float = 10_000.0,
-                 n_barcodes: int = 1, indel_every: int = 22):
-    """A large batch directly in libbossgpu's packed form (no text), vectorised: regular indel spacing,
-    uniform starts. Used by the device-resident legs of bench.py where text generation would dominate.
+def packed_batch(contig_lengths, n_reads: int, seed: int, mean_len: float = 10_000.0, n_barcodes: int = 1,
+                 indel_every: int = 22) -> dict:
+    """A large batch directly in libbossgpu's packed form (no text), fully vectorised: every read is
+    [M(indel_every) D(1) M(indel_every) I(1)]* M(rest) with random bases. For scatter-throughput runs where
+    text generation would dominate; the parity tests use `read_batch`.
 
     Returns dict(seg, tstart, barcode, cig_off, cigar, base_off, bases, n_ref_positions)."""
     rng = np.random.default_rng(seed)
@@ -157,35 +160,26 @@ def packed_batch(contig_lengths, ref_codes, n_reads: int, seed: int, mean_len: f
     span = np.clip(rng.gamma(4.0, mean_len / 4.0, size=n_reads), 1000, 60_000).astype(np.int64)
     span = np.minimum(span, lens[seg] - 1)
     tstart = (rng.random(n_reads) * (lens[seg] - span)).astype(np.int64)
-    # alignment = blocks of (indel_every M, 1 D) / (indel_every M, 1 I) alternating, closed by an M run
-    n_blk = span // (indel_every + 1)
-    tail = span - n_blk * (indel_every + 1) + 0          # final M run (may be 0 -> merged below)
-    n_del = (n_blk + 1) // 2
+    n_blk = span // (indel_every + 1)                 # blocks of indel_every matches + one indel
+    n_del = (n_blk + 1) // 2                          # even blocks delete, odd blocks insert
     n_ins = n_blk // 2
-    # ops per read: 2 per block + 1
+    last_m = span - (n_blk * indel_every + n_del)     # closing match run keeps the reference span exact
     n_ops = 2 * n_blk + 1
     cig_off = np.zeros(n_reads + 1, dtype=np.int64)
     np.cumsum(n_ops, out=cig_off[1:])
-    cigar = np.empty(int(cig_off[-1]), dtype=np.uint32)
-    pos = np.arange(int(cig_off[-1])) - np.repeat(cig_off[:-1], n_ops)
+    total_ops = int(cig_off[-1])
     rd = np.repeat(np.arange(n_reads), n_ops)
-    is_last = pos == (n_ops[rd] - 1)
-    is_m = (pos % 2 == 0)
-    blk = pos // 2
-    cls = np.where(is_m, 0, np.where(blk % 2 == 0, 2, 1))            # D on even blocks, I on odd blocks
-    # deletion consumes one reference position of the block's indel_every+1; insertion consumes none, so give
-    # the following match run one more base to keep the reference span exact
-    m_len = np.where(is_last, tail[rd], indel_every + np.where((blk % 2 == 1), 1, 0) * 0)
-    ln = np.where(is_m, m_len, 1)
-    # reference use per block: M(indel_every) + D(1) = indel_every+1 ; M(indel_every) + I = indel_every -> pad last run
-    ref_used = n_blk * indel_every + n_del
-    last_m = span - ref_used
-    ln = np.where(is_last, last_m[rd], ln)
-    cigar[:] = (ln.astype(np.uint32) << 4) | cls.astype(np.uint32)
+    pos = np.arange(total_ops) - cig_off[:-1][rd]
+    is_last = pos == n_ops[rd] - 1
+    is_m = pos % 2 == 0
+    cls = np.where(is_m, 0, np.where((pos // 2) % 2 == 0, 2, 1)).astype(np.uint32)
+    ln = np.where(is_last, last_m[rd], np.where(is_m, indel_every, 1)).astype(np.uint32)
+    cigar = (ln << 4) | cls
     q_len = n_blk * indel_every + n_ins + last_m
     base_off = np.zeros(n_reads + 1, dtype=np.int64)
     np.cumsum(q_len, out=base_off[1:])
     bases = rng.integers(0, 4, size=int(base_off[-1]), dtype=np.uint8)
-    barcode = rng.integers(0, n_barcodes, size=n_reads).astype(np.int32) if n_barcodes > 1 else np.zeros(n_reads, np.int32)
+    barcode = (rng.integers(0, n_barcodes, size=n_reads).astype(np.int32) if n_barcodes > 1
+               else np.zeros(n_reads, dtype=np.int32))
     return dict(seg=seg, tstart=tstart, barcode=barcode, cig_off=cig_off, cigar=cigar, base_off=base_off, bases=bases,
                 n_ref_positions=int(span.sum()))
