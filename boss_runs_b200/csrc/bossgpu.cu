@@ -195,10 +195,13 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     A(dev_alloc(&h->d_tile_start, h->n_seg + 1));
     A(dev_alloc(&h->d_row_start, h->n_seg + 1));
     A(dev_alloc(&h->d_srow_start, h->n_seg + 1));
+    A(dev_alloc(&h->d_sm_tile_start, h->n_seg + 1));
+    A(dev_alloc(&h->d_contig_len, h->n_contigs_total));
     A(dev_alloc(&h->d_ref, (size_t)P));
     A(dev_alloc(&h->d_cov, (size_t)h->nb * 5 * P));
     if (h->nb > 1) A(dev_alloc(&h->d_rowflag, (size_t)P));
-    A(dev_alloc(&h->d_table, (size_t)NPAT * 4));
+    A(dev_alloc(&h->d_table, (size_t)(NPAT + 3) * 4));
+    A(dev_alloc((TileDesc**)&h->d_tiles, (size_t)tiles));
     A(dev_alloc(&h->d_etable, (size_t)NPAT * 4));
     A(dev_alloc(&h->d_phi, (size_t)5 * h->len_g));
     A(dev_alloc(&h->d_priors, (size_t)4 * h->len_g));
@@ -230,6 +233,13 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         BOSS_CUDA(cudaMemcpy(h->d_tile_start, ts.data(), sizeof(int64_t) * ts.size(), cudaMemcpyHostToDevice));
         BOSS_CUDA(cudaMemcpy(h->d_row_start, rs.data(), sizeof(int64_t) * rs.size(), cudaMemcpyHostToDevice));
         BOSS_CUDA(cudaMemcpy(h->d_srow_start, ss.data(), sizeof(int64_t) * ss.size(), cudaMemcpyHostToDevice));
+        std::vector<int64_t> st(h->n_seg + 1);
+        int64_t nt = 0;
+        for (int s = 0; s < h->n_seg; ++s) { st[s] = nt; nt += ceil_div(h->segs[s].n_bins, SM_TILE); }
+        st[h->n_seg] = nt;
+        h->n_sm_tiles = nt;
+        BOSS_CUDA(cudaMemcpy(h->d_sm_tile_start, st.data(), sizeof(int64_t) * st.size(), cudaMemcpyHostToDevice));
+        BOSS_CUDA(cudaMemcpy(h->d_contig_len, h->contig_len_all.data(), sizeof(int64_t) * h->n_contigs_total, cudaMemcpyHostToDevice));
     }
     // reference bases, segment by segment onto the padded axis
     {
@@ -249,7 +259,41 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     k_build_table<<<(unsigned)ceil_div(NPAT, 128), 128, 0, h->stream>>>(h->len_g, h->d_phi, h->d_priors, h->d_phi_pow,
                                                                        h->d_table, h->d_etable);
     BOSS_KERNEL_CHECK();
+    {   // special rows behind the pattern table: frozen, never observed, dropped
+        double extra[12];
+        for (int i = 0; i < 4; ++i) { extra[i] = TINY; extra[4 + i] = h->score0; extra[8 + i] = 0.0; }
+        BOSS_CUDA(cudaMemcpyAsync(h->d_table + (size_t)NPAT * 4, extra, sizeof extra, cudaMemcpyHostToDevice, h->stream));
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));
+        // Without barcodes the all-zero pattern IS "never observed" (Q5: contig score0, not the table value), so
+        // row 0 of the working table is patched; the true values are kept for bossgpu_get_score_table.
+        BOSS_CUDA(cudaMemcpy(h->row0_true, h->d_table, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+        BOSS_CUDA(cudaMemcpy(h->row0_true + 4, h->d_etable, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+        if (h->nb == 1) {
+            BOSS_CUDA(cudaMemcpy(h->d_table, extra + 4, sizeof(double) * 4, cudaMemcpyHostToDevice));
+            double e0[4] = {h->ent0, h->ent0, h->ent0, h->ent0};
+            BOSS_CUDA(cudaMemcpy(h->d_etable, e0, sizeof e0, cudaMemcpyHostToDevice));
+        }
+    }
+    {   // tile descriptors of the score/bin pass
+        std::vector<TileDesc> td((size_t)tiles);
+        for (int s = 0; s < h->n_seg; ++s) {
+            const SegDev& S = h->segs[s];
+            for (int64_t i = 0; i < S.n_tiles; ++i) {
+                TileDesc& d = td[(size_t)(S.tile_off + i)];
+                const int64_t local0 = i * TILE;
+                d.site_off = S.site_off + local0;
+                d.ds_index = S.ds_off + local0 / BIN;
+                d.n_sites = (int32_t)std::max<int64_t>(0, std::min<int64_t>(TILE, S.len - local0));
+                d.n_bins = (int32_t)std::min<int64_t>(TILE / BIN, S.n_bins - local0 / BIN);
+                const int64_t bucket = local0 / BUCKET;
+                d.bucket = bucket < S.n_full_buckets ? (int32_t)(S.sw_off + bucket) : -1;
+                d.contig = S.contig;
+            }
+        }
+        BOSS_CUDA(cudaMemcpy(h->d_tiles, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice));
+    }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BOSS_CUDA(cudaFuncSetAttribute(k_smooth_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
     return 0;
@@ -262,8 +306,8 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
     void* ptrs[] = {h->d_segs, h->d_tile_start, h->d_row_start, h->d_srow_start, h->d_ref, h->d_cov, h->d_rowflag,
                     h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
                     h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
-                    h->d_hist, h->d_strat, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all,
-                    h->d_shard_row_start, h->d_halo};
+                    h->d_hist, h->d_strat, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
+                    h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
@@ -499,30 +543,24 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     // reset per-update device scalars (keeps `error`)
     BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
     BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
-    {
-        // contig lengths live at the front of scratch for the threshold kernel
-        size_t bytes = sizeof(int64_t) * h->n_contigs_total;
-        TRY(ensure_scratch(h, bytes));
-        BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, h->contig_len_all.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-        k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
-            h->n_contigs_total, (const int64_t*)h->scratch_d, h->nb, h->d_cov_total, h->d_drop_thr);
-        BOSS_KERNEL_CHECK();
-        h->launches++;
-    }
+    k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
+        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
     ScoreArgs a;
-    a.segs = h->d_segs; a.tile_start = h->d_tile_start; a.n_seg = h->n_seg; a.nb = h->nb; a.P = h->P;
+    a.tiles = (const TileDesc*)h->d_tiles; a.nb = h->nb; a.P = h->P;
     a.ref = h->d_ref; a.cov = h->d_cov; a.rowflag = h->d_rowflag; a.table = h->d_table; a.drop_thr = h->d_drop_thr;
-    a.score0 = h->score0; a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
+    a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
     a.n_dropout = &h->d_upd->n_dropout;
     dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
     EV_BEGIN(1);
     if (h->nb > 1) {
         k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
         BOSS_KERNEL_CHECK();
-        k_score_bin<true><<<grid, TILE_THREADS, 0, h->stream>>>(a);
+        k_score_bin<true><<<grid, SB_THREADS, 0, h->stream>>>(a);
         h->launches += 2;
     } else {
-        k_score_bin<false><<<grid, TILE_THREADS, 0, h->stream>>>(a);
+        k_score_bin<false><<<grid, SB_THREADS, 0, h->stream>>>(a);
         h->launches++;
     }
     BOSS_KERNEL_CHECK();
@@ -550,29 +588,41 @@ static int ensure_debug(bossgpu_handle* h) {
 static int phase1_smooth(bossgpu_handle* h, const bossgpu_update_params* p) {
     if (p->write_debug) TRY(ensure_debug(h));
     EV_BEGIN(3);
-    // per-segment tile table for the smoothing kernel (host-built, tiny)
-    std::vector<int64_t> st(h->n_seg + 1);
-    int64_t t = 0;
-    for (int s = 0; s < h->n_seg; ++s) { st[s] = t; t += ceil_div(h->segs[s].n_bins, SM_TILE); }
-    st[h->n_seg] = t;
-    size_t bytes = sizeof(int64_t) * st.size();
-    TRY(ensure_scratch(h, bytes + 64));
-    BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, st.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-    BOSS_CUDA(cudaStreamSynchronize(h->stream));      // st is a stack vector; cheap (tiny copy) and keeps lifetime simple
+    const int64_t t = h->n_sm_tiles;
     SmoothArgs a;
-    a.segs = h->d_segs; a.row_start = h->d_row_start; a.n_seg = h->n_seg; a.nb = h->nb; a.ds = h->d_ds; a.ds_len = h->ds_len;
+    a.segs = h->d_segs; a.n_seg = h->n_seg; a.nb = h->nb; a.ds = h->d_ds; a.ds_len = h->ds_len;
     a.benefit = h->d_benefit;
     a.smu = p->write_debug ? h->d_smu : nullptr;
     a.expected = p->write_debug ? h->d_expected : nullptr;
     a.n_rows = h->n_rows;
-    int wmax = 4;
-    for (int i = 0; i < NSTEPS; ++i) { a.w[i] = p->w[i]; a.mult[i] = p->mult[i]; wmax = std::max(wmax, p->w[i]); }
+    int wmax = 4, dmax = 1;
+    for (int i = 0; i < NSTEPS; ++i) {
+        a.mult[i] = p->mult[i];
+        wmax = std::max(wmax, p->w[i]);
+        dmax = std::max(dmax, p->w[i] - (i ? p->w[i - 1] : 0));
+    }
     a.wmax = wmax;
     a.R0 = h->R0; a.target_rows = h->target_rows; a.upd = h->d_upd;
-    size_t smem = sizeof(double) * (SM_TILE + 2 * (size_t)(wmax - 1));
-    if (smem > 200 * 1024) return fail(BOSSGPU_EINVAL, "staircase window of %d bins needs %zu B of shared memory", wmax, smem);
+    // levels: as many power-of-two widths as the largest increment needs and shared memory allows
+    const size_t span = SM_TILE + 2 * (size_t)(wmax - 1);
+    int levels = 1;
+    while (levels < SM_MAX_LEVELS && (1 << levels) <= dmax && (size_t)(levels + 1) * span * sizeof(double) <= 160 * 1024) ++levels;
+    const bool planned = plan_smoothing(p->w, levels, a);
     dim3 grid((unsigned)t, (unsigned)h->nb);
-    k_smooth<<<grid, SM_TILE, smem, h->stream>>>(a, (const int64_t*)h->scratch_d);
+    if (planned) {
+        a.n_levels = levels;
+        size_t smem = sizeof(double) * span * levels;
+        k_smooth<<<grid, SM_TILE, smem, h->stream>>>(a, h->d_sm_tile_start);
+    } else {
+        // very long staircase: bin-by-bin sums; windows go through scratch (behind the tile table)
+        size_t smem = sizeof(double) * span;
+        if (smem > 200 * 1024) return fail(BOSSGPU_EINVAL, "staircase window of %d bins needs %zu B of shared memory", wmax, smem);
+        TRY(ensure_scratch(h, 256));
+        int32_t* d_w = (int32_t*)h->scratch_d;
+        BOSS_CUDA(cudaMemcpyAsync(d_w, p->w, sizeof(int32_t) * NSTEPS, cudaMemcpyHostToDevice, h->stream));
+        a.n_levels = 1;
+        k_smooth_direct<<<grid, SM_TILE, smem, h->stream>>>(a, h->d_sm_tile_start, d_w);
+    }
     BOSS_KERNEL_CHECK();
     h->launches++;
     EV_END(3);
@@ -603,8 +653,8 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
     HistArgs a;
     a.benefit = h->d_benefit; a.n_rows = h->n_rows; a.nb = h->nb; a.R0 = h->R0; a.M = h->M_rows; a.target = h->target_rows;
     a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.hist = h->d_hist; a.upd = h->d_upd;
-    unsigned gx = (unsigned)std::min<int64_t>(ceil_div(h->n_rows, 256), 148 * 8);
-    k_hist<<<dim3(gx, (unsigned)h->nb), 256, 0, h->stream>>>(a);
+    unsigned gx = (unsigned)ceil_div(h->n_rows, HIST_THREADS * HIST_ROWS_PER_THREAD);
+    k_hist<<<dim3(gx, (unsigned)h->nb), HIST_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     h->launches += 3;
     EV_END(4);
@@ -984,8 +1034,14 @@ extern "C" int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_gr
 
 extern "C" int bossgpu_get_score_table(bossgpu_handle* h, double* scores, double* entropies) {
     H_CHECK(h);
-    if (scores) BOSS_CUDA(cudaMemcpy(scores, h->d_table, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
-    if (entropies) BOSS_CUDA(cudaMemcpy(entropies, h->d_etable, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
+    if (scores) {
+        BOSS_CUDA(cudaMemcpy(scores, h->d_table, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
+        memcpy(scores, h->row0_true, sizeof(double) * 4);
+    }
+    if (entropies) {
+        BOSS_CUDA(cudaMemcpy(entropies, h->d_etable, sizeof(double) * (size_t)NPAT * 4, cudaMemcpyDeviceToHost));
+        memcpy(entropies, h->row0_true + 4, sizeof(double) * 4);
+    }
     return 0;
 }
 

@@ -46,7 +46,6 @@ constexpr int      NPAT      = BOSSGPU_N_PATTERNS;
 constexpr int      HBINS     = BOSSGPU_HIST_BINS;
 constexpr int      NSTEPS    = BOSSGPU_N_STEPS;
 constexpr int      TILE      = 2000;          // sites per CTA in the score+bin pass: 20 bins, 1/10 bucket
-constexpr int      TILE_THREADS = 512;        // 500 active threads x 4 sites
 constexpr int64_t  SITE_ALIGN = 256;          // segment starts on the padded site axis
 constexpr double   TINY      = 2.2250738585072014e-308;   // np.finfo(float).tiny (sequences.py:430)
 
@@ -126,6 +125,10 @@ struct bossgpu_handle {
     int64_t*  d_tile_start = nullptr;   // [n_seg+1]
     int64_t*  d_row_start = nullptr;    // [n_seg+1]
     int64_t*  d_srow_start = nullptr;   // [n_seg+1]
+    int64_t*  d_sm_tile_start = nullptr; // [n_seg+1] first smoothing tile of each segment
+    int64_t   n_sm_tiles = 0;
+    int64_t*  d_contig_len = nullptr;   // [n_contigs_total]
+    void*     d_tiles = nullptr;        // [n_tiles] TileDesc (score_pass.cuh)
     uint8_t*  d_ref = nullptr;          // [P]
     uint16_t* d_cov = nullptr;          // [nb][5][P]
     uint32_t* d_rowflag = nullptr;      // [P] (nb > 1 only)
@@ -135,6 +138,7 @@ struct bossgpu_handle {
     double*   d_priors = nullptr;       // [4][len_g]
     double*   d_phi_pow = nullptr;      // [5][len_g][30]
     double    score0 = 0, ent0 = 0;
+    double    row0_true[8] = {0};       // table / etable values of the all-zero pattern (row 0 is patched when nb == 1)
     unsigned long long* d_cov_total = nullptr;   // [n_contigs_total]
     int32_t*  d_drop_thr = nullptr;              // [n_contigs_total]  -1 = dropout rule inactive
     double*   d_ds = nullptr;                    // [nb][ds_len]

@@ -23,23 +23,34 @@
 
 namespace boss {
 
+// one entry per CTA of the score/bin pass, built on the host at create time
+struct TileDesc {
+    int64_t site_off;     // first site of the tile on the padded site axis (multiple of 8)
+    int64_t ds_index;     // index of the tile's first bin in scores_ds (barcode 0)
+    int32_t n_sites;      // valid sites in the tile (0 for the tile that only holds a contig's empty last bin)
+    int32_t n_bins;       // bins of this tile that exist (<= 20)
+    int32_t bucket;       // entry of bucket_sum this tile adds to, or -1 (partial bucket at the contig end)
+    int32_t contig;       // global contig index (dropout threshold)
+};
+
 struct ScoreArgs {
-    const SegDev* segs;
-    const int64_t* tile_start;       // [n_seg+1]
-    int n_seg;
+    const TileDesc* tiles;
     int nb;
     int64_t P;
     const uint8_t* ref;
     const uint16_t* cov;
     const uint32_t* rowflag;         // nb > 1: (touched << 31) | min over barcodes of depth
-    const double* table;
+    const double* table;             // [NPAT + 3][4]; the three extra rows hold tiny, score0, 0.0
     const int32_t* drop_thr;         // per global contig; -1 = rule inactive
-    double score0;
     double* ds;                      // [nb][ds_len]
     int64_t ds_len;
     unsigned long long* bucket_sum;  // [n_sw][nb]
     unsigned long long* n_dropout;
 };
+
+constexpr int ROW_TINY = NPAT;       // depth >= 30: frozen site            (sequences.py:419-420,430)
+constexpr int ROW_SCORE0 = NPAT + 1; // row never observed: contig score0   (reference.py:103-104, Q5)
+constexpr int ROW_ZERO = NPAT + 2;   // dropped row                         (reference.py:161)
 
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ starts, int n, int64_t x) {
     int lo = 0, hi = n;                  // starts[lo] <= x < starts[hi]
@@ -73,95 +84,132 @@ k_rowflags(int64_t P4, int nb, int64_t P, const uint16_t* __restrict__ cov, uint
     reinterpret_cast<uint4*>(rowflag)[g] = out;
 }
 
-__device__ __forceinline__ double site_score(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4,
-                                             uint32_t cs, bool dropped, bool touched, unsigned refb,
-                                             const double* __restrict__ table, double score0) {
-    if (dropped) return 0.0;
-    if (cs >= (uint32_t)FREEZE) return TINY;
-    if (!touched) return score0;
-    return __ldg(table + (size_t)pattern_rank(c0, c1, c2, c3, c4) * 4 + refb);
+constexpr int SB_THREADS = 256;      // 250 active threads x 8 sites = one 2000-site tile
+constexpr int SB_SITES = 8;
+
+// Table row of one site. Branch-free: the special cases select a ROW, not a value, so every site costs
+// one 8-byte gather. s_T[k][p] = C(p + k + 1, k + 2) are the binomials of the pattern rank (table.cuh).
+// Without barcodes "row never observed" is the all-zero pattern itself, so table row 0 holds the contig's
+// score0 in that case (patched at create) and no extra select is needed.
+template <bool MULTI>
+__device__ __forceinline__ uint32_t site_row(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4, uint32_t flag,
+                                             int32_t thr, const uint32_t (*s_T)[FREEZE], uint32_t& depth, uint32_t& dropped) {
+    const uint32_t p1 = c0, p2 = p1 + c1, p3 = p2 + c2, p4 = p3 + c3, cs = p4 + c4;
+    depth = cs;
+    // clamped prefixes keep the shared-memory lookups in range when the site is frozen
+    const uint32_t rank = min(p1, 29u) + s_T[0][min(p2, 29u)] + s_T[1][min(p3, 29u)] + s_T[2][min(p4, 29u)] +
+                          s_T[3][min(cs, 29u)];
+    uint32_t row = cs < (uint32_t)FREEZE ? rank : (uint32_t)ROW_TINY;
+    if (MULTI) row = (flag >> 31) ? row : (uint32_t)ROW_SCORE0;
+    const int32_t row_min = MULTI ? (int32_t)(flag & 0x7FFFFFFFu) : (int32_t)cs;
+    const bool drop = row_min <= thr;                    // thr = -1 while the depth rule is inactive
+    dropped = drop ? 1u : 0u;
+    return drop ? (uint32_t)ROW_ZERO : row;
 }
 
 // grid = (tiles, nb); one CTA = 2000 consecutive sites of one segment for one barcode
 template <bool MULTI>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(SB_THREADS)
 k_score_bin(ScoreArgs a) {
     __shared__ double s_part[TILE / 4];
-    __shared__ unsigned s_cov[TILE_THREADS / 32];
-    __shared__ unsigned s_drop[TILE_THREADS / 32];
+    __shared__ uint32_t s_T[4][FREEZE];
+    __shared__ unsigned s_cov, s_drop;
 
-    const int64_t tile = blockIdx.x;
+    const TileDesc td = a.tiles[blockIdx.x];
     const int b = blockIdx.y;
-    const int sg = find_segment(a.tile_start, a.n_seg, tile);
-    const SegDev S = a.segs[sg];
-    const int64_t local0 = (tile - S.tile_off) * TILE;         // first site of the tile within the segment
     const int t = threadIdx.x;
-    const int32_t thr = a.drop_thr[S.contig];
-    const bool rule = thr >= 0;
+    if (t < 4 * FREEZE) {
+        const int k = t / FREEZE, p = t - k * FREEZE;
+        const int64_t q = p + k + 1;
+        s_T[k][p] = (uint32_t)(k == 0 ? binom2(q) : k == 1 ? binom3(q) : k == 2 ? binom4(q) : binom5(q));
+    }
+    if (t == 0) { s_cov = 0; s_drop = 0; }
+    __syncthreads();
+    const int32_t thr_i = a.drop_thr[td.contig];        // -1 while the depth rule is inactive
 
     unsigned covsum = 0, ndrop = 0;
-    if (t < TILE / 4) {
-        const int64_t l = local0 + 4 * t;
-        double part = 0.0;
-        if (l < S.len) {
-            const size_t g = (size_t)(S.site_off + l) >> 2;
+    if (t < TILE / SB_SITES) {
+        const int l = SB_SITES * t;
+        double part0 = 0.0, part1 = 0.0;
+        if (l < td.n_sites) {
+            const size_t g = ((size_t)td.site_off >> 3) + t;             // 8-site group on the padded axis
             const uint16_t* plane = a.cov + (size_t)b * 5 * a.P;
-            uint2 v0 = __ldg(reinterpret_cast<const uint2*>(plane) + g);
-            uint2 v1 = __ldg(reinterpret_cast<const uint2*>(plane + a.P) + g);
-            uint2 v2 = __ldg(reinterpret_cast<const uint2*>(plane + 2 * a.P) + g);
-            uint2 v3 = __ldg(reinterpret_cast<const uint2*>(plane + 3 * a.P) + g);
-            uint2 v4 = __ldg(reinterpret_cast<const uint2*>(plane + 4 * a.P) + g);
-            uint32_t rb = __ldg(reinterpret_cast<const uint32_t*>(a.ref) + g);
-            uint4 rf = make_uint4(0, 0, 0, 0);
-            if (MULTI) rf = __ldg(reinterpret_cast<const uint4*>(a.rowflag) + g);
-            const uint32_t rfv[4] = {rf.x, rf.y, rf.z, rf.w};
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(plane) + g);
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(plane + a.P) + g);
+            const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(plane + 2 * a.P) + g);
+            const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(plane + 3 * a.P) + g);
+            const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(plane + 4 * a.P) + g);
+            const uint2 rb = __ldg(reinterpret_cast<const uint2*>(a.ref) + g);
+            uint4 f0 = make_uint4(0, 0, 0, 0), f1 = make_uint4(0, 0, 0, 0);
+            if (MULTI) {
+                f0 = __ldg(reinterpret_cast<const uint4*>(a.rowflag) + 2 * g);
+                f1 = __ldg(reinterpret_cast<const uint4*>(a.rowflag) + 2 * g + 1);
+            }
+            const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w},
+                           w2[4] = {v2.x, v2.y, v2.z, v2.w}, w3[4] = {v3.x, v3.y, v3.z, v3.w},
+                           w4[4] = {v4.x, v4.y, v4.z, v4.w};
+            const uint32_t fl[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            const int nvalid = td.n_sites - l;                           // >= 8 except in a contig's last tile
+            double s[SB_SITES];
+            uint32_t c[SB_SITES][5], cs[SB_SITES], mx = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t w0 = i < 2 ? v0.x : v0.y, w1 = i < 2 ? v1.x : v1.y, w2 = i < 2 ? v2.x : v2.y,
-                               w3 = i < 2 ? v3.x : v3.y, w4 = i < 2 ? v4.x : v4.y;
-                const int sh = (i & 1) * 16;
-                const uint32_t c0 = (w0 >> sh) & 0xFFFFu, c1 = (w1 >> sh) & 0xFFFFu, c2 = (w2 >> sh) & 0xFFFFu,
-                               c3 = (w3 >> sh) & 0xFFFFu, c4 = (w4 >> sh) & 0xFFFFu;
-                const uint32_t cs = c0 + c1 + c2 + c3 + c4;
-                const bool in = l + i < S.len;
-                uint32_t row_min = cs;
-                bool touched = cs > 0;
-                if (MULTI) { row_min = rfv[i] & 0x7FFFFFFFu; touched = (rfv[i] >> 31) != 0; }
-                const bool dropped = rule && row_min <= (uint32_t)thr;
-                const double s = site_score(c0, c1, c2, c3, c4, cs, dropped, touched, (rb >> (8 * i)) & 0xFFu,
-                                            a.table, a.score0);
-                if (in) {
-                    part += s;                  // sites of one thread are added in position order
-                    covsum += cs;
-                    ndrop += dropped ? 1u : 0u;
+            for (int i = 0; i < SB_SITES; ++i) {
+                const int wi = i >> 1;
+                if (i & 1) { c[i][0] = w0[wi] >> 16; c[i][1] = w1[wi] >> 16; c[i][2] = w2[wi] >> 16; c[i][3] = w3[wi] >> 16; c[i][4] = w4[wi] >> 16; }
+                else { c[i][0] = w0[wi] & 0xFFFFu; c[i][1] = w1[wi] & 0xFFFFu; c[i][2] = w2[wi] & 0xFFFFu; c[i][3] = w3[wi] & 0xFFFFu; c[i][4] = w4[wi] & 0xFFFFu; }
+                cs[i] = c[i][0] + c[i][1] + c[i][2] + c[i][3] + c[i][4];
+                mx = max(mx, cs[i]);
+                covsum += cs[i];                                         // padding counters are zero
+            }
+            if (!MULTI && mx < (uint32_t)FREEZE && nvalid >= SB_SITES) {
+                // common case: no frozen site, no padding -> no clamps, no special rows except "dropped"
+#pragma unroll
+                for (int i = 0; i < SB_SITES; ++i) {
+                    const uint32_t p2 = c[i][0] + c[i][1], p3 = p2 + c[i][2], p4 = p3 + c[i][3];
+                    const uint32_t rank = c[i][0] + s_T[0][p2] + s_T[1][p3] + s_T[2][p4] + s_T[3][cs[i]];
+                    const bool drop = (int32_t)cs[i] <= thr_i;
+                    const uint32_t row = drop ? (uint32_t)ROW_ZERO : rank;
+                    const uint32_t refb = ((i < 4 ? rb.x : rb.y) >> (8 * (i & 3))) & 0xFFu;
+                    s[i] = __ldg(a.table + (size_t)(row * 4 + refb));
+                    ndrop += drop ? 1u : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < SB_SITES; ++i) {
+                    uint32_t depth, dropped;
+                    uint32_t row = site_row<MULTI>(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4], fl[i], thr_i, s_T, depth, dropped);
+                    if (i >= nvalid) { row = ROW_ZERO; dropped = 0; }    // padding behind the contig end
+                    const uint32_t refb = ((i < 4 ? rb.x : rb.y) >> (8 * (i & 3))) & 0xFFu;
+                    s[i] = __ldg(a.table + (size_t)(row * 4 + refb));
+                    ndrop += dropped;
                 }
             }
+            part0 = ((s[0] + s[1]) + s[2]) + s[3];                       // position order within a thread
+            part1 = ((s[4] + s[5]) + s[6]) + s[7];
         }
-        s_part[t] = part;
+        s_part[2 * t] = part0;
+        s_part[2 * t + 1] = part1;
     }
-    // block sums of depth (for the bucket means) and of dropped rows (for the log line)
-    for (int o = 16; o > 0; o >>= 1) {
-        covsum += __shfl_down_sync(0xFFFFFFFFu, covsum, o);
-        ndrop += __shfl_down_sync(0xFFFFFFFFu, ndrop, o);
+    // block sums of depth (bucket means) and dropped rows (log line)
+    covsum = __reduce_add_sync(0xFFFFFFFFu, covsum);
+    ndrop = __reduce_add_sync(0xFFFFFFFFu, ndrop);
+    if ((t & 31) == 0) {
+        if (covsum) atomicAdd(&s_cov, covsum);
+        if (ndrop) atomicAdd(&s_drop, ndrop);
     }
-    if ((t & 31) == 0) { s_cov[t >> 5] = covsum; s_drop[t >> 5] = ndrop; }
     __syncthreads();
 
     if (t < TILE / BIN) {
-        // bin j of the tile = 25 consecutive thread partials, added in position order
-        const int64_t bin = local0 / BIN + t;
-        if (bin < S.n_bins) {
+        // bin j of the tile = 25 consecutive 4-site partials, added in position order
+        if (t < td.n_bins) {
             double acc = 0.0;
 #pragma unroll 5
             for (int k = 0; k < 25; ++k) acc += s_part[25 * t + k];
-            a.ds[(size_t)b * a.ds_len + S.ds_off + bin] = acc;
+            a.ds[(size_t)b * a.ds_len + td.ds_index + t] = acc;
         }
     } else if (t == 32) {
-        unsigned long long tot = 0, dr = 0;
-        for (int w = 0; w < TILE_THREADS / 32; ++w) { tot += s_cov[w]; dr += s_drop[w]; }
-        const int64_t bucket = local0 / BUCKET;
-        if (bucket < S.n_full_buckets && tot) atomicAdd(&a.bucket_sum[(size_t)(S.sw_off + bucket) * a.nb + b], tot);
-        if (dr && b == 0) atomicAdd(a.n_dropout, dr);
+        if (td.bucket >= 0 && s_cov) atomicAdd(&a.bucket_sum[(size_t)td.bucket * a.nb + b], (unsigned long long)s_cov);
+        if (s_drop && b == 0) atomicAdd(a.n_dropout, (unsigned long long)s_drop);
     }
 }
 

@@ -21,9 +21,11 @@ namespace boss {
 
 constexpr int SM_TILE = 256;   // output bins per CTA in the smoothing kernel
 
+constexpr int SM_MAX_PIECES = 192;
+constexpr int SM_MAX_LEVELS = 14;
+
 struct SmoothArgs {
     const SegDev* segs;
-    const int64_t* row_start;     // [n_seg+1] merged rows (local)
     int n_seg, nb;
     const double* ds;
     int64_t ds_len;
@@ -31,17 +33,46 @@ struct SmoothArgs {
     double2* smu;                 // optional
     double2* expected;            // optional
     int64_t n_rows;
-    int32_t w[NSTEPS];            // non-decreasing
     double mult[NSTEPS];
     int32_t wmax;                 // max(w[9], 4)
+    int32_t n_levels;             // sliding power-of-two sums kept in shared memory: widths 1, 2, ..., 2^(n_levels-1)
+    // the ten nested boxes as a list of power-of-two pieces: piece p adds the 2^lvl[p] bins starting off[p] bins
+    // ahead (forward strand) / ending off[p] bins behind (reverse strand); step i ends before piece step_end[i]
+    int32_t step_end[NSTEPS];
+    int16_t piece_off[SM_MAX_PIECES];
+    int8_t  piece_lvl[SM_MAX_PIECES];
     int64_t R0, target_rows;      // rows >= target are cut by adjust_length (core.py:179-181)
     UpdateDev* upd;
 };
 
-// grid = (ceil(bins/SM_TILE) per segment flattened, nb). Dynamic smem: (SM_TILE + 2*(wmax-1)) doubles.
+// Host side: split the increments between consecutive staircase windows into power-of-two pieces.
+inline bool plan_smoothing(const int32_t w[NSTEPS], int max_levels, SmoothArgs& a) {
+    int n = 0, prev = 0;
+    for (int i = 0; i < NSTEPS; ++i) {
+        int off = prev, d = w[i] - prev;
+        while (d > 0) {
+            int k = 0;
+            while (k + 1 < max_levels && (2 << k) <= d) ++k;     // largest kept width <= d
+            if (n >= SM_MAX_PIECES || off > 32767) return false;
+            a.piece_off[n] = (int16_t)off;
+            a.piece_lvl[n] = (int8_t)k;
+            ++n;
+            off += 1 << k;
+            d -= 1 << k;
+        }
+        a.step_end[i] = n;
+        prev = w[i];
+    }
+    return true;
+}
+
+// grid = (ceil(bins/SM_TILE) per segment flattened, nb).
+// Dynamic smem: n_levels * (SM_TILE + 2*(wmax-1)) doubles. Level k holds, for every position, the sum of the
+// 2^k bins starting there (built by doubling), so a box of width w costs popcount-many loads instead of w.
+// Every window is still summed from the bins themselves — no running accumulator, no cancellation.
 __global__ void __launch_bounds__(SM_TILE)
 k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
-    extern __shared__ double s_ds[];
+    extern __shared__ double s_lv[];
     __shared__ unsigned long long s_max;
     const int b = blockIdx.y;
     const int sg = find_segment(sm_tile_start, a.n_seg, blockIdx.x);
@@ -57,23 +88,36 @@ k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
         int64_t j = j0 - halo + i;
         double v = 0.0;
         if (j >= -(int64_t)S.halo_l && j < S.n_bins + S.halo_r) v = src[j];
-        s_ds[i] = v;
+        s_lv[i] = v;
     }
     __syncthreads();
+    for (int k = 1; k < a.n_levels; ++k) {
+        const double* lo = s_lv + (size_t)(k - 1) * span;
+        double* hi = s_lv + (size_t)k * span;
+        const int half = 1 << (k - 1);
+        for (int i = threadIdx.x; i + 2 * half <= span; i += SM_TILE) hi[i] = lo[i] + lo[i + half];
+        __syncthreads();
+    }
     const int64_t j = j0 + threadIdx.x;
     unsigned long long mybits = 0ull;
     if (j < S.n_bins) {
-        const double* c = s_ds + halo + threadIdx.x;
+        const int c = halo + threadIdx.x;
+        const double* A0 = s_lv + c;
         // S_mu: 4-bin forward / backward box (reference.py:233-237)
-        const double smu_f = ((c[0] + c[1]) + c[2]) + c[3];
-        const double smu_r = ((c[0] + c[-1]) + c[-2]) + c[-3];
+        const double smu_f = ((A0[0] + A0[1]) + A0[2]) + A0[3];
+        const double smu_r = ((A0[0] + A0[-1]) + A0[-2]) + A0[-3];
         // staircase: sum_i mult_i * box_{w_i}; the boxes are nested, so one running sum per strand
         double run_f = 0.0, run_r = 0.0, eb_f = 0.0, eb_r = 0.0;
-        int k = 0;
+        int p = 0;
 #pragma unroll 1
         for (int i = 0; i < NSTEPS; ++i) {
-            const int wi = a.w[i];
-            for (; k < wi; ++k) { run_f += c[k]; run_r += c[-k]; }
+            const int pe = a.step_end[i];
+            for (; p < pe; ++p) {
+                const int off = a.piece_off[p], k = a.piece_lvl[p];
+                const double* L = s_lv + (size_t)k * span + c;
+                run_f += L[off];
+                run_r += L[-off - (1 << k) + 1];
+            }
             eb_f += run_f * a.mult[i];
             eb_r += run_r * a.mult[i];
         }
@@ -86,6 +130,64 @@ k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
         if (a.expected) a.expected[o] = make_double2(eb_f, eb_r);
         if (a.R0 + S.row_off + j < a.target_rows) {
             // non-negative doubles order like their bit patterns; NaN would sort above everything
+            unsigned long long bf = (unsigned long long)__double_as_longlong(ad_f);
+            unsigned long long br = (unsigned long long)__double_as_longlong(ad_r);
+            mybits = bf > br ? bf : br;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xFFFFFFFFu, mybits, o);
+        mybits = other > mybits ? other : mybits;
+    }
+    if ((threadIdx.x & 31) == 0 && mybits) atomicMax(&s_max, mybits);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(&a.upd->norm_bits, s_max);
+}
+
+// Fallback for very long staircases (ultra-long reads) whose piece list or level arrays do not fit:
+// every box is summed bin by bin from one staged copy of the tile.
+__global__ void __launch_bounds__(SM_TILE)
+k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const int32_t* __restrict__ w) {
+    extern __shared__ double s_lv[];
+    __shared__ unsigned long long s_max;
+    const int b = blockIdx.y;
+    const int sg = find_segment(sm_tile_start, a.n_seg, blockIdx.x);
+    const SegDev S = a.segs[sg];
+    const int64_t j0 = (blockIdx.x - sm_tile_start[sg]) * SM_TILE;
+    const int halo = a.wmax - 1;
+    const int span = SM_TILE + 2 * halo;
+    const double* src = a.ds + (size_t)b * a.ds_len + S.ds_off;
+    if (threadIdx.x == 0) s_max = 0ull;
+    for (int i = threadIdx.x; i < span; i += SM_TILE) {
+        int64_t j = j0 - halo + i;
+        double v = 0.0;
+        if (j >= -(int64_t)S.halo_l && j < S.n_bins + S.halo_r) v = src[j];
+        s_lv[i] = v;
+    }
+    __syncthreads();
+    const int64_t j = j0 + threadIdx.x;
+    unsigned long long mybits = 0ull;
+    if (j < S.n_bins) {
+        const double* c = s_lv + halo + threadIdx.x;
+        const double smu_f = ((c[0] + c[1]) + c[2]) + c[3];
+        const double smu_r = ((c[0] + c[-1]) + c[-2]) + c[-3];
+        double run_f = 0.0, run_r = 0.0, eb_f = 0.0, eb_r = 0.0;
+        int k = 0;
+#pragma unroll 1
+        for (int i = 0; i < NSTEPS; ++i) {
+            const int wi = w[i];
+            for (; k < wi; ++k) { run_f += c[k]; run_r += c[-k]; }
+            eb_f += run_f * a.mult[i];
+            eb_r += run_r * a.mult[i];
+        }
+        double ad_f = eb_f - smu_f, ad_r = eb_r - smu_r;
+        if (ad_f < 0.0) ad_f = 0.0;
+        if (ad_r < 0.0) ad_r = 0.0;
+        const size_t o = (size_t)b * a.n_rows + S.row_off + j;
+        a.benefit[o] = make_double2(ad_f, ad_r);
+        if (a.smu) a.smu[o] = make_double2(smu_f, smu_r);
+        if (a.expected) a.expected[o] = make_double2(eb_f, eb_r);
+        if (a.R0 + S.row_off + j < a.target_rows) {
             unsigned long long bf = (unsigned long long)__double_as_longlong(ad_f);
             unsigned long long br = (unsigned long long)__double_as_longlong(ad_r);
             mybits = bf > br ? bf : br;
@@ -180,14 +282,29 @@ struct HistArgs {
     UpdateDev* upd;
 };
 
-__device__ __forceinline__ int abs_frexp_exponent(double x) {
-    // |e| with x = m * 2^e, 0.5 <= m < 1 (np.frexp + np.abs, sequences.py:590-593), x > 0 finite
+// |e| with x/norm = m * 2^e, 0.5 <= m < 1 (np.frexp + np.abs, sequences.py:589-593), for 0 < x <= norm.
+// Both operands normal and the quotient far from the subnormal range: the exponent follows from the two
+// exponent fields and one mantissa comparison (the correctly rounded quotient of mantissas stays on its
+// side of 1), no division needed. Anything else takes the literal path.
+__device__ __forceinline__ int abs_exponent_of_ratio(double x, double norm, unsigned long long nbits) {
+    const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+    const int ex = (int)(xb >> 52), en = (int)(nbits >> 52);
     int e;
-    frexp(x, &e);
+    if (ex != 0 && en != 0 && ex - en > -1000) {
+        e = ex - en + ((xb & 0xFFFFFFFFFFFFFull) >= (nbits & 0xFFFFFFFFFFFFFull) ? 1 : 0);
+    } else {
+        frexp(x / norm, &e);
+    }
     return e < 0 ? -e : e;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_ROWS_PER_THREAD = 32;
+
+// One thread walks rows base+t, base+t+256, ...; consecutive rows of a thread are 25.6 kb apart and mostly
+// fall into the same binary-exponent bin, so the current bin is accumulated in registers and only written
+// to the CTA's shared histogram (integer atomics) when the bin changes.
+__global__ void __launch_bounds__(HIST_THREADS)
 k_hist(HistArgs a) {
     __shared__ unsigned s_cnt[HBINS];
     __shared__ unsigned long long s_hi[HBINS];
@@ -197,39 +314,56 @@ k_hist(HistArgs a) {
     if (threadIdx.x < 3) s_u[threadIdx.x] = 0;
     __syncthreads();
 
-    const double norm = __longlong_as_double((long long)a.upd->norm_bits);
+    const unsigned long long nbits = a.upd->norm_bits;
+    const double norm = __longlong_as_double((long long)nbits);
     const double scale = a.upd->fhat_scale;
     int norm_e;
     frexp(norm, &norm_e);                       // norm < 2^norm_e  =>  fhat*b*2^(shift-norm_e) < fhat*2^shift
+    const double two_shift = ldexp(1.0, a.shift);
+    const int ue = a.shift - norm_e;
+    const bool ue_ok = ue > -1000 && ue < 1000;
+    const double two_ue = ue_ok ? ldexp(1.0, ue) : 0.0;
     const int b = blockIdx.y;
     const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail
     unsigned long long u_hi = 0, u_lo = 0, nnz = 0;
+    int cur = -1;
+    unsigned c_cnt = 0;
+    unsigned long long c_hi = 0, c_lo = 0;
 
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t base = (int64_t)blockIdx.x * (HIST_THREADS * HIST_ROWS_PER_THREAD);
+#pragma unroll 1
+    for (int k = 0; k < HIST_ROWS_PER_THREAD; ++k) {
+        const int64_t i = base + (int64_t)k * HIST_THREADS + threadIdx.x;
+        if (i >= a.n_rows) break;
         const int64_t r = a.R0 + i;
         const double2 v = a.benefit[(size_t)b * a.n_rows + i];
-#pragma unroll
+        if (v.x == 0.0 && v.y == 0.0) continue;                   // np.nonzero (sequences.py:585)
+#pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
             int64_t rr = r;
             if (rep == 0) { if (r >= a.target) continue; }
-            else { if (!(extra > 0 && r >= a.M - extra)) continue; rr = r + extra; }
+            else { if (!(extra > 0 && r >= a.M - extra)) break; rr = r + extra; }
             const int64_t win = fhat_window_of_row(a.fg, rr);
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const double x = s == 0 ? v.x : v.y;
-                if (x == 0.0) continue;                                   // np.nonzero (sequences.py:585)
+                if (x == 0.0) continue;
                 const double f = a.fw[2 * win + s] * scale;               // np.multiply(fhat_exp, normalizer)
-                const int e = abs_frexp_exponent(x / norm);
+                const int e = abs_exponent_of_ratio(x, norm, nbits);
                 unsigned long long h, l;
-                to_limbs(ldexp(f, a.shift), h, l);
-                atomicAdd(&s_cnt[e], 1u);
-                atomicAdd(&s_hi[e], h);
-                atomicAdd(&s_lo[e], l);
-                to_limbs(ldexp(f * x, a.shift - norm_e), h, l);           // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
+                to_limbs(f * two_shift, h, l);
+                if (e != cur) {
+                    if (c_cnt) { atomicAdd(&s_cnt[cur], c_cnt); atomicAdd(&s_hi[cur], c_hi); atomicAdd(&s_lo[cur], c_lo); }
+                    cur = e; c_cnt = 0; c_hi = 0; c_lo = 0;
+                }
+                c_cnt += 1; c_hi += h; c_lo += l;
+                const double t = f * x;                                   // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
+                to_limbs(ue_ok ? t * two_ue : ldexp(t, ue), h, l);
                 u_hi += h; u_lo += l; nnz++;
             }
         }
     }
+    if (c_cnt) { atomicAdd(&s_cnt[cur], c_cnt); atomicAdd(&s_hi[cur], c_hi); atomicAdd(&s_lo[cur], c_lo); }
     for (int o = 16; o > 0; o >>= 1) {
         u_hi += __shfl_down_sync(0xFFFFFFFFu, u_hi, o);
         u_lo += __shfl_down_sync(0xFFFFFFFFu, u_lo, o);
