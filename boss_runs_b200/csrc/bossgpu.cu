@@ -197,9 +197,9 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     A(dev_alloc(&h->d_srow_start, h->n_seg + 1));
     A(dev_alloc(&h->d_sm_tile_start, h->n_seg + 1));
     A(dev_alloc(&h->d_contig_len, h->n_contigs_total));
-    A(dev_alloc(&h->d_ref, (size_t)P));
-    A(dev_alloc(&h->d_cov, (size_t)h->nb * 5 * P));
-    if (h->nb > 1) A(dev_alloc(&h->d_rowflag, (size_t)P));
+    A(dev_alloc(&h->d_ref, (size_t)(P + SBT_TAIL_PAD)));
+    A(dev_alloc(&h->d_cov, (size_t)h->nb * 5 * P + SBT_TAIL_PAD));
+    if (h->nb > 1) A(dev_alloc(&h->d_rowflag, (size_t)(P + SBT_TAIL_PAD)));
     A(dev_alloc(&h->d_table, (size_t)(NPAT + 3) * 4));
     A(dev_alloc((TileDesc**)&h->d_tiles, (size_t)tiles));
     A(dev_alloc(&h->d_etable, (size_t)NPAT * 4));
@@ -293,6 +293,22 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         BOSS_CUDA(cudaMemcpy(h->d_tiles, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice));
     }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
+    BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 4)));
+    BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(true, 2)));
+    {
+        cudaDeviceProp prop;
+        BOSS_CUDA(cudaGetDeviceProperties(&prop, h->device));
+        h->n_sm = prop.multiProcessorCount;
+        const char* env = getenv("BOSSGPU_SCORE_KERNEL");       // development A/B switch: "ldg" = non-staged variant
+        h->score_kernel_ldg = env && strcmp(env, "ldg") == 0;
+        const char* e2 = getenv("BOSSGPU_SCORE_STAGES");
+        const char* e3 = getenv("BOSSGPU_SCORE_CTAS");
+        // measured on B200 (scripts/sweep_score.sh): 2 stages x 3 CTAs/SM beats 4 stages x 2 CTAs/SM — the table
+        // gathers want warps (and L1) more than the copies want depth
+        h->score_stages = e2 ? atoi(e2) : 2;
+        h->score_ctas_per_sm = e3 ? atoi(e3) : 3;
+    }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -552,17 +568,23 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     a.ref = h->d_ref; a.cov = h->d_cov; a.rowflag = h->d_rowflag; a.table = h->d_table; a.drop_thr = h->d_drop_thr;
     a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
     a.n_dropout = &h->d_upd->n_dropout;
-    dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
     EV_BEGIN(1);
     if (h->nb > 1) {
         k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
         BOSS_KERNEL_CHECK();
-        k_score_bin<true><<<grid, SB_THREADS, 0, h->stream>>>(a);
-        h->launches += 2;
-    } else {
-        k_score_bin<false><<<grid, SB_THREADS, 0, h->stream>>>(a);
         h->launches++;
     }
+    if (h->score_kernel_ldg) {
+        dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
+        if (h->nb > 1) k_score_bin<true><<<grid, SB_THREADS, 0, h->stream>>>(a);
+        else k_score_bin<false><<<grid, SB_THREADS, 0, h->stream>>>(a);
+    } else {
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), (unsigned)h->nb);
+        if (h->nb > 1) k_score_bin_tma<true, 2><<<grid, SBT_THREADS, sbt_smem_bytes(true, 2), h->stream>>>(a, h->n_tiles);
+        else if (h->score_stages == 4) k_score_bin_tma<false, 4><<<grid, SBT_THREADS, sbt_smem_bytes(false, 4), h->stream>>>(a, h->n_tiles);
+        else k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+    }
+    h->launches++;
     BOSS_KERNEL_CHECK();
     EV_END(1);
     EV_BEGIN(2);

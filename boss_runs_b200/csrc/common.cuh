@@ -164,6 +164,9 @@ struct bossgpu_handle {
     bool  ev_valid[BOSSGPU_N_TIMERS] = {false};
     int64_t launches = 0;
     int phase_done = -1;
+    int n_sm = 148;
+    bool score_kernel_ldg = false;
+    int score_stages = 2, score_ctas_per_sm = 3;
     // multi-shard exchange state (bossgpu_set_shards)
     int n_shards = 1, shard_index = 0;
     std::vector<int64_t> shard_row_start;

@@ -213,6 +213,227 @@ k_score_bin(ScoreArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged persistent variant of the pass (the one the library launches).
+//
+// One CTA = 8 consumer warps + 1 producer warp, grid = (min(tiles, 2 CTAs per SM), barcodes). The
+// producer's elected lane walks the CTA's tiles (tile = blockIdx.x + it * gridDim.x) and, four tiles ahead
+// of the consumers, arms the stage's "full" mbarrier with the byte count and issues the bulk copies
+// (cp.async.bulk global -> shared: 5 counter planes x 4000 B + 2000 B of reference bases, + 8000 B of row
+// flags with barcodes). Consumers wait on "full", score their 8 sites out of shared memory, release the
+// stage through the "empty" mbarrier and meet at a named barrier for the 100-site bin sums. HBM latency is
+// covered by ~88 KB of copies in flight per CTA instead of by occupancy.
+// ------------------------------------------------------------------------------------------------
+constexpr int SBT_CONSUMERS = 256;
+constexpr int SBT_THREADS = SBT_CONSUMERS + 32;
+constexpr int SBT_PLANE_BYTES = TILE * 2;                  // 4000
+constexpr int SBT_REF_OFF = 5 * SBT_PLANE_BYTES;           // 20000
+constexpr int SBT_FLAG_OFF = SBT_REF_OFF + 2048;           // 22048 (reference bases padded to 2048)
+constexpr int SBT_STAGE_BYTES = 22144;                     // multiple of 128, without row flags
+constexpr int SBT_STAGE_BYTES_MULTI = SBT_FLAG_OFF + TILE * 4 + 96;   // 30144
+constexpr int64_t SBT_TAIL_PAD = 2048;                     // elements allocated behind the site arrays: the last
+                                                           // tile of a segment is copied whole
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SBT_CONSUMERS) : "memory"); }
+
+template <bool MULTI, int SBT_STAGES>
+__global__ void __launch_bounds__(SBT_THREADS, 3)
+k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    constexpr int STAGE = MULTI ? SBT_STAGE_BYTES_MULTI : SBT_STAGE_BYTES;
+    unsigned char* s_stage = s_raw;
+    TileDesc* s_td = reinterpret_cast<TileDesc*>(s_raw + SBT_STAGES * STAGE);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_td + SBT_STAGES);     // full[4], empty[4]
+    double* s_part = reinterpret_cast<double*>(s_bar + 2 * SBT_STAGES);                       // [2][TILE/4]
+    uint32_t (*s_T)[FREEZE] = reinterpret_cast<uint32_t (*)[FREEZE]>(s_part + 2 * (TILE / 4));
+    unsigned* s_covw = reinterpret_cast<unsigned*>(s_T + 4);                                   // [2][8]
+    unsigned* s_dropw = s_covw + 16;                                                           // [2][8]
+
+    const int t = threadIdx.x;
+    const int b = blockIdx.y;
+    if (t < 4 * FREEZE) {
+        const int k = t / FREEZE, p = t - k * FREEZE;
+        const int64_t q = p + k + 1;
+        s_T[k][p] = (uint32_t)(k == 0 ? binom2(q) : k == 1 ? binom3(q) : k == 2 ? binom4(q) : binom5(q));
+    }
+    if (t == 0) {
+        for (int s = 0; s < SBT_STAGES; ++s) {
+            mbar_init(smem_u32(&s_bar[s]), 1);                              // full: the producer's expect_tx arrival
+            mbar_init(smem_u32(&s_bar[SBT_STAGES + s]), SBT_CONSUMERS / 32); // empty: one arrival per consumer warp
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // make the inits visible to the copy engine
+    }
+    __syncthreads();
+
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+
+    if (t >= SBT_CONSUMERS) {
+        // ------------------------------- producer warp -------------------------------
+        if (t == SBT_CONSUMERS) {
+            const uint16_t* plane0 = a.cov + (size_t)b * 5 * a.P;
+            int it = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+                const int stage = it % SBT_STAGES;
+                const uint32_t full = smem_u32(&s_bar[stage]), empty = smem_u32(&s_bar[SBT_STAGES + stage]);
+                if (it >= SBT_STAGES) mbar_wait(empty, ((it / SBT_STAGES) - 1) & 1);
+                const TileDesc td = a.tiles[tile];
+                s_td[stage] = td;
+                const uint32_t dst = smem_u32(s_stage + (size_t)stage * STAGE);
+                mbar_expect_tx(full, MULTI ? (5 * SBT_PLANE_BYTES + TILE + TILE * 4) : (5 * SBT_PLANE_BYTES + TILE));
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    bulk_g2s(dst + k * SBT_PLANE_BYTES, plane0 + (size_t)k * a.P + td.site_off, SBT_PLANE_BYTES, full);
+                bulk_g2s(dst + SBT_REF_OFF, a.ref + td.site_off, TILE, full);
+                if (MULTI) bulk_g2s(dst + SBT_FLAG_OFF, a.rowflag + td.site_off, TILE * 4, full);
+            }
+        }
+        return;
+    }
+
+    // ----------------------------------- consumers -----------------------------------
+    int it = 0, buf = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it, buf ^= 1) {
+        const int stage = it % SBT_STAGES;
+        mbar_wait(smem_u32(&s_bar[stage]), (it / SBT_STAGES) & 1);
+        const TileDesc td = s_td[stage];
+        const unsigned char* sb = s_stage + (size_t)stage * STAGE;
+        const int32_t thr_i = a.drop_thr[td.contig];        // -1 while the depth rule is inactive
+        double* part = s_part + buf * (TILE / 4);
+        unsigned covsum = 0, ndrop = 0;
+        // pull this thread's 8 sites out of the stage, then hand the stage back to the producer at once:
+        // the rest of the iteration works from registers
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0, v4 = v0, f0 = v0, f1 = v0;
+        uint2 rb = make_uint2(0, 0);
+        if (t < TILE / SB_SITES) {
+            v0 = reinterpret_cast<const uint4*>(sb)[t];
+            v1 = reinterpret_cast<const uint4*>(sb + SBT_PLANE_BYTES)[t];
+            v2 = reinterpret_cast<const uint4*>(sb + 2 * SBT_PLANE_BYTES)[t];
+            v3 = reinterpret_cast<const uint4*>(sb + 3 * SBT_PLANE_BYTES)[t];
+            v4 = reinterpret_cast<const uint4*>(sb + 4 * SBT_PLANE_BYTES)[t];
+            rb = reinterpret_cast<const uint2*>(sb + SBT_REF_OFF)[t];
+            if (MULTI) {
+                f0 = reinterpret_cast<const uint4*>(sb + SBT_FLAG_OFF)[2 * t];
+                f1 = reinterpret_cast<const uint4*>(sb + SBT_FLAG_OFF)[2 * t + 1];
+            }
+        }
+        {
+            // the arrival must not overtake the loads: fold every loaded word into a value the arriving lane needs
+            const unsigned seen = v0.x ^ v0.y ^ v0.z ^ v0.w ^ v1.x ^ v1.y ^ v1.z ^ v1.w ^ v2.x ^ v2.y ^ v2.z ^ v2.w ^ v3.x ^ v3.y ^
+                                  v3.z ^ v3.w ^ v4.x ^ v4.y ^ v4.z ^ v4.w ^ rb.x ^ rb.y ^ f0.x ^ f0.y ^ f0.z ^ f0.w ^ f1.x ^ f1.y ^
+                                  f1.z ^ f1.w;
+            const unsigned all_seen = __reduce_or_sync(0xFFFFFFFFu, seen);
+            if ((t & 31) == 0) {
+                asm volatile("" ::"r"(all_seen) : "memory");
+                mbar_arrive(smem_u32(&s_bar[SBT_STAGES + stage]));       // this warp is done with the stage
+            }
+        }
+        if (t < TILE / SB_SITES) {
+            const int l = SB_SITES * t;
+            double part0 = 0.0, part1 = 0.0;
+            if (l < td.n_sites) {
+                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w},
+                               w2[4] = {v2.x, v2.y, v2.z, v2.w}, w3[4] = {v3.x, v3.y, v3.z, v3.w},
+                               w4[4] = {v4.x, v4.y, v4.z, v4.w};
+                const uint32_t fl[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                const int nvalid = td.n_sites - l;                       // >= 8 except in a contig's last tile
+                double s[SB_SITES];
+                uint32_t c[SB_SITES][5], cs[SB_SITES], mx = 0;
+#pragma unroll
+                for (int i = 0; i < SB_SITES; ++i) {
+                    const int wi = i >> 1;
+                    if (i & 1) { c[i][0] = w0[wi] >> 16; c[i][1] = w1[wi] >> 16; c[i][2] = w2[wi] >> 16; c[i][3] = w3[wi] >> 16; c[i][4] = w4[wi] >> 16; }
+                    else { c[i][0] = w0[wi] & 0xFFFFu; c[i][1] = w1[wi] & 0xFFFFu; c[i][2] = w2[wi] & 0xFFFFu; c[i][3] = w3[wi] & 0xFFFFu; c[i][4] = w4[wi] & 0xFFFFu; }
+                    cs[i] = c[i][0] + c[i][1] + c[i][2] + c[i][3] + c[i][4];
+                    mx = max(mx, cs[i]);
+                }
+                if (!MULTI && mx < (uint32_t)FREEZE && nvalid >= SB_SITES) {
+                    // common case: no frozen site, no padding -> no clamps, no special rows except "dropped".
+                    // The 30-entry binomial tables sit in 30 different banks: lookups never conflict.
+#pragma unroll
+                    for (int i = 0; i < SB_SITES; ++i) {
+                        const uint32_t p2 = c[i][0] + c[i][1], p3 = p2 + c[i][2], p4 = p3 + c[i][3];
+                        const uint32_t rank = c[i][0] + s_T[0][p2] + s_T[1][p3] + s_T[2][p4] + s_T[3][cs[i]];
+                        const bool drop = (int32_t)cs[i] <= thr_i;
+                        const uint32_t row = drop ? (uint32_t)ROW_ZERO : rank;
+                        const uint32_t refb = ((i < 4 ? rb.x : rb.y) >> (8 * (i & 3))) & 0xFFu;
+                        s[i] = __ldg(a.table + (size_t)(row * 4 + refb));
+                        ndrop += drop ? 1u : 0u;
+                        covsum += cs[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SB_SITES; ++i) {
+                        uint32_t depth, dropped;
+                        uint32_t row = site_row<MULTI>(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4], fl[i], thr_i, s_T, depth, dropped);
+                        if (i >= nvalid) { row = ROW_ZERO; dropped = 0; depth = 0; }   // whatever follows the contig end
+                        const uint32_t refb = ((i < 4 ? rb.x : rb.y) >> (8 * (i & 3))) & 0xFFu;
+                        s[i] = __ldg(a.table + (size_t)(row * 4 + (refb & 3u)));
+                        ndrop += dropped;
+                        covsum += depth;
+                    }
+                }
+                part0 = ((s[0] + s[1]) + s[2]) + s[3];                   // position order within a thread
+                part1 = ((s[4] + s[5]) + s[6]) + s[7];
+            }
+            part[2 * t] = part0;
+            part[2 * t + 1] = part1;
+        }
+        covsum = __reduce_add_sync(0xFFFFFFFFu, covsum);
+        ndrop = __reduce_add_sync(0xFFFFFFFFu, ndrop);
+        if ((t & 31) == 0) {
+            s_covw[buf * 8 + (t >> 5)] = covsum;
+            s_dropw[buf * 8 + (t >> 5)] = ndrop;
+        }
+        consumer_bar();
+        if (t < TILE / BIN) {
+            // bin j of the tile = 25 consecutive 4-site partials, added in position order
+            if (t < td.n_bins) {
+                double acc = 0.0;
+#pragma unroll 5
+                for (int k = 0; k < 25; ++k) acc += part[25 * t + k];
+                a.ds[(size_t)b * a.ds_len + td.ds_index + t] = acc;
+            }
+        } else if (t == 32) {
+            unsigned cov = 0, dr = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { cov += s_covw[buf * 8 + w]; dr += s_dropw[buf * 8 + w]; }
+            if (td.bucket >= 0 && cov) atomicAdd(&a.bucket_sum[(size_t)td.bucket * a.nb + b], (unsigned long long)cov);
+            if (dr && b == 0) atomicAdd(a.n_dropout, (unsigned long long)dr);
+        }
+    }
+}
+
+constexpr size_t sbt_smem_bytes(bool multi, int SBT_STAGES) {
+    return (size_t)SBT_STAGES * (multi ? SBT_STAGE_BYTES_MULTI : SBT_STAGE_BYTES) + SBT_STAGES * sizeof(TileDesc) +
+           2 * SBT_STAGES * sizeof(unsigned long long) + 2 * (TILE / 4) * sizeof(double) + 4 * FREEZE * sizeof(uint32_t) +
+           32 * sizeof(unsigned) + 64;
+}
+
 // per-contig dropout threshold from the running depth total (reference.py:157-158,175-177):
 // mean = total / (L * nb); active iff mean > 5; thr = int(mean / 8)
 __global__ void k_drop_thresholds(int n_contigs, const int64_t* __restrict__ contig_len, int nb,
