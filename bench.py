@@ -255,7 +255,7 @@ def run_b200(args, spec):
         batches.append((pd, rb.seqs, rb))
     run.rl_dist.update({rid: recs[0].qlen for pd, _, _ in batches for rid, recs in pd.items()})
     for pd, _, _ in batches:
-        run.read_starts.count_read_starts(pd)
+        run.count_read_starts(pd)
     setup_s = time.time() - t_setup
 
     def barrier():
@@ -265,20 +265,24 @@ def run_b200(args, spec):
         torch.cuda.synchronize()
 
     # ---- leg 1: end to end through the public API, host buffers ------------------------------------------
-    e2e_times = []
+    e2e_times, e2e_parts = [], []
     h2d = d2h = 0
     for it in range(args.warmup + args.steps):
         pd, seqs, rb = batches[it % n_batches]
         barrier()
         t0 = time.perf_counter()
         inc = run.cc.convert_records(paf_dict=pd, seqs=seqs)
+        t1 = time.perf_counter()
         run._effect_increments(inc)
+        t2 = time.perf_counter()
         run.update_wrapper()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             e2e_times.append(dt)
-            h2d = (len(inc.cigar_text) // 2 * 4 + len(inc.seq_text) + len(inc) * 40 + eng.n_windows_total * 16)
+            e2e_parts.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
+            # packed CIGAR ops (4 B each, ~1 per 2 text characters) + aligned read bases + per-read scalars
+            h2d = int(inc.cigar_len.sum()) // 2 * 4 + int((inc.seq_to - inc.seq_from).sum()) + len(inc) * 40
             d2h = int(sum(c.strat.size for c in run.contigs_filt.values())) + 128
     e2e_t = torch.tensor([float(np.mean(e2e_times))], device="cuda")
     if world > 1:
@@ -363,7 +367,10 @@ def run_b200(args, spec):
                    "reads_per_batch": spec["reads"], "l2": "inputs (counters >= 46 MB ... 31 GB) exceed L2; 3 batches cycled",
                    "sharding": f"genome axis split over {world} GPU(s)"},
         "e2e": {"value": total_sites / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+                "d2h_bytes_per_step": int(d2h),
+                "host_ms": dict(zip(("convert_records", "ingest", "update_wrapper"),
+                                    (float(x) * 1e3 for x in np.mean(np.array(e2e_parts), axis=0)))),
+                "update_wrapper_ms": getattr(run, "last_host_ms", None)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_score_bin", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"

@@ -46,7 +46,8 @@ class Config(C.Structure):
 class UpdateParams(C.Structure):
     _fields_ = [("w", C.c_int32 * N_STEPS), ("mult", C.c_double * N_STEPS), ("tc", C.c_double),
                 ("bucket_threshold", C.c_double), ("fhat_windows", C.c_void_p),
-                ("write_debug", C.c_int32), ("reserved", C.c_int32)]
+                ("write_debug", C.c_int32), ("fhat_from_counts", C.c_int32),
+                ("rs_alpha", C.c_double), ("rs_denom", C.c_double), ("rs_zero_value", C.c_double)]
 
 
 class UpdateResult(C.Structure):
@@ -66,6 +67,11 @@ SYMBOLS = {
     "bossgpu_synchronize": (C.c_int, [_P]),
     "bossgpu_ingest_packed": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bossgpu_ingest_records": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
+    "bossgpu_ingest_records_ptr": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
+    "bossgpu_strat_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "bossgpu_get_seg_accept": (C.c_int, [_P, _P, C.c_int64]),
+    "bossgpu_read_starts_add": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "bossgpu_get_read_starts": (C.c_int, [_P, _P, C.c_int64]),
     "bossgpu_tokenize_cigar": (C.c_int64, [C.c_char_p, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bossgpu_update": (C.c_int, [_P, C.POINTER(UpdateParams), C.POINTER(UpdateResult)]),
     "bossgpu_update_phase": (C.c_int, [_P, C.c_int, C.POINTER(UpdateParams), C.POINTER(UpdateResult)]),
@@ -143,3 +149,13 @@ def ptr(a: np.ndarray | None):
 
 def as_c(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+# pointer to the UTF-8 bytes of a str object (for ASCII strings: its own buffer, no copy); valid while the object lives
+_as_utf8 = C.pythonapi.PyUnicode_AsUTF8AndSize
+_as_utf8.restype = C.c_void_p
+_as_utf8.argtypes = [C.py_object, C.c_void_p]
+
+
+def str_ptr(s: str) -> int:
+    return _as_utf8(s, None)

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <algorithm>
 #include <thread>
+#include <chrono>
 
 #include "common.cuh"
 #include "table.cuh"
@@ -215,6 +216,8 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     A(dev_alloc(&h->d_fhat_w, (size_t)h->n_windows_total * 2));
     A(dev_alloc(&h->d_hist, (size_t)3 * HBINS + 4));
     A(dev_alloc(&h->d_strat, (size_t)srows * 2 * h->nb));
+    A(dev_alloc(&h->d_seg_accept, (size_t)h->n_seg * 2));
+    A(dev_alloc(&h->d_rs_counts, (size_t)h->n_windows_total * 2));
     A(dev_alloc(&h->d_upd, 1));
     A(dev_alloc(&h->d_ingest_err, 1));
     A(dev_alloc((int64_t**)&h->scratch_d, 1));   // placeholder so scratch is never null
@@ -222,6 +225,10 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     if (rc != 0) { bossgpu_destroy(h); return rc; }
     BOSS_CUDA(cudaMallocHost((void**)&h->h_upd, sizeof(UpdateDev)));
     BOSS_CUDA(cudaMallocHost((void**)&h->h_ingest_err, sizeof(int32_t)));
+    BOSS_CUDA(cudaMallocHost((void**)&h->h_strat, std::max<size_t>(1, (size_t)srows * 2 * h->nb)));
+    BOSS_CUDA(cudaMallocHost((void**)&h->h_seg_accept, sizeof(unsigned long long) * 2 * h->n_seg));
+    memset(h->h_strat, 1, (size_t)srows * 2 * h->nb);          // Contig.strat starts all-accept (reference.py:118)
+    memset(h->h_seg_accept, 0, sizeof(unsigned long long) * 2 * h->n_seg);
     for (auto& ev : h->ev) BOSS_CUDA(cudaEventCreate(&ev));
 
     // geometry tables
@@ -323,10 +330,12 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
                     h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
                     h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
                     h->d_hist, h->d_strat, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
-                    h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len};
+                    h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
+    if (h->h_strat) cudaFreeHost(h->h_strat);
+    if (h->h_seg_accept) cudaFreeHost(h->h_seg_accept);
     if (h->stage_h) cudaFreeHost(h->stage_h);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     delete h;
@@ -439,6 +448,119 @@ extern "C" int64_t bossgpu_tokenize_cigar(const char* text, int64_t len, uint32_
     return n;
 }
 
+// Common text path: per read a CIGAR string and the aligned slice of the read, wherever they live.
+struct TextRead {
+    const char* cigar; int64_t cigar_len;
+    const char* seq;   int64_t seq_len;       // the slice itself, original orientation
+};
+
+static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+                            const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
+                            const std::vector<TextRead>& reads, int n_threads) {
+    // map global contig -> local segment (text API is for whole-contig shards; split shards use ingest_packed)
+    std::vector<int32_t> seg_of_contig(h->n_contigs_total, -1);
+    for (int s = 0; s < h->n_seg; ++s) {
+        if (h->segs[s].start != 0 || !h->segs[s].is_tail)
+            return fail(BOSSGPU_ESTATE, "the text ingest path needs whole-contig segments");
+        seg_of_contig[h->segs[s].contig] = s;
+    }
+    const bool trace = getenv("BOSSGPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t_begin = now();
+    int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (n_reads < 64) T = 1;
+    T = (int)std::min<int64_t>(T, n_reads);
+    // ---- pass 1 (parallel): count ops and spans per read -------------------------------------------------
+    std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads);
+    std::vector<int64_t> cut(T + 1, 0);
+    {
+        // split by characters so long reads do not pile up in one thread
+        int64_t total_chars = 0;
+        for (int64_t i = 0; i < n_reads; ++i) total_chars += reads[i].cigar_len + reads[i].seq_len;
+        int64_t per = total_chars / T + 1, acc = 0;
+        int t = 1;
+        for (int64_t i = 0; i < n_reads && t < T; ++i) {
+            acc += reads[i].cigar_len + reads[i].seq_len;
+            if (acc >= per * t) cut[t++] = i + 1;
+        }
+        for (; t <= T; ++t) cut[t] = n_reads;
+    }
+    auto run_parallel = [&](auto&& fn) {
+        if (T == 1) { fn(0, n_reads); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) if (cut[t + 1] > cut[t]) pool.emplace_back(fn, cut[t], cut[t + 1]);
+        for (auto& th : pool) th.join();
+    };
+    run_parallel([&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i)
+            n_ops[i] = tokenize_cigar(reads[i].cigar, reads[i].cigar_len, nullptr, 0, &rspan[i], &qspan[i]);
+    });
+    const double ms_pass1 = ms_since(t_begin);
+    // ---- validate like upstream, lay out the staging blob --------------------------------------------------
+    int64_t total_ops = 0, total_bases = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
+        if (qspan[i] != reads[i].seq_len)
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
+                        (long long)i, (long long)qspan[i], (long long)reads[i].seq_len);
+        if (rspan[i] != t1 - t0)
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
+                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
+        if (contig[i] < 0 || contig[i] >= h->n_contigs_total)
+            return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
+        total_ops += n_ops[i];
+        total_bases += reads[i].seq_len;
+    }
+    size_t o_seg = 0;
+    size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
+    size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_cg = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(total_ops, 1), 16);
+    size_t total = o_bs + round_up(std::max<int64_t>(total_bases, 1), 16);
+    TRY(ensure_stage(h, total));
+    char* hs = (char*)h->stage_h;
+    int32_t* s_seg = (int32_t*)(hs + o_seg);
+    int32_t* s_bc = (int32_t*)(hs + o_bc);
+    int64_t* s_ts = (int64_t*)(hs + o_ts);
+    int64_t* s_co = (int64_t*)(hs + o_co);
+    int64_t* s_bo = (int64_t*)(hs + o_bo);
+    uint32_t* s_cg = (uint32_t*)(hs + o_cg);
+    uint8_t* s_bs = (uint8_t*)(hs + o_bs);
+    s_co[0] = 0; s_bo[0] = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        s_seg[i] = seg_of_contig[contig[i]];
+        s_bc[i] = barcode[i];
+        s_ts[i] = std::min(tstart[i], tend[i]);
+        s_co[i + 1] = s_co[i] + n_ops[i];
+        s_bo[i + 1] = s_bo[i] + reads[i].seq_len;
+    }
+    const double ms_layout = ms_since(t_begin);
+    // ---- pass 2 (parallel): tokenise into place, copy / reverse-complement the slices into pinned memory ----
+    run_parallel([&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            int64_t r, q;
+            tokenize_cigar(reads[i].cigar, reads[i].cigar_len, s_cg + s_co[i], n_ops[i], &r, &q);
+            if (rev[i]) revcomp_copy(reads[i].seq, reads[i].seq_len, (char*)s_bs + s_bo[i]);       // boss/utils.py:85-95
+            else memcpy(s_bs + s_bo[i], reads[i].seq, (size_t)reads[i].seq_len);
+        }
+    });
+    const double ms_pass2 = ms_since(t_begin);
+    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
+    char* ds = (char*)h->stage_d;
+    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
+                       (const uint8_t*)(ds + o_bs), /*ascii=*/1, /*count_totals=*/true));
+    int rc = check_ingest_error(h);
+    if (trace)
+        fprintf(stderr, "[bossgpu] ingest %lld reads, %d threads (hw %u): count %.2f ms, layout %.2f, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
+                (long long)n_reads, T, std::thread::hardware_concurrency(), ms_pass1, ms_layout - ms_pass1, ms_pass2 - ms_layout,
+                ms_since(t_begin) - ms_pass2, total);
+    return rc;
+}
+
 extern "C" int bossgpu_ingest_records(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
                                       const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
                                       const int64_t* cig_off, const char* cigar_text, const int64_t* seq_off,
@@ -449,93 +571,29 @@ extern "C" int bossgpu_ingest_records(bossgpu_handle* h, int64_t n_reads, const 
     if (!contig || !tstart || !tend || !barcode || !rev || !cig_off || !cigar_text || !seq_off || !seq_text)
         return fail(BOSSGPU_EINVAL, "null batch array");
     if (cig_off[0] != 0 || seq_off[0] != 0) return fail(BOSSGPU_EINVAL, "offset arrays must start at 0");
-    // map global contig -> local segment (records API is for whole-contig shards; split shards use ingest_packed)
-    std::vector<int32_t> seg_of_contig(h->n_contigs_total, -1);
-    for (int s = 0; s < h->n_seg; ++s) {
-        if (h->segs[s].start != 0 || !h->segs[s].is_tail)
-            return fail(BOSSGPU_ESTATE, "bossgpu_ingest_records needs whole-contig segments");
-        seg_of_contig[h->segs[s].contig] = s;
-    }
-    // upper bound on ops: every op needs at least 2 characters
-    const int64_t cig_chars = cig_off[n_reads], n_bases = seq_off[n_reads];
-    const int64_t ops_cap = cig_chars / 2 + n_reads;
-    size_t o_seg = 0;
-    size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
-    size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
-    size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
-    size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_bs = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_cg = o_bs + round_up(std::max<int64_t>(n_bases, 1), 16);
-    size_t total = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
-    TRY(ensure_stage(h, total));
-    char* hs = (char*)h->stage_h;
-    int32_t* s_seg = (int32_t*)(hs + o_seg);
-    int32_t* s_bc = (int32_t*)(hs + o_bc);
-    int64_t* s_ts = (int64_t*)(hs + o_ts);
-    int64_t* s_co = (int64_t*)(hs + o_co);
-    int64_t* s_bo = (int64_t*)(hs + o_bo);
-    uint8_t* s_bs = (uint8_t*)(hs + o_bs);
-    uint32_t* s_cg = (uint32_t*)(hs + o_cg);
+    std::vector<TextRead> reads((size_t)n_reads);
+    for (int64_t i = 0; i < n_reads; ++i)
+        reads[i] = TextRead{cigar_text + cig_off[i], cig_off[i + 1] - cig_off[i], seq_text + seq_off[i], seq_off[i + 1] - seq_off[i]};
+    return ingest_text_impl(h, n_reads, contig, tstart, tend, barcode, rev, reads, n_threads);
+}
 
-    // ---- tokenise in parallel: each read writes at its worst-case op offset, compacted afterwards ----
-    std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads), cap_off(n_reads + 1);
-    cap_off[0] = 0;
-    for (int64_t i = 0; i < n_reads; ++i) cap_off[i + 1] = cap_off[i] + (cig_off[i + 1] - cig_off[i]) / 2 + 1;
-    int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-    if (n_reads < 64) T = 1;
-    auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            n_ops[i] = tokenize_cigar(cigar_text + cig_off[i], cig_off[i + 1] - cig_off[i], s_cg + cap_off[i],
-                                      cap_off[i + 1] - cap_off[i], &rspan[i], &qspan[i]);
-            const int64_t a = seq_off[i], b = seq_off[i + 1];
-            if (rev[i]) revcomp_copy(seq_text + a, b - a, (char*)s_bs + a);       // boss/utils.py:85-95
-            else memcpy(s_bs + a, seq_text + a, (size_t)(b - a));
-        }
-    };
-    if (T == 1) work(0, n_reads);
-    else {
-        std::vector<std::thread> pool;
-        // split by bases so long reads do not pile up in one thread
-        int64_t per = n_bases / T + 1, lo = 0;
-        for (int t = 0; t < T && lo < n_reads; ++t) {
-            int64_t hi = lo;
-            int64_t lim = seq_off[lo] + per;
-            while (hi < n_reads && (seq_off[hi] < lim || hi == lo)) ++hi;
-            if (t == T - 1) hi = n_reads;
-            pool.emplace_back(work, lo, hi);
-            lo = hi;
-        }
-        for (auto& th : pool) th.join();
-    }
-    // validate like upstream, then compact the ops
-    int64_t w = 0;
-    s_co[0] = 0;
+extern "C" int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+                                          const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
+                                          const uint64_t* cigar_ptr, const int64_t* cigar_len, const uint64_t* seq_ptr,
+                                          const int64_t* seq_from, const int64_t* seq_to, int n_threads) {
+    H_CHECK(h);
+    if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
+    if (n_reads == 0) return 0;
+    if (!contig || !tstart || !tend || !barcode || !rev || !cigar_ptr || !cigar_len || !seq_ptr || !seq_from || !seq_to)
+        return fail(BOSSGPU_EINVAL, "null batch array");
+    std::vector<TextRead> reads((size_t)n_reads);
     for (int64_t i = 0; i < n_reads; ++i) {
-        if (n_ops[i] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
-        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
-        if (qspan[i] != seq_off[i + 1] - seq_off[i])
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
-                        (long long)i, (long long)qspan[i], (long long)(seq_off[i + 1] - seq_off[i]));
-        if (rspan[i] != t1 - t0)
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
-                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
-        if (contig[i] < 0 || contig[i] >= h->n_contigs_total) return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
-        s_seg[i] = seg_of_contig[contig[i]];
-        s_bc[i] = barcode[i];
-        s_ts[i] = t0;
-        s_bo[i] = seq_off[i];
-        if (w != cap_off[i]) memmove(s_cg + w, s_cg + cap_off[i], sizeof(uint32_t) * n_ops[i]);
-        w += n_ops[i];
-        s_co[i + 1] = w;
+        if (seq_to[i] < seq_from[i] || seq_from[i] < 0 || cigar_len[i] < 0)
+            return fail(BOSSGPU_EINVAL, "read %lld: bad slice bounds", (long long)i);
+        reads[i] = TextRead{(const char*)(uintptr_t)cigar_ptr[i], cigar_len[i],
+                            (const char*)(uintptr_t)seq_ptr[i] + seq_from[i], seq_to[i] - seq_from[i]};
     }
-    s_bo[n_reads] = n_bases;
-    size_t used = o_cg + sizeof(uint32_t) * std::max<int64_t>(w, 1);
-    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, used, cudaMemcpyHostToDevice, h->stream));
-    char* ds = (char*)h->stage_d;
-    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
-                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
-                       (const uint8_t*)(ds + o_bs), /*ascii=*/1, /*count_totals=*/true));
-    return check_ingest_error(h);
+    return ingest_text_impl(h, n_reads, contig, tstart, tend, barcode, rev, reads, n_threads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -652,6 +710,15 @@ static int phase1_smooth(bossgpu_handle* h, const bossgpu_update_params* p) {
 }
 
 static int upload_fhat(bossgpu_handle* h, const bossgpu_update_params* p) {
+    if (p->fhat_from_counts) {
+        const int64_t n = h->n_windows_total * 2;
+        k_fhat_from_counts<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(n, h->d_rs_counts, p->rs_alpha, p->rs_denom,
+                                                                               p->rs_zero_value, h->d_fhat_w);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+        h->have_fhat = true;
+        return 0;
+    }
     if (p->fhat_windows) {
         size_t bytes = sizeof(double) * 2 * h->n_windows_total;
         TRY(ensure_stage(h, bytes));
@@ -698,12 +765,16 @@ static int phase4_distribute(bossgpu_handle* h, const uint8_t* merged_mask) {
     a.segs = h->d_segs; a.srow_start = h->d_srow_start; a.n_seg = h->n_seg; a.nb = h->nb; a.benefit = h->d_benefit;
     a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.merged_mask = merged_mask; a.bucket_sw = h->d_bucket_sw;
     a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards; a.mask_stride = h->mask_stride;
-    a.strat = h->d_strat; a.n_srows = h->n_srows; a.upd = h->d_upd; a.n_accept = h->d_upd->n_accept;
+    a.strat = h->d_strat; a.n_srows = h->n_srows; a.upd = h->d_upd; a.seg_accept = h->d_seg_accept;
+    BOSS_CUDA(cudaMemsetAsync(h->d_seg_accept, 0, sizeof(unsigned long long) * 2 * h->n_seg, h->stream));
     int64_t total = h->n_srows * 2 * h->nb;
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
     k_distribute<<<grid, 256, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     h->launches++;
+    // refresh the pinned host mirror of every mask (what Contig.strat views) and the per-segment accept counts
+    BOSS_CUDA(cudaMemcpyAsync(h->h_strat, h->d_strat, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaMemcpyAsync(h->h_seg_accept, h->d_seg_accept, sizeof(unsigned long long) * 2 * h->n_seg, cudaMemcpyDeviceToHost, h->stream));
     EV_END(6);
     return 0;
 }
@@ -724,8 +795,10 @@ static int fetch_result(bossgpu_handle* h, bossgpu_update_result* r) {
         r->fhat_sum = h->last.fhat_sum;
         r->n_nonzero = (int64_t)h->last.n_nonzero;
         r->n_dropout = (int64_t)h->last.n_dropout;
-        r->n_accept[0] = (int64_t)h->last.n_accept[0];
-        r->n_accept[1] = (int64_t)h->last.n_accept[1];
+        for (int sg = 0; sg < h->n_seg; ++sg) {
+            r->n_accept[0] += (int64_t)h->h_seg_accept[2 * sg];
+            r->n_accept[1] += (int64_t)h->h_seg_accept[2 * sg + 1];
+        }
     }
     TRY(check_ingest_error(h));
     return 0;
@@ -1094,6 +1167,51 @@ extern "C" int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double m
                                                       frac_dropout, frac_deep);
         BOSS_KERNEL_CHECK();
     }
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// host mirror of the masks, per-segment accept counts, device-side read-start counts
+// ------------------------------------------------------------------------------------------------
+extern "C" int bossgpu_strat_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes) {
+    if (!h || !ptr || !bytes) return fail(BOSSGPU_EINVAL, "null argument");
+    *ptr = h->h_strat;
+    *bytes = h->n_srows * 2 * h->nb;
+    return 0;
+}
+
+extern "C" int bossgpu_get_seg_accept(bossgpu_handle* h, int64_t* out, int64_t n) {
+    if (!h || !out || n != 2 * (int64_t)h->n_seg) return fail(BOSSGPU_EINVAL, "accept buffer must hold 2 * n_segments entries");
+    for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)h->h_seg_accept[i];
+    return 0;
+}
+
+extern "C" int bossgpu_read_starts_add(bossgpu_handle* h, int64_t n, const int64_t* window, const uint8_t* strand) {
+    H_CHECK(h);
+    if (n < 0) return fail(BOSSGPU_EINVAL, "negative count");
+    if (n == 0) return 0;
+    if (!window || !strand) return fail(BOSSGPU_EINVAL, "null array");
+    size_t o_s = round_up(sizeof(int64_t) * n, 16);
+    size_t total = o_s + round_up((size_t)n, 16);
+    TRY(ensure_stage(h, total));
+    memcpy(h->stage_h, window, sizeof(int64_t) * n);
+    memcpy((char*)h->stage_h + o_s, strand, (size_t)n);
+    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, h->stage_h, total, cudaMemcpyHostToDevice, h->stream));
+    k_count_read_starts<<<(unsigned)ceil_div(n, 256), 256, 0, h->stream>>>(n, (const int64_t*)h->stage_d,
+                                                                          (const uint8_t*)((char*)h->stage_d + o_s),
+                                                                          h->n_windows_total, h->d_rs_counts);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));      // the staging buffer is reused by the next call
+    return 0;
+}
+
+extern "C" int bossgpu_get_read_starts(bossgpu_handle* h, int64_t* out, int64_t n) {
+    H_CHECK(h);
+    if (!out || n != 2 * h->n_windows_total) return fail(BOSSGPU_EINVAL, "buffer must hold 2 * n_windows_total entries");
+    BOSS_CUDA(cudaMemcpyAsync(out, h->d_rs_counts, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -150,6 +150,10 @@ struct bossgpu_handle {
     double*   d_fhat_w = nullptr;                // [n_windows_total][2]
     unsigned long long* d_hist = nullptr;        // [3*HBINS + 4]
     uint8_t*  d_strat = nullptr;                 // [n_srows][2][nb]
+    uint8_t*  h_strat = nullptr;                 // pinned host mirror of d_strat, refreshed by every update that derives a strategy
+    unsigned long long* d_seg_accept = nullptr;  // [n_seg][2] accepted entries per segment and strand
+    unsigned long long* h_seg_accept = nullptr;  // pinned
+    unsigned long long* d_rs_counts = nullptr;   // [n_windows_total][2] read-start counts (readstartdist.py:26)
     boss::UpdateDev* d_upd = nullptr;
     boss::UpdateDev* h_upd = nullptr;            // pinned
     // staging for ingest

@@ -442,13 +442,16 @@ struct DistArgs {
     uint8_t* strat;               // [n_srows][2][nb]
     int64_t n_srows;
     const UpdateDev* upd;
-    unsigned long long* n_accept; // [2]
+    unsigned long long* seg_accept; // [n_seg][2]
 };
 
 __global__ void __launch_bounds__(256)
 k_distribute(DistArgs a) {
     const int64_t total = a.n_srows * 2 * a.nb;
     const double thr = a.upd->threshold;
+    // accepted entries per (segment, strand) for the per-contig log line (core.py:152-154); a thread keeps the
+    // count of its current segment in a register and flushes when the segment changes
+    int cur_sg = -1;
     unsigned acc0 = 0, acc1 = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(i % a.nb);
@@ -472,16 +475,42 @@ k_distribute(DistArgs a) {
             cur = m ? 1 : 0;
             a.strat[i] = cur;
         }
+        if (sg != cur_sg) {
+            if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
+            if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
+            cur_sg = sg; acc0 = 0; acc1 = 0;
+        }
         if (s == 0) acc0 += cur; else acc1 += cur;
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        acc0 += __shfl_down_sync(0xFFFFFFFFu, acc0, o);
-        acc1 += __shfl_down_sync(0xFFFFFFFFu, acc1, o);
+    // most warps sit inside one segment: one atomic per warp instead of 32
+    const bool uniform = __all_sync(0xFFFFFFFFu, cur_sg == __shfl_sync(0xFFFFFFFFu, cur_sg, 0));
+    if (uniform) {
+        acc0 = __reduce_add_sync(0xFFFFFFFFu, acc0);
+        acc1 = __reduce_add_sync(0xFFFFFFFFu, acc1);
+        if ((threadIdx.x & 31) != 0) { acc0 = 0; acc1 = 0; }
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (acc0) atomicAdd(&a.n_accept[0], (unsigned long long)acc0);
-        if (acc1) atomicAdd(&a.n_accept[1], (unsigned long long)acc1);
+    if (cur_sg >= 0) {
+        if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
+        if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
     }
+}
+
+// F-hat per window from the read-start counts kept on the device (readstartdist.py:96-115):
+// (alpha + C) / denom where C > 0, the point-mass value elsewhere
+__global__ void k_fhat_from_counts(int64_t n, const unsigned long long* __restrict__ counts, double alpha, double denom,
+                                   double zero_value, double* __restrict__ fw) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long c = counts[i];
+    fw[i] = c ? __ddiv_rn(__dadd_rn(alpha, (double)c), denom) : zero_value;
+}
+
+__global__ void k_count_read_starts(int64_t n, const int64_t* __restrict__ win, const uint8_t* __restrict__ strand,
+                                    int64_t n_windows, unsigned long long* __restrict__ counts) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t w = win[i];
+    if (w >= 0 && w < n_windows) atomicAdd(&counts[2 * w + (strand[i] ? 1 : 0)], 1ull);
 }
 
 // packed mask of this shard's merged rows: bit (i*2+s)*nb+b for local row i (rows cut by adjust_length are 0)

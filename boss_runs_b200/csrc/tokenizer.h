@@ -10,7 +10,7 @@ namespace boss {
 // Upstream's regex `(\d+)([MIDNSHP=XB])` is applied with findall: anything that does not match is
 // skipped silently. Op classes as consumed by the scatter kernel: 1 = I (read only), 2 = D (reference
 // only), 0 = every other letter (upstream fills those columns from the read and keeps them).
-// Returns the number of ops written, or -1 if `cap` is too small.
+// Returns the number of ops written (counted only when out == nullptr), or -1 if `cap` is too small.
 inline int64_t tokenize_cigar(const char* s, int64_t n, uint32_t* out, int64_t cap, int64_t* ref_span, int64_t* query_span) {
     int64_t k = 0, r = 0, q = 0;
     uint64_t num = 0;
@@ -32,8 +32,11 @@ inline int64_t tokenize_cigar(const char* s, int64_t n, uint32_t* out, int64_t c
         if (have && cls >= 0) {
             // lengths are uint32 upstream (np.array(lengths, dtype=np.uint32)); 28 bits is > any real run
             uint32_t len = (uint32_t)(num & 0x0FFFFFFFu);
-            if (k >= cap) return -1;
-            out[k++] = (len << 4) | (uint32_t)cls;
+            if (out) {
+                if (k >= cap) return -1;
+                out[k] = (len << 4) | (uint32_t)cls;
+            }
+            ++k;
             if (cls != 1) r += len;
             if (cls != 2) q += len;
         }

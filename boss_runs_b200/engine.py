@@ -159,8 +159,29 @@ class Engine:
                                               ptr(cig_off), C.cast(C.c_char_p(cigar_text), C.c_void_p), ptr(seq_off),
                                               C.cast(C.c_char_p(seq_text), C.c_void_p), int(n_threads)))
 
+    def ingest_records_ptr(self, contig, tstart, tend, barcode, rev, cigar_ptr, cigar_len, seq_ptr, seq_from, seq_to,
+                           n_threads: int = 0) -> None:
+        """Text ingest straight from the callers' string buffers (pointers as uint64)."""
+        contig = as_c(contig, np.int32); tstart = as_c(tstart, np.int64); tend = as_c(tend, np.int64)
+        barcode = as_c(barcode, np.int32); rev = as_c(rev, np.uint8)
+        cigar_ptr = as_c(cigar_ptr, np.uint64); cigar_len = as_c(cigar_len, np.int64)
+        seq_ptr = as_c(seq_ptr, np.uint64); seq_from = as_c(seq_from, np.int64); seq_to = as_c(seq_to, np.int64)
+        check(self.lib.bossgpu_ingest_records_ptr(self.h, len(contig), ptr(contig), ptr(tstart), ptr(tend), ptr(barcode),
+                                                  ptr(rev), ptr(cigar_ptr), ptr(cigar_len), ptr(seq_ptr), ptr(seq_from),
+                                                  ptr(seq_to), int(n_threads)))
+
+    def read_starts_add(self, window, strand) -> None:
+        window = as_c(window, np.int64); strand = as_c(strand, np.uint8)
+        assert len(window) == len(strand)
+        check(self.lib.bossgpu_read_starts_add(self.h, len(window), ptr(window), ptr(strand)))
+
+    def read_starts(self) -> np.ndarray:
+        out = np.empty((self.n_windows_total, 2), dtype=np.int64)
+        check(self.lib.bossgpu_get_read_starts(self.h, ptr(out), out.size))
+        return out
+
     # -- strategy update -------------------------------------------------------------------------
-    def _params(self, approx_ccl, time_cost, bucket_threshold, fhat_windows, debug) -> tuple:
+    def _params(self, approx_ccl, time_cost, bucket_threshold, fhat_windows, debug, fhat_scalars=None) -> tuple:
         p = _lib.UpdateParams()
         w = np.asarray(approx_ccl) // BIN                       # reference.py:252
         assert w.shape == (N_STEPS,)
@@ -175,6 +196,10 @@ class Engine:
             assert keep.shape == (self.n_windows_total, 2), "fhat_windows must be [sum int(L/2000)][2]"
             p.fhat_windows = keep.ctypes.data
         p.write_debug = int(bool(debug))
+        if fhat_scalars is not None:
+            assert fhat_windows is None
+            p.fhat_from_counts = 1
+            p.rs_alpha, p.rs_denom, p.rs_zero_value = (float(x) for x in fhat_scalars)
         return p, keep
 
     @staticmethod
@@ -182,8 +207,11 @@ class Engine:
         return UpdateOutcome(bool(r.switched_on), r.threshold, r.strat_size, r.normaliser, r.ubar0, r.fhat_sum,
                              r.n_nonzero, r.n_dropout, (r.n_accept[0], r.n_accept[1]))
 
-    def update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None, debug: bool = False) -> UpdateOutcome:
-        p, _keep = self._params(approx_ccl, time_cost, bucket_threshold, fhat_windows, debug)
+    def update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None, debug: bool = False,
+               fhat_scalars=None) -> UpdateOutcome:
+        """`fhat_windows`: compact F-hat [n_windows_total][2] from the host, or `fhat_scalars` = (alpha, denom,
+        zero_value) to derive it on the device from the counts added with `read_starts_add`; neither = reuse."""
+        p, _keep = self._params(approx_ccl, time_cost, bucket_threshold, fhat_windows, debug, fhat_scalars)
         r = _lib.UpdateResult()
         check(self.lib.bossgpu_update(self.h, C.byref(p), C.byref(r)))
         return self._outcome(r)
@@ -213,6 +241,20 @@ class Engine:
         if out is None:
             out = np.empty((rows, 2, self.nb), dtype=np.bool_)
         check(self.lib.bossgpu_get_strat_all(self.h, ptr(out), out.size))
+        return out
+
+    def strat_host(self) -> np.ndarray:
+        """Zero-copy view of the library's pinned host mirror of every mask: bool [all rows][2][nb]. The library
+        rewrites it at the end of each update that derives a strategy. The view keeps this engine alive."""
+        p, n = C.c_void_p(), C.c_int64()
+        check(self.lib.bossgpu_strat_host(self.h, C.byref(p), C.byref(n)))
+        raw = (C.c_uint8 * n.value).from_address(p.value)
+        raw._owner = self                      # numpy's base chain -> this ctypes block -> the engine
+        return np.frombuffer(raw, dtype=np.bool_).reshape(-1, 2, self.nb)
+
+    def seg_accept(self) -> np.ndarray:
+        out = np.empty((len(self.segments), 2), dtype=np.int64)
+        check(self.lib.bossgpu_get_seg_accept(self.h, ptr(out), out.size))
         return out
 
     def strat_packed(self) -> np.ndarray:

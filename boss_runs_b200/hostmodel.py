@@ -167,18 +167,68 @@ class ReadStartDist:
             assert lendiff < self.window_size
 
     def merge(self) -> np.ndarray:
-        return np.concatenate(list(self.read_starts.values()))
+        return self._merged_rows()
 
-    def count_read_starts(self, paf_dict: dict) -> None:
-        fwd, rev = defaultdict(list), defaultdict(list)
+    def window_events(self, paf_dict: dict) -> tuple[np.ndarray, np.ndarray]:
+        """The batch's read starts as (global window index, strand) pairs — what `count_read_starts` adds, in
+        the sparse form the GPU-side counter takes. Binning follows np.histogram over [0, 2000*n_windows]:
+        the right edge is closed, everything outside is dropped (readstartdist.py:68-78)."""
+        if not hasattr(self, "_win_off"):
+            off, acc = {}, 0
+            for name, arr in self.read_starts.items():
+                off[name] = (acc, int(arr.shape[0]))
+                acc += int(arr.shape[0])
+            self._win_off = off
+        wins, strands = [], []
         for recs in paf_dict.values():
             rec = best_record(recs)
-            (rev if rec.rev else fwd)[rec.tname].append(rec.tend if rec.rev else rec.tstart)
-        for name, arr in self.read_starts.items():
-            nw = int(arr.shape[0])
-            span = (0, self.window_size * nw)
-            arr[:, 0] += np.histogram(fwd[name], bins=nw, range=span)[0].astype(dtype="float")
-            arr[:, 1] += np.histogram(rev[name], bins=nw, range=span)[0].astype(dtype="float")
+            ent = self._win_off.get(rec.tname)
+            if ent is None:
+                continue
+            pos = rec.tend if rec.rev else rec.tstart
+            base, nw = ent
+            if pos < 0 or pos > self.window_size * nw:
+                continue
+            w = min(pos // self.window_size, nw - 1)
+            wins.append(base + w)
+            strands.append(1 if rec.rev else 0)
+        return np.asarray(wins, dtype=np.int64), np.asarray(strands, dtype=np.uint8)
+
+    def pointmass_scalars(self, csum: float | None = None) -> tuple[float, float, float]:
+        """(alpha, denom, zero_value) of `update_f_pointmass` (readstartdist.py:96-111): F-hat is
+        (alpha + C) / denom where C > 0 and zero_value elsewhere. `csum` = total count (default: from the host
+        mirror of the counts)."""
+        nw = int(self.total_len)
+        if csum is None:
+            csum = getattr(self, "csum", 0.0)       # every event adds exactly 1 to exactly one window
+        csum = np.float64(csum)
+        denom = 2 * nw * self.alpha + csum
+        rhs = self.alpha / (2 * nw * self.alpha + csum)
+        beta_num = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha + csum)))
+        beta_denom = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha))) or 1e-20
+        p0_bit = self.p0 / (self.p0 + (1 - self.p0))
+        return float(self.alpha), float(denom), float((1 - p0_bit * (beta_num / beta_denom)) * rhs)
+
+    def count_read_starts(self, paf_dict: dict) -> tuple[np.ndarray, np.ndarray]:
+        """Adds the batch's read starts to the per-contig window counts (same bins as upstream's np.histogram
+        calls) and returns them as (global window, strand) events for the GPU-side counter."""
+        wins, strands = self.window_events(paf_dict)
+        if len(wins):
+            merged_view = self._merged_rows()
+            np.add.at(merged_view, (wins, strands), 1.0)
+            self.csum = getattr(self, "csum", 0.0) + float(len(wins))
+        return wins, strands
+
+    def _merged_rows(self) -> np.ndarray:
+        """One (total windows, 2) array whose per-contig slices ARE `read_starts[name]` (so `merge()` is free)."""
+        if not hasattr(self, "_merged"):
+            self._merged = np.concatenate(list(self.read_starts.values())) if self.read_starts else np.zeros((0, 2))
+            row = 0
+            for name, arr in list(self.read_starts.items()):
+                n = arr.shape[0]
+                self.read_starts[name] = self._merged[row: row + n]
+                row += n
+        return self._merged
 
     def update_f_pointmass(self) -> np.ndarray:
         merged = self.merge()

@@ -23,7 +23,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ._lib import BIN, BUCKET
+from ._lib import BIN, BUCKET, str_ptr
 from .engine import Engine, UpdateOutcome
 from .hostmodel import ReadlengthDist, ReadStartDist, best_record
 from .priors import Scoring
@@ -40,26 +40,41 @@ def seq_to_int(seq: str) -> np.ndarray:
 
 @dataclass
 class PackedBatch:
-    """What `CoverageConverter.convert_records` hands to `_effect_increments`: the batch as flat arrays,
-    still as text (the library tokenises CIGARs and reverse-complements in C++ threads)."""
+    """What `CoverageConverter.convert_records` hands to `_effect_increments`: per-read scalars plus POINTERS
+    to the CIGAR and read strings (no text is copied or joined on the Python side; the library tokenises the
+    CIGARs and copies / reverse-complements the aligned slices in C++ threads, straight into pinned memory)."""
     contig: np.ndarray      # int32 index into contigs_filt order
     tstart: np.ndarray      # int64
     tend: np.ndarray        # int64
     barcode: np.ndarray     # int32
     rev: np.ndarray         # uint8
-    cig_off: np.ndarray     # int64 [n+1]
-    cigar_text: bytes
-    seq_off: np.ndarray     # int64 [n+1]
-    seq_text: bytes
+    cigar_ptr: np.ndarray   # uint64: address of the CIGAR characters
+    cigar_len: np.ndarray   # int64
+    seq_ptr: np.ndarray     # uint64: address of the read's characters
+    seq_from: np.ndarray    # int64: aligned slice [from, to) of the read, original orientation
+    seq_to: np.ndarray
+    keep: list              # the str objects the pointers refer to
     n_skipped: int = 0      # reads whose target is not a tracked contig
 
     def __len__(self) -> int:
         return int(self.contig.shape[0])
 
+    def texts(self):
+        """(cig_off, cigar_text, seq_off, seq_text): the joined-text form `bossgpu_ingest_records` takes."""
+        cigs = self.keep[0::2]
+        seqs = [s[a:b] for s, a, b in zip(self.keep[1::2], self.seq_from, self.seq_to)]
+        n = len(self)
+        cig_off = np.zeros(n + 1, dtype=np.int64)
+        seq_off = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(c) for c in cigs], out=cig_off[1:])
+            np.cumsum([len(p) for p in seqs], out=seq_off[1:])
+        return cig_off, "".join(cigs).encode("ascii", "replace"), seq_off, "".join(seqs).encode("ascii", "replace")
+
 
 class CoverageConverter:
-    """Host half of the coverage update (sequences.py:657-739): picks each read's record, slices the
-    aligned part of the read and flattens the batch. CIGAR expansion and counting happen on the GPU."""
+    """Host half of the coverage update (sequences.py:657-739): picks each read's record and the aligned
+    slice of the read. CIGAR expansion and counting happen on the GPU."""
 
     def __init__(self, contig_index: dict[str, int], qt: int = 0):
         if qt != 0:
@@ -69,41 +84,43 @@ class CoverageConverter:
 
     def convert_records(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
                         barcodes: dict[str, int] | None = None) -> PackedBatch:
-        contig, tstart, tend, bc, rev, cig, sl = [], [], [], [], [], [], []
+        contig, tstart, tend, bc, rev, cp, cl, sp, sf, st, keep = [], [], [], [], [], [], [], [], [], [], []
         skipped = 0
-        for rid in list(paf_dict.keys()):
-            rec = best_record(paf_dict[rid])
-            k = self.contig_index.get(rec.tname)
+        index = self.contig_index
+        for recs in paf_dict.values():
+            rec = recs[0] if len(recs) == 1 else best_record(recs)
+            k = index.get(rec.tname)
             if k is None:
                 skipped += 1          # upstream collects these under a key nobody reads (core.py:83-86)
                 continue
             s = seqs[rec.qname]
-            n = len(s)
             if rec.rev:
                 # upstream slices the reverse complement of the WHOLE string with qlen-based coordinates
-                # (sequences.py:707-711; Q12): rc[a:b] == revcomp(s[n-b:n-a])
+                # (sequences.py:707-711; Q12): rc[a:b] == revcomp(s[n-b:n-a]), with Python's slice clamping
+                n = len(s)
                 a, b = rec.qlen - rec.qend, rec.qlen - rec.qstart
-                piece = s[max(n - b, 0): max(n - a, 0)]
+                lo, hi = max(n - min(b, n), 0), max(n - min(a, n), 0)
             else:
-                piece = s[rec.qstart: rec.qend]
-            assert rec.cigar is not None
+                lo, hi = min(rec.qstart, len(s)), min(rec.qend, len(s))
+            cig = rec.cigar
+            assert cig is not None
             contig.append(k)
             tstart.append(rec.tstart)
             tend.append(rec.tend)
             bc.append(0 if rec.barcode is None else rec.barcode)
-            rev.append(1 if rec.rev else 0)
-            cig.append(rec.cigar)
-            sl.append(piece)
-        n = len(contig)
-        cig_off = np.zeros(n + 1, dtype=np.int64)
-        seq_off = np.zeros(n + 1, dtype=np.int64)
-        if n:
-            np.cumsum([len(c) for c in cig], out=cig_off[1:])
-            np.cumsum([len(p) for p in sl], out=seq_off[1:])
+            rev.append(rec.rev)
+            cp.append(str_ptr(cig))
+            cl.append(len(cig))
+            sp.append(str_ptr(s))
+            sf.append(lo)
+            st.append(max(hi, lo))
+            keep.append(cig)
+            keep.append(s)
         return PackedBatch(np.asarray(contig, dtype=np.int32), np.asarray(tstart, dtype=np.int64),
                            np.asarray(tend, dtype=np.int64), np.asarray(bc, dtype=np.int32),
-                           np.asarray(rev, dtype=np.uint8), cig_off, "".join(cig).encode("ascii", "replace"),
-                           seq_off, "".join(sl).encode("ascii", "replace"), skipped)
+                           np.asarray(rev, dtype=np.uint8), np.asarray(cp, dtype=np.uint64), np.asarray(cl, dtype=np.int64),
+                           np.asarray(sp, dtype=np.uint64), np.asarray(sf, dtype=np.int64), np.asarray(st, dtype=np.int64),
+                           keep, skipped)
 
 
 class Contig:
@@ -267,6 +284,7 @@ class BossRuns:
         for i, c in enumerate(self.contigs_filt.values()):
             c._bind(self.engine, i)
         self.batch = 0
+        self._strat_views = None
         self.threshold: float | None = None
         self.last: UpdateOutcome | None = None
         if self.out_dir is not None:
@@ -284,27 +302,37 @@ class BossRuns:
     # -- coverage (core.py:77-86) ----------------------------------------------------------------------
     def _effect_increments(self, increments: PackedBatch) -> None:
         b = increments
-        self.engine.ingest_records(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cig_off, b.cigar_text,
-                                   b.seq_off, b.seq_text)
+        self.engine.ingest_records_ptr(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
+                                       b.seq_ptr, b.seq_from, b.seq_to)
 
     # -- update (core.py:160-198) ----------------------------------------------------------------------
     def update_wrapper(self) -> None:
-        fhat_w = self.read_starts.update_f_pointmass()
+        import time as _t
+        t0 = _t.perf_counter()
+        # F-hat: three scalars from the host; the per-window values are formed on the GPU from its own counts
+        scalars = self.read_starts.pointmass_scalars()
+        t1 = _t.perf_counter()
         # `time_cost` does not exist before the first successful read-length update (Q14). Upstream only
         # reads it once some bucket is on (core.py:172,192), so the AttributeError is raised at that point.
         time_cost = getattr(self.rl_dist, "time_cost", None)
         out = self.engine.update(approx_ccl=self.rl_dist.approx_ccl,
                                  time_cost=np.float64("nan") if time_cost is None else time_cost,
-                                 bucket_threshold=self.bucket_threshold, fhat_windows=fhat_w,
-                                 debug=self.write_debug)
+                                 bucket_threshold=self.bucket_threshold, fhat_scalars=scalars, debug=self.write_debug)
+        t2 = _t.perf_counter()
         self.last = out
         self._pull_switches()
+        t3 = _t.perf_counter()
         if out.switched_on:
             if time_cost is None:
                 self.rl_dist.time_cost      # AttributeError, as upstream
             self.threshold = out.threshold
             self._pull_strategies()
+            t4 = _t.perf_counter()
             self._write_contig_strategies(self.ref.get_strategy_dict())
+        else:
+            t4 = t3
+        self.last_host_ms = {"fhat_host": (t1 - t0) * 1e3, "engine_update": (t2 - t1) * 1e3,
+                             "pull_switches": (t3 - t2) * 1e3, "pull_strategies": (t4 - t3) * 1e3}
 
     def _pull_switches(self) -> None:
         for i, c in enumerate(self.contigs_filt.values()):
@@ -313,16 +341,27 @@ class BossRuns:
             c.switched_on[...] = on
 
     def _pull_strategies(self) -> None:
-        """One device->host copy of every contig's mask, then per-contig views (no per-contig round trips)."""
-        flat = self.engine.strat_all()
-        row = 0
-        for c in self.contigs_filt.values():
-            n = c.length // BIN
-            c.strat = flat[row: row + n]
-            row += n
-            f_perc = np.count_nonzero(c.strat[:, 0]) / c.strat.shape[0]
-            r_perc = np.count_nonzero(c.strat[:, 1]) / c.strat.shape[0]
-            logging.info(f"{c.name}: {f_perc}, {r_perc}")
+        """`Contig.strat` of every contig is a view into the library's pinned host mirror, which the update has
+        just refreshed with one device->host copy; nothing is copied here. Accept fractions for the log line
+        (core.py:152-154) come from counters the distribution kernel filled."""
+        if self._strat_views is None:
+            flat = self.engine.strat_host()
+            self._strat_views = []
+            row = 0
+            for c in self.contigs_filt.values():
+                n = c.length // BIN
+                self._strat_views.append(flat[row: row + n])
+                row += n
+        acc = self.engine.seg_accept()
+        for i, c in enumerate(self.contigs_filt.values()):
+            c.strat = self._strat_views[i]
+            rows = max(c.strat.shape[0], 1)
+            logging.info(f"{c.name}: {acc[i, 0] / rows}, {acc[i, 1] / rows}")
+
+    def count_read_starts(self, paf_dict) -> None:
+        """`ReadStartDist.count_read_starts` on the host mirror AND on the GPU-side counter."""
+        wins, strands = self.read_starts.count_read_starts(paf_dict=paf_dict)
+        self.engine.read_starts_add(wins, strands)
 
     # -- one batch (core.py:202-224, minus the mapping call) -------------------------------------------
     def process_batch_runs(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
@@ -332,7 +371,7 @@ class BossRuns:
         (simulation.py:171)."""
         increments = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
         self._effect_increments(increments=increments)
-        self.read_starts.count_read_starts(paf_dict=paf_dict if paf_dict_starts is None else paf_dict_starts)
+        self.count_read_starts(paf_dict if paf_dict_starts is None else paf_dict_starts)
         self.update_wrapper()
         self.batch += 1
 
@@ -347,10 +386,11 @@ class BossRuns:
         import ctypes as C
         lib = self.engine.lib
         n = len(batch)
+        b_cig_off, cigar_text, b_seq_off, seq_text = batch.texts()
         cig_off = np.zeros(n + 1, dtype=np.int64)
-        ops = np.empty(len(batch.cigar_text) // 2 + n + 1, dtype=np.uint32)
-        text = np.frombuffer(batch.cigar_text, dtype=np.uint8)
-        seq = np.frombuffer(batch.seq_text, dtype=np.uint8)
+        ops = np.empty(len(cigar_text) // 2 + n + 1, dtype=np.uint32)
+        text = np.frombuffer(cigar_text, dtype=np.uint8)
+        seq = np.frombuffer(seq_text, dtype=np.uint8)
         bases = np.empty(len(seq), dtype=np.uint8)
         comp = np.arange(256, dtype=np.uint8)
         for a, b in zip(b"ATGC", b"TACG"):
@@ -358,19 +398,19 @@ class BossRuns:
         r, q = C.c_int64(), C.c_int64()
         w = 0
         for i in range(n):
-            a, b = int(batch.cig_off[i]), int(batch.cig_off[i + 1])
+            a, b = int(b_cig_off[i]), int(b_cig_off[i + 1])
             k = lib.bossgpu_tokenize_cigar(text[a:b].tobytes(), b - a, ops[w:].ctypes.data, len(ops) - w, C.byref(r), C.byref(q))
             if k < 0:
                 raise ValueError("CIGAR tokenizer failed")
             w += k
             cig_off[i + 1] = w
-            sa, sb = int(batch.seq_off[i]), int(batch.seq_off[i + 1])
+            sa, sb = int(b_seq_off[i]), int(b_seq_off[i + 1])
             if q.value != sb - sa or r.value != abs(int(batch.tend[i]) - int(batch.tstart[i])):
                 raise AssertionError(f"read {i}: CIGAR does not span the aligned slice / target interval")
             bases[sa:sb] = comp[seq[sa:sb][::-1]] if batch.rev[i] else seq[sa:sb]
         return dict(n=n, seg=batch.contig.astype(np.int32), tstart=np.minimum(batch.tstart, batch.tend).astype(np.int64),
                     barcode=batch.barcode.astype(np.int32), cig_off=cig_off, cigar=ops[:max(w, 1)].copy(),
-                    base_off=batch.seq_off.astype(np.int64), bases=bases if len(bases) else np.zeros(1, np.uint8))
+                    base_off=b_seq_off.astype(np.int64), bases=bases if len(bases) else np.zeros(1, np.uint8))
 
     def ingest_device(self, d: dict) -> None:
         """`d`: the dict of `pack_for_device` with every array replaced by a CUDA tensor on this device."""

@@ -135,6 +135,22 @@ int bossgpu_ingest_records(bossgpu_handle* h, int64_t n_reads,
                            const int64_t* seq_off, const char* seq_text,
                            int n_threads);
 
+/* ingest_records_ptr: as ingest_records, but the text stays where the caller has it: cigar_ptr[i] points at
+ * cigar_len[i] characters, seq_ptr[i] at the read's characters of which [seq_from[i], seq_to[i]) is the
+ * aligned slice (original orientation). Lets a Python caller pass the buffers of its str objects without
+ * joining or copying them. */
+int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads,
+                               const int32_t* contig, const int64_t* tstart, const int64_t* tend,
+                               const int32_t* barcode, const uint8_t* rev,
+                               const uint64_t* cigar_ptr, const int64_t* cigar_len,
+                               const uint64_t* seq_ptr, const int64_t* seq_from, const int64_t* seq_to,
+                               int n_threads);
+
+/* Multi-shard geometry and halo staging (see bossgpu_update_phase) */
+int bossgpu_set_shards(bossgpu_handle* h, int32_t n_shards, int32_t shard_index, const int64_t* row_start);
+int bossgpu_halo_pack(bossgpu_handle* h);
+int bossgpu_halo_unpack(bossgpu_handle* h);
+
 /* Host tokenizer on its own (no device work): CIGAR text -> packed ops. Returns the number of ops
  * written (<= cap) or a negative error; ref_span/query_span receive the spans the ops consume. */
 int64_t bossgpu_tokenize_cigar(const char* text, int64_t len, uint32_t* out, int64_t cap,
@@ -157,7 +173,12 @@ typedef struct bossgpu_update_params {
     const double* fhat_windows;       /* HOST [n_windows_total][2]: F-hat per 2 kb window before expansion
                                          (readstartdist.py:86-115); NULL keeps the previous upload */
     int32_t write_debug;              /* != 0: also keep S_mu and expected benefit for the getters */
-    int32_t reserved;
+    int32_t fhat_from_counts;         /* != 0: derive F-hat on the device from the counts added with
+                                         bossgpu_read_starts_add, using the three scalars below
+                                         (readstartdist.py:96-115): (alpha + C) / denom where C > 0, else zero_value */
+    double  rs_alpha;
+    double  rs_denom;                 /* 2 * n_windows * alpha + sum(C) */
+    double  rs_zero_value;            /* (1 - p0' * B(alpha, ..+sum C) / B(alpha, ..)) * alpha / denom */
 } bossgpu_update_params;
 
 typedef struct bossgpu_update_result {
@@ -205,6 +226,21 @@ int bossgpu_get_strat_all(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
 /* same bits packed little-endian, 8 per byte, over the flattened [row][strand][barcode] order */
 int bossgpu_get_strat_packed(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
 int64_t bossgpu_strat_rows(bossgpu_handle* h, int32_t seg);   /* seg = -1: all segments */
+
+/* Pinned host mirror of every segment's strategy, back to back in the layout of bossgpu_get_strat_all. The
+ * library refreshes it at the end of every update that derives a strategy, so callers can wrap it once
+ * (zero-copy) instead of copying masks out after each update. Valid until bossgpu_destroy. */
+int bossgpu_strat_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes);
+/* accepted entries per segment and strand after the last update, int64 [n_segments][2]
+ * (numerators of the per-contig log line, core.py:152-154) */
+int bossgpu_get_seg_accept(bossgpu_handle* h, int64_t* out, int64_t n);
+
+/* Read-start counts on the device. Replaces the accumulation half of ReadStartDist.count_read_starts
+ * (boss/runs/readstartdist.py:68-82): window = global index of the 2 kb window (contigs_filt order,
+ * int(L/2000) windows per contig; entries outside [0, n_windows_total) are dropped like np.histogram drops
+ * out-of-range starts), strand 0 forward / 1 reverse. */
+int bossgpu_read_starts_add(bossgpu_handle* h, int64_t n, const int64_t* window, const uint8_t* strand);
+int bossgpu_get_read_starts(bossgpu_handle* h, int64_t* out, int64_t n);   /* int64 [n_windows_total][2] */
 
 /* Contig.coverage uint16 [len][5][n_barcodes] (reference.py:77) */
 int bossgpu_get_coverage(bossgpu_handle* h, int32_t seg, uint16_t* out, int64_t out_elems);
