@@ -352,19 +352,24 @@ extern "C" int bossgpu_synchronize(bossgpu_handle* h) {
 // ingest
 // ------------------------------------------------------------------------------------------------
 static int launch_scatter(bossgpu_handle* h, int64_t n_reads, const int32_t* d_seg, const int64_t* d_tstart,
-                          const int32_t* d_bc, const int64_t* d_cig_off, const uint32_t* d_cig,
-                          const int64_t* d_base_off, const uint8_t* d_bases, int ascii, bool count_totals) {
+                          const int32_t* d_bc, const int64_t* d_cig_off, const int64_t* d_cig_end, const uint32_t* d_cig,
+                          const int64_t* d_base_off, const uint8_t* d_bases, const uint8_t* d_rev, int ascii, bool count_totals,
+                          bool check_spans = true) {
     BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    k_check_spans<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_cig_off, d_cig, d_base_off, h->d_ingest_err);
-    BOSS_KERNEL_CHECK();
+    if (check_spans) {
+        k_check_spans<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_cig_off, d_cig_end, d_cig, d_base_off,
+                                                                              h->d_ingest_err);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
     unsigned grid = (unsigned)std::min<int64_t>(n_reads, 1 << 20);
-    k_scatter<<<grid, SC_THREADS, 0, h->stream>>>(n_reads, d_seg, d_tstart, d_bc, d_cig_off, d_cig, d_base_off, d_bases,
-                                                  ascii, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
+    k_scatter<<<grid, SC_THREADS, 0, h->stream>>>(n_reads, d_seg, d_tstart, d_bc, d_cig_off, d_cig_end, d_cig, d_base_off, d_bases,
+                                                  d_rev, ascii, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
                                                   count_totals ? 1 : 0, h->d_ingest_err);
     BOSS_KERNEL_CHECK();
     BOSS_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->ev_valid[0] = true;
-    h->launches += 2;
+    h->launches++;
     return 0;
 }
 
@@ -406,7 +411,8 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
     if (n_reads == 0) return 0;
     if (!seg || !tstart || !barcode || !cig_off || !cigar || !base_off || !bases) return fail(BOSSGPU_EINVAL, "null batch array");
     if (on_device) {
-        TRY(launch_scatter(h, n_reads, seg, tstart, barcode, cig_off, cigar, base_off, bases, base_is_ascii, contig_cov_add == nullptr));
+        TRY(launch_scatter(h, n_reads, seg, tstart, barcode, cig_off, cig_off + 1, cigar, base_off, bases, nullptr, base_is_ascii,
+                           contig_cov_add == nullptr));
         return 0;   // errors surface at the next update / synchronize-checked call
     }
     const int64_t n_ops = cig_off[n_reads], n_bases = base_off[n_reads];
@@ -432,8 +438,8 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
     BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
     char* ds = (char*)h->stage_d;
     TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
-                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
-                       (const uint8_t*)(ds + o_bs), base_is_ascii, contig_cov_add == nullptr));
+                       (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_co) + 1, (const uint32_t*)(ds + o_cg),
+                       (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), nullptr, base_is_ascii, contig_cov_add == nullptr));
     return check_ingest_error(h);
 }
 
@@ -471,13 +477,18 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* c
     int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
     if (n_reads < 64) T = 1;
     T = (int)std::min<int64_t>(T, n_reads);
-    // ---- pass 1 (parallel): count ops and spans per read -------------------------------------------------
+    // ---- staging blob: every read gets its worst-case CIGAR slot (an op needs >= 2 characters), so one
+    //      parallel pass tokenises in place and copies the slices; no counting pass, no compaction ----------
     std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads);
     std::vector<int64_t> cut(T + 1, 0);
+    int64_t total_chars = 0, ops_cap = 0, total_bases = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        total_chars += reads[i].cigar_len + reads[i].seq_len;
+        ops_cap += reads[i].cigar_len / 2 + 1;
+        total_bases += reads[i].seq_len;
+    }
     {
         // split by characters so long reads do not pile up in one thread
-        int64_t total_chars = 0;
-        for (int64_t i = 0; i < n_reads; ++i) total_chars += reads[i].cigar_len + reads[i].seq_len;
         int64_t per = total_chars / T + 1, acc = 0;
         int t = 1;
         for (int64_t i = 0; i < n_reads && t < T; ++i) {
@@ -486,39 +497,15 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* c
         }
         for (; t <= T; ++t) cut[t] = n_reads;
     }
-    auto run_parallel = [&](auto&& fn) {
-        if (T == 1) { fn(0, n_reads); return; }
-        std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) if (cut[t + 1] > cut[t]) pool.emplace_back(fn, cut[t], cut[t + 1]);
-        for (auto& th : pool) th.join();
-    };
-    run_parallel([&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i)
-            n_ops[i] = tokenize_cigar(reads[i].cigar, reads[i].cigar_len, nullptr, 0, &rspan[i], &qspan[i]);
-    });
-    const double ms_pass1 = ms_since(t_begin);
-    // ---- validate like upstream, lay out the staging blob --------------------------------------------------
-    int64_t total_ops = 0, total_bases = 0;
-    for (int64_t i = 0; i < n_reads; ++i) {
-        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
-        if (qspan[i] != reads[i].seq_len)
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
-                        (long long)i, (long long)qspan[i], (long long)reads[i].seq_len);
-        if (rspan[i] != t1 - t0)
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
-                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
-        if (contig[i] < 0 || contig[i] >= h->n_contigs_total)
-            return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
-        total_ops += n_ops[i];
-        total_bases += reads[i].seq_len;
-    }
     size_t o_seg = 0;
     size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
     size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
     size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
-    size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_cg = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(total_ops, 1), 16);
+    size_t o_ce = o_co + round_up(sizeof(int64_t) * n_reads, 16);
+    size_t o_bo = o_ce + round_up(sizeof(int64_t) * n_reads, 16);
+    size_t o_rv = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_cg = o_rv + round_up((size_t)n_reads, 16);
+    size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
     size_t total = o_bs + round_up(std::max<int64_t>(total_bases, 1), 16);
     TRY(ensure_stage(h, total));
     char* hs = (char*)h->stage_h;
@@ -526,37 +513,65 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* c
     int32_t* s_bc = (int32_t*)(hs + o_bc);
     int64_t* s_ts = (int64_t*)(hs + o_ts);
     int64_t* s_co = (int64_t*)(hs + o_co);
+    int64_t* s_ce = (int64_t*)(hs + o_ce);
     int64_t* s_bo = (int64_t*)(hs + o_bo);
+    uint8_t* s_rv = (uint8_t*)(hs + o_rv);
     uint32_t* s_cg = (uint32_t*)(hs + o_cg);
     uint8_t* s_bs = (uint8_t*)(hs + o_bs);
-    s_co[0] = 0; s_bo[0] = 0;
-    for (int64_t i = 0; i < n_reads; ++i) {
-        s_seg[i] = seg_of_contig[contig[i]];
-        s_bc[i] = barcode[i];
-        s_ts[i] = std::min(tstart[i], tend[i]);
-        s_co[i + 1] = s_co[i] + n_ops[i];
-        s_bo[i + 1] = s_bo[i] + reads[i].seq_len;
-    }
-    const double ms_layout = ms_since(t_begin);
-    // ---- pass 2 (parallel): tokenise into place, copy / reverse-complement the slices into pinned memory ----
-    run_parallel([&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            int64_t r, q;
-            tokenize_cigar(reads[i].cigar, reads[i].cigar_len, s_cg + s_co[i], n_ops[i], &r, &q);
-            if (rev[i]) revcomp_copy(reads[i].seq, reads[i].seq_len, (char*)s_bs + s_bo[i]);       // boss/utils.py:85-95
-            else memcpy(s_bs + s_bo[i], reads[i].seq, (size_t)reads[i].seq_len);
+    {
+        int64_t co = 0, bo = 0;
+        for (int64_t i = 0; i < n_reads; ++i) {
+            if (contig[i] < 0 || contig[i] >= h->n_contigs_total)
+                return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
+            s_seg[i] = seg_of_contig[contig[i]];
+            s_bc[i] = barcode[i];
+            s_ts[i] = std::min(tstart[i], tend[i]);
+            s_rv[i] = rev[i] ? 1 : 0;
+            s_co[i] = co;
+            s_bo[i] = bo;
+            co += reads[i].cigar_len / 2 + 1;
+            bo += reads[i].seq_len;
         }
-    });
+        s_bo[n_reads] = bo;
+    }
+    const double ms_pass1 = ms_since(t_begin);
+    const double ms_layout = ms_pass1;
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            n_ops[i] = tokenize_cigar(reads[i].cigar, reads[i].cigar_len, s_cg + s_co[i], reads[i].cigar_len / 2 + 1, &rspan[i], &qspan[i]);
+            s_ce[i] = s_co[i] + std::max<int64_t>(n_ops[i], 0);
+            // slices stay in sequencing orientation; the scatter kernel reverse-complements on the fly
+            memcpy(s_bs + s_bo[i], reads[i].seq, (size_t)reads[i].seq_len);
+        }
+    };
+    if (T == 1) work(0, n_reads);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) if (cut[t + 1] > cut[t]) pool.emplace_back(work, cut[t], cut[t + 1]);
+        for (auto& th : pool) th.join();
+    }
+    // validate like upstream before anything reaches the counters
+    for (int64_t i = 0; i < n_reads; ++i) {
+        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
+        if (n_ops[i] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
+        if (qspan[i] != reads[i].seq_len)
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
+                        (long long)i, (long long)qspan[i], (long long)reads[i].seq_len);
+        if (rspan[i] != t1 - t0)
+            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
+                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
+    }
     const double ms_pass2 = ms_since(t_begin);
     BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
     char* ds = (char*)h->stage_d;
     TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
-                       (const int64_t*)(ds + o_co), (const uint32_t*)(ds + o_cg), (const int64_t*)(ds + o_bo),
-                       (const uint8_t*)(ds + o_bs), /*ascii=*/1, /*count_totals=*/true));
+                       (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_ce), (const uint32_t*)(ds + o_cg),
+                       (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), (const uint8_t*)(ds + o_rv), /*ascii=*/1,
+                       /*count_totals=*/true, /*check_spans=*/false));
     int rc = check_ingest_error(h);
     if (trace)
-        fprintf(stderr, "[bossgpu] ingest %lld reads, %d threads (hw %u): count %.2f ms, layout %.2f, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
-                (long long)n_reads, T, std::thread::hardware_concurrency(), ms_pass1, ms_layout - ms_pass1, ms_pass2 - ms_layout,
+        fprintf(stderr, "[bossgpu] ingest %lld reads, %d threads (hw %u): layout %.2f ms, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
+                (long long)n_reads, T, std::thread::hardware_concurrency(), ms_layout, ms_pass2 - ms_layout,
                 ms_since(t_begin) - ms_pass2, total);
     return rc;
 }

@@ -45,9 +45,10 @@ __device__ __forceinline__ void add_u16_pair(unsigned* word, unsigned add) {
 // one CTA per read
 __global__ void __launch_bounds__(SC_THREADS)
 k_scatter(int64_t n_reads, const int32_t* __restrict__ seg_of, const int64_t* __restrict__ tstart,
-          const int32_t* __restrict__ barcode, const int64_t* __restrict__ cig_off,
+          const int32_t* __restrict__ barcode, const int64_t* __restrict__ cig_off, const int64_t* __restrict__ cig_end,
           const uint32_t* __restrict__ cigar, const int64_t* __restrict__ base_off,
-          const uint8_t* __restrict__ bases, int base_is_ascii, const SegDev* __restrict__ segs, int n_seg,
+          const uint8_t* __restrict__ bases, const uint8_t* __restrict__ rev, int base_is_ascii,
+          const SegDev* __restrict__ segs, int n_seg,
           int nb, int64_t P, uint16_t* __restrict__ cov, unsigned long long* __restrict__ cov_total,
           int count_totals, int32_t* __restrict__ err) {
     using Scan = cub::BlockScan<Span2, SC_THREADS>;
@@ -62,8 +63,11 @@ k_scatter(int64_t n_reads, const int32_t* __restrict__ seg_of, const int64_t* __
         const SegDev S = segs[sg];
         int b = barcode[read];
         if (b < 0 || b >= nb) b = 0;                     // Q11: unknown / unclassified -> index 0
-        const int64_t c0 = cig_off[read], c1 = cig_off[read + 1];
+        const int64_t c0 = cig_off[read], c1 = cig_end[read];
         const int64_t q0 = base_off[read], q1 = base_off[read + 1];
+        // reverse-strand reads arrive in sequencing orientation: walk the slice backwards and complement
+        // (boss/utils.py:85-95: ATGC <-> TACG, everything else unchanged)
+        const bool is_rev = rev != nullptr && rev[read] != 0;
         const int64_t t0 = tstart[read];
         int64_t ref_done = 0, q_done = 0;
         unsigned long long in_seg = 0;
@@ -110,9 +114,15 @@ k_scatter(int64_t n_reads, const int32_t* __restrict__ seg_of, const int64_t* __
                     if (s_cls[lo] == 2) {
                         code = 4;                    // deletion column (sequences.py:792-793)
                     } else {
-                        int64_t qi = q0 + q_done + s_q[lo] + (p - s_r[lo]);
-                        unsigned ch = qi < q1 ? bases[qi] : 0xFFu;
-                        code = base_is_ascii ? base_code_ascii(ch) : ch;
+                        const int64_t k = q_done + s_q[lo] + (p - s_r[lo]);     // index in alignment orientation
+                        const int64_t qi = is_rev ? q1 - 1 - k : q0 + k;
+                        unsigned ch = (qi >= q0 && qi < q1) ? bases[qi] : 0xFFu;
+                        if (base_is_ascii) {
+                            if (is_rev) ch = ch == 'A' ? 'T' : ch == 'T' ? 'A' : ch == 'G' ? 'C' : ch == 'C' ? 'G' : ch;
+                            code = base_code_ascii(ch);
+                        } else {
+                            code = (is_rev && ch < 4u) ? 3u - ch : ch;
+                        }
                     }
                     int64_t site = t0 + ref_done + p - S.start;          // segment-local
                     if (code > 4) {
@@ -159,12 +169,12 @@ k_scatter(int64_t n_reads, const int32_t* __restrict__ seg_of, const int64_t* __
 // span check of a tokenised batch: ref span must equal tend-tstart is checked on the host; this
 // kernel verifies that the read slice is exactly consumed (upstream: NumPy shape error at
 // sequences.py:785 when len(int_seq[start:end]) != number of non-deletion columns)
-__global__ void k_check_spans(int64_t n_reads, const int64_t* __restrict__ cig_off, const uint32_t* __restrict__ cigar,
-                              const int64_t* __restrict__ base_off, int32_t* __restrict__ err) {
+__global__ void k_check_spans(int64_t n_reads, const int64_t* __restrict__ cig_off, const int64_t* __restrict__ cig_end,
+                              const uint32_t* __restrict__ cigar, const int64_t* __restrict__ base_off, int32_t* __restrict__ err) {
     int64_t read = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (read >= n_reads) return;
     int64_t q = 0;
-    for (int64_t i = cig_off[read]; i < cig_off[read + 1]; ++i) {
+    for (int64_t i = cig_off[read]; i < cig_end[read]; ++i) {
         unsigned op = cigar[i];
         if ((op & 15u) != 2u) q += op >> 4;
     }
