@@ -18,7 +18,7 @@ BIN, BUCKET, RSD_WINDOW, FREEZE = 100, 20_000, 2000, 30
 N_PATTERNS, N_STEPS, HIST_BINS, N_TIMERS = 278_256, 10, 1088, 8
 
 OK, EINVAL, ECUDA, ENOMEM, EBASE, ESHAPE, ESTATE, EEMPTY = 0, -1, -2, -3, -4, -5, -6, -7
-BUF_SWITCH, BUF_NORM, BUF_HIST, BUF_MASK, BUF_HALO_SEND, BUF_HALO_RECV = range(6)
+BUF_SWITCH, BUF_NORM, BUF_HIST, BUF_MASK, BUF_HALO_SEND, BUF_HALO_RECV, BUF_STRAT, BUF_COV_TOTAL = range(8)
 
 
 class BossGpuError(RuntimeError):

@@ -460,51 +460,73 @@ struct TextRead {
     const char* seq;   int64_t seq_len;       // the slice itself, original orientation
 };
 
-static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* contig, const int64_t* tstart,
                             const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
-                            const std::vector<TextRead>& reads, int n_threads) {
-    // map global contig -> local segment (text API is for whole-contig shards; split shards use ingest_packed)
+                            const std::vector<TextRead>& all_reads, int n_threads) {
+    // The caller hands every shard the WHOLE batch. A shard holds one contiguous range of the genome axis, so
+    // at most one of its segments belongs to any contig: reads are routed to that segment when they overlap
+    // it (the scatter kernel clips at the segment edges, so a read spanning a shard edge lands in both
+    // shards), and the depth total of every contig (dropout rule, reference.py:157-158) advances by the
+    // reference span of ALL the batch's reads on it, local or not.
     std::vector<int32_t> seg_of_contig(h->n_contigs_total, -1);
     for (int s = 0; s < h->n_seg; ++s) {
-        if (h->segs[s].start != 0 || !h->segs[s].is_tail)
-            return fail(BOSSGPU_ESTATE, "the text ingest path needs whole-contig segments");
+        if (seg_of_contig[h->segs[s].contig] >= 0)
+            return fail(BOSSGPU_ESTATE, "the text ingest path needs at most one segment per contig in a shard");
         seg_of_contig[h->segs[s].contig] = s;
     }
     const bool trace = getenv("BOSSGPU_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
     auto t_begin = now();
+    std::vector<int64_t> sel;
+    sel.reserve((size_t)n_all);
+    std::vector<unsigned long long> cov_add((size_t)h->n_contigs_total, 0ull);
+    for (int64_t i = 0; i < n_all; ++i) {
+        if (contig[i] < 0 || contig[i] >= h->n_contigs_total)
+            return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
+        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
+        cov_add[contig[i]] += (unsigned long long)(t1 - t0);
+        const int32_t sg = seg_of_contig[contig[i]];
+        if (sg < 0) continue;
+        const SegDev& S = h->segs[sg];
+        if (t1 <= S.start || t0 >= S.start + S.len) continue;
+        sel.push_back(i);
+    }
+    const int64_t n_reads = (int64_t)sel.size();
     int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
     if (n_reads < 64) T = 1;
-    T = (int)std::min<int64_t>(T, n_reads);
+    T = (int)std::max<int64_t>(1, std::min<int64_t>(T, n_reads));
     // ---- staging blob: every read gets its worst-case CIGAR slot (an op needs >= 2 characters), so one
     //      parallel pass tokenises in place and copies the slices; no counting pass, no compaction ----------
     std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads);
     std::vector<int64_t> cut(T + 1, 0);
     int64_t total_chars = 0, ops_cap = 0, total_bases = 0;
-    for (int64_t i = 0; i < n_reads; ++i) {
-        total_chars += reads[i].cigar_len + reads[i].seq_len;
-        ops_cap += reads[i].cigar_len / 2 + 1;
-        total_bases += reads[i].seq_len;
+    for (int64_t j = 0; j < n_reads; ++j) {
+        const TextRead& R = all_reads[sel[j]];
+        total_chars += R.cigar_len + R.seq_len;
+        ops_cap += R.cigar_len / 2 + 1;
+        total_bases += R.seq_len;
     }
     {
         // split by characters so long reads do not pile up in one thread
         int64_t per = total_chars / T + 1, acc = 0;
         int t = 1;
-        for (int64_t i = 0; i < n_reads && t < T; ++i) {
-            acc += reads[i].cigar_len + reads[i].seq_len;
-            if (acc >= per * t) cut[t++] = i + 1;
+        for (int64_t j = 0; j < n_reads && t < T; ++j) {
+            acc += all_reads[sel[j]].cigar_len + all_reads[sel[j]].seq_len;
+            if (acc >= per * t) cut[t++] = j + 1;
         }
         for (; t <= T; ++t) cut[t] = n_reads;
     }
+    const int64_t nr1 = std::max<int64_t>(n_reads, 1);
     size_t o_seg = 0;
-    size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
-    size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
-    size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
-    size_t o_ce = o_co + round_up(sizeof(int64_t) * n_reads, 16);
-    size_t o_bo = o_ce + round_up(sizeof(int64_t) * n_reads, 16);
-    size_t o_rv = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_cg = o_rv + round_up((size_t)n_reads, 16);
+    size_t o_bc = o_seg + round_up(sizeof(int32_t) * nr1, 16);
+    size_t o_ts = o_bc + round_up(sizeof(int32_t) * nr1, 16);
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * nr1, 16);
+    size_t o_ce = o_co + round_up(sizeof(int64_t) * nr1, 16);
+    size_t o_bo = o_ce + round_up(sizeof(int64_t) * nr1, 16);
+    size_t o_rv = o_bo + round_up(sizeof(int64_t) * (nr1 + 1), 16);
+    size_t o_ca = o_rv + round_up((size_t)nr1, 16);
+    size_t o_cg = o_ca + round_up(sizeof(unsigned long long) * h->n_contigs_total, 16);
     size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
     size_t total = o_bs + round_up(std::max<int64_t>(total_bases, 1), 16);
     TRY(ensure_stage(h, total));
@@ -518,30 +540,30 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* c
     uint8_t* s_rv = (uint8_t*)(hs + o_rv);
     uint32_t* s_cg = (uint32_t*)(hs + o_cg);
     uint8_t* s_bs = (uint8_t*)(hs + o_bs);
+    memcpy(hs + o_ca, cov_add.data(), sizeof(unsigned long long) * h->n_contigs_total);
     {
         int64_t co = 0, bo = 0;
-        for (int64_t i = 0; i < n_reads; ++i) {
-            if (contig[i] < 0 || contig[i] >= h->n_contigs_total)
-                return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
-            s_seg[i] = seg_of_contig[contig[i]];
-            s_bc[i] = barcode[i];
-            s_ts[i] = std::min(tstart[i], tend[i]);
-            s_rv[i] = rev[i] ? 1 : 0;
-            s_co[i] = co;
-            s_bo[i] = bo;
-            co += reads[i].cigar_len / 2 + 1;
-            bo += reads[i].seq_len;
+        for (int64_t j = 0; j < n_reads; ++j) {
+            const int64_t i = sel[j];
+            s_seg[j] = seg_of_contig[contig[i]];
+            s_bc[j] = barcode[i];
+            s_ts[j] = std::min(tstart[i], tend[i]);
+            s_rv[j] = rev[i] ? 1 : 0;
+            s_co[j] = co;
+            s_bo[j] = bo;
+            co += all_reads[i].cigar_len / 2 + 1;
+            bo += all_reads[i].seq_len;
         }
         s_bo[n_reads] = bo;
     }
-    const double ms_pass1 = ms_since(t_begin);
-    const double ms_layout = ms_pass1;
+    const double ms_layout = ms_since(t_begin);
     auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            n_ops[i] = tokenize_cigar(reads[i].cigar, reads[i].cigar_len, s_cg + s_co[i], reads[i].cigar_len / 2 + 1, &rspan[i], &qspan[i]);
-            s_ce[i] = s_co[i] + std::max<int64_t>(n_ops[i], 0);
+        for (int64_t j = lo; j < hi; ++j) {
+            const TextRead& R = all_reads[sel[j]];
+            n_ops[j] = tokenize_cigar(R.cigar, R.cigar_len, s_cg + s_co[j], R.cigar_len / 2 + 1, &rspan[j], &qspan[j]);
+            s_ce[j] = s_co[j] + std::max<int64_t>(n_ops[j], 0);
             // slices stay in sequencing orientation; the scatter kernel reverse-complements on the fly
-            memcpy(s_bs + s_bo[i], reads[i].seq, (size_t)reads[i].seq_len);
+            memcpy(s_bs + s_bo[j], R.seq, (size_t)R.seq_len);
         }
     };
     if (T == 1) work(0, n_reads);
@@ -551,27 +573,33 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_reads, const int32_t* c
         for (auto& th : pool) th.join();
     }
     // validate like upstream before anything reaches the counters
-    for (int64_t i = 0; i < n_reads; ++i) {
+    for (int64_t j = 0; j < n_reads; ++j) {
+        const int64_t i = sel[j];
         const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
-        if (n_ops[i] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
-        if (qspan[i] != reads[i].seq_len)
+        if (n_ops[j] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
+        if (qspan[j] != all_reads[i].seq_len)
             return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
-                        (long long)i, (long long)qspan[i], (long long)reads[i].seq_len);
-        if (rspan[i] != t1 - t0)
+                        (long long)i, (long long)qspan[j], (long long)all_reads[i].seq_len);
+        if (rspan[j] != t1 - t0)
             return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
-                        (long long)i, (long long)rspan[i], (long long)(t1 - t0));
+                        (long long)i, (long long)rspan[j], (long long)(t1 - t0));
     }
     const double ms_pass2 = ms_since(t_begin);
     BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
     char* ds = (char*)h->stage_d;
-    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
-                       (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_ce), (const uint32_t*)(ds + o_cg),
-                       (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), (const uint8_t*)(ds + o_rv), /*ascii=*/1,
-                       /*count_totals=*/true, /*check_spans=*/false));
+    k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total, (const unsigned long long*)(ds + o_ca),
+                                                                                 h->n_contigs_total);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    if (n_reads > 0)
+        TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+                           (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_ce), (const uint32_t*)(ds + o_cg),
+                           (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), (const uint8_t*)(ds + o_rv), /*ascii=*/1,
+                           /*count_totals=*/false, /*check_spans=*/false));
     int rc = check_ingest_error(h);
     if (trace)
-        fprintf(stderr, "[bossgpu] ingest %lld reads, %d threads (hw %u): layout %.2f ms, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
-                (long long)n_reads, T, std::thread::hardware_concurrency(), ms_layout, ms_pass2 - ms_layout,
+        fprintf(stderr, "[bossgpu] ingest %lld of %lld reads, %d threads (hw %u): layout %.2f ms, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
+                (long long)n_reads, (long long)n_all, T, std::thread::hardware_concurrency(), ms_layout, ms_pass2 - ms_layout,
                 ms_since(t_begin) - ms_pass2, total);
     return rc;
 }
@@ -854,13 +882,35 @@ static int pack_own_mask(bossgpu_handle* h);
 extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_params* p, bossgpu_update_result* r) {
     H_CHECK(h);
     TRY(validate_params(p));
-    if (phase != 0 && phase != h->phase_done + 1) return fail(BOSSGPU_ESTATE, "phase %d after phase %d", phase, h->phase_done);
+    // phase 4 may follow phase 0 directly: with every bucket still off the strategy half is skipped (core.py:172)
+    if (phase != 0 && phase != h->phase_done + 1 && !(phase == 4 && h->phase_done == 0))
+        return fail(BOSSGPU_ESTATE, "phase %d after phase %d", phase, h->phase_done);
     switch (phase) {
         case 0: EV_BEGIN(7); TRY(phase0_scores(h, p)); break;
         case 1: TRY(upload_fhat(h, p)); TRY(phase1_smooth(h, p)); break;
         case 2: TRY(phase2_hist(h, p)); break;
         case 3: TRY(phase3_threshold(h, p)); TRY(pack_own_mask(h)); break;
-        case 4: TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_all : nullptr)); EV_END(7); TRY(fetch_result(h, r)); break;
+        case 4:
+            // upstream raises on an all-zero benefit before touching any strategy (sequences.py:588); the flag is
+            // the same on every shard because the histogram it derives from has been allreduced
+            BOSS_CUDA(cudaMemcpyAsync(h->h_upd, h->d_upd, sizeof(UpdateDev), cudaMemcpyDeviceToHost, h->stream));
+            BOSS_CUDA(cudaStreamSynchronize(h->stream));
+            if (!h->h_upd->switched_on) {          // (allreduced) switch still off: leave every strategy as it is
+                EV_END(7);
+                TRY(fetch_result(h, r));
+                break;
+            }
+            if (h->phase_done != 3) return fail(BOSSGPU_ESTATE, "a bucket is on but phases 1-3 were skipped");
+            if (h->h_upd->empty) {
+                EV_END(7);
+                h->phase_done = -1;
+                fetch_result(h, r);
+                return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
+            }
+            TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_all : nullptr));
+            EV_END(7);
+            TRY(fetch_result(h, r));
+            break;
         default: return fail(BOSSGPU_EINVAL, "unknown phase %d", phase);
     }
     h->phase_done = phase == 4 ? -1 : phase;
@@ -962,6 +1012,8 @@ extern "C" int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_
         case BOSSGPU_BUF_HALO_RECV:
             if (!h->d_halo) return fail(BOSSGPU_ESTATE, "bossgpu_set_shards not called");
             *dev_ptr = (char*)h->d_halo + 2 * hb; *bytes = 2 * hb; break;
+        case BOSSGPU_BUF_COV_TOTAL: *dev_ptr = h->d_cov_total; *bytes = sizeof(unsigned long long) * h->n_contigs_total; break;
+        case BOSSGPU_BUF_STRAT: *dev_ptr = h->d_strat; *bytes = (size_t)h->n_srows * 2 * h->nb; break;
         default: return fail(BOSSGPU_EINVAL, "unknown exchange buffer %d", which);
     }
     return 0;

@@ -91,6 +91,7 @@ class Engine:
         h = C.c_void_p()
         check(self.lib.bossgpu_create(C.byref(cfg), C.byref(h)))
         self.h = h
+        self.device = int(device)
         self.halo_bins = int(halo_bins)
         self._mult = staircase_mult()
 
@@ -225,6 +226,36 @@ class Engine:
         p, n = C.c_void_p(), C.c_size_t()
         check(self.lib.bossgpu_exchange_buffer(self.h, which, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def exchange_tensor(self, which: int):
+        """The exchange buffer as a uint8 torch tensor ALIASING the library's device memory (no copy), for
+        torch.distributed collectives. torch is plumbing here: it never computes on these."""
+        import torch
+        ptr_, nbytes = self.exchange_buffer(which)
+
+        class _Dev:
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr_, False), "version": 2}
+        d._owner = self
+        return torch.as_tensor(d, device=torch.device("cuda", self.device))
+
+    def set_shards(self, n_shards: int, shard_index: int, row_start) -> None:
+        row_start = as_c(row_start, np.int64)
+        assert row_start.shape == (n_shards + 1,)
+        check(self.lib.bossgpu_set_shards(self.h, n_shards, shard_index, ptr(row_start)))
+
+    def halo_pack(self) -> None:
+        check(self.lib.bossgpu_halo_pack(self.h))
+
+    def halo_unpack(self) -> None:
+        check(self.lib.bossgpu_halo_unpack(self.h))
+
+    def params(self, approx_ccl, time_cost, bucket_threshold, debug: bool = False, fhat_windows=None, fhat_scalars=None):
+        """UpdateParams for `update_phase` (keeps the F-hat array alive on the returned object)."""
+        p, keep = self._params(approx_ccl, time_cost, bucket_threshold, fhat_windows, debug, fhat_scalars)
+        p._keep = keep
+        return p
 
     # -- results / state -------------------------------------------------------------------------
     def strat(self, seg: int, out: np.ndarray | None = None) -> np.ndarray:

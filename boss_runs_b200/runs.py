@@ -277,12 +277,8 @@ class BossRuns:
         self.read_starts = ReadStartDist(contigs=self.contigs_filt, strict=strict_upstream_asserts)
         self._names = list(self.contigs_filt.keys())
         self.cc = CoverageConverter({n: i for i, n in enumerate(self._names)})
-        self.engine = Engine(contig_lengths=[c.length for c in self.contigs_filt.values()],
-                             ref_codes=[c.seq_int for c in self.contigs_filt.values()],
-                             n_barcodes=self.nbarcodes, ploidy=ploidy, n_sites_total=int(self.ref.n_sites),
-                             device=device, stream=stream)
-        for i, c in enumerate(self.contigs_filt.values()):
-            c._bind(self.engine, i)
+        self.ploidy = ploidy
+        self._create_engine(device=device, stream=stream)
         self.batch = 0
         self._strat_views = None
         self.threshold: float | None = None
@@ -290,6 +286,15 @@ class BossRuns:
         if self.out_dir is not None:
             Path(self.out_dir, "masks").mkdir(parents=True, exist_ok=True)
             self._write_contig_strategies(self.ref.get_strategy_dict())
+
+    def _create_engine(self, device: int, stream) -> None:
+        """One GPU holds every contig whole. `sharding.ShardedRun` overrides this with one engine per shard."""
+        self.engine = Engine(contig_lengths=[c.length for c in self.contigs_filt.values()],
+                             ref_codes=[c.seq_int for c in self.contigs_filt.values()],
+                             n_barcodes=self.nbarcodes, ploidy=self.ploidy, n_sites_total=int(self.ref.n_sites),
+                             device=device, stream=stream)
+        for i, c in enumerate(self.contigs_filt.values()):
+            c._bind(self.engine, i)
 
     # -- output (core.py:59-69) ----------------------------------------------------------------------
     def _write_contig_strategies(self, contig_strats: dict[str, np.ndarray]) -> None:

@@ -1,0 +1,450 @@
+"""Multi-GPU strategy update: the genome axis split into contiguous shards, one per B200.
+
+The reference is a single process; per-contig work is independent upstream
+(boss/runs/core.py:83-86,95-99,107-108,119-121 are per-contig loops) and only three things couple positions:
+the box-filter support of the smoothing (reference.py:233-260), the single global threshold
+(sequences.py:566-649) and the row shift of `_distribute_strategy` (core.py:141,155; quirk Q2). So:
+
+  * `plan_shards` cuts the concatenated genome into N ranges balanced by sites. Cuts fall on contig ends or,
+    inside a contig, on multiples of the 20 kb bucket (so bucket sums, 100-site bins and 2 kb windows never
+    straddle a cut).
+  * every shard is handed the whole (small) batch; the library keeps the reads overlapping its range.
+  * one update = the same kernels as on one GPU, interleaved with five small exchanges
+    (include/bossgpu.h, bossgpu_update_phase):
+        halo of scores_ds bins to both neighbours (only meaningful where a contig is split),
+        allreduce(max) of the bucket switch, allreduce(max) of the normaliser bits,
+        allreduce(sum) of the integer-limb histogram (exact, so the threshold does not depend on N),
+        allgather of the packed merged mask (strategy row d reads merged row d, which may live next door).
+
+`ShardGroup` runs those exchanges either between the shards of ONE process (`LocalGroup`: N engines on one
+GPU — "virtual shards", used by the GPU parity tests and to dry-run the sharded path without N GPUs) or between
+processes with one shard each (`DistGroup`: torch.distributed, NCCL over NVLink on the GPU box, gloo in the CPU
+tests). torch is plumbing here; no numerics run in it.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from ._lib import BIN, BUCKET, BUF_SWITCH, BUF_NORM, BUF_HIST, BUF_MASK, BUF_HALO_SEND, BUF_HALO_RECV, BUF_STRAT, BUF_COV_TOTAL
+from .engine import Engine, SegmentSpec, UpdateOutcome
+from .runs import BossRuns, PackedBatch
+
+
+# ------------------------------------------------------------------------------------------------------
+# planning
+# ------------------------------------------------------------------------------------------------------
+def plan_shards(contig_lengths, n_shards: int) -> list[list[SegmentSpec]]:
+    """Split the concatenated contigs (contigs_filt order) into `n_shards` contiguous, non-empty ranges of
+    near-equal size. Inside a contig a cut must be a multiple of BUCKET that leaves at least one complete bucket
+    on its right (the tail segment owns the contig's extra last switch, which repeats the last complete bucket's
+    mean: reference.py:198-202, utils.py:215-217)."""
+    lens = [int(x) for x in contig_lengths]
+    if n_shards < 1:
+        raise ValueError("n_shards must be >= 1")
+    if any(L < BUCKET for L in lens):
+        raise ValueError("contigs shorter than one bucket cannot be tracked")
+    starts = np.concatenate(([0], np.cumsum(lens)))
+    total = int(starts[-1])
+
+    def candidates(k):
+        """allowed cut offsets inside contig k, plus its two ends"""
+        L = lens[k]
+        last = (L // BUCKET - 1) * BUCKET
+        return 0, L, (BUCKET, last) if last >= BUCKET else None
+
+    cuts = [0]
+    for i in range(1, n_shards):
+        want = total * i // n_shards
+        k = int(np.searchsorted(starts, want, side="right") - 1)
+        k = min(k, len(lens) - 1)
+        x = want - int(starts[k])
+        lo, hi, inner = candidates(k)
+        opts = [lo, hi]
+        if inner is not None:
+            c = int(round(x / BUCKET)) * BUCKET
+            opts.append(min(max(c, inner[0]), inner[1]))
+        best = min(opts, key=lambda o: abs(o - x))
+        g = int(starts[k]) + best
+        if g <= cuts[-1]:
+            # nearest allowed position is already taken: move right to the next allowed one
+            g = _next_cut_after(cuts[-1], lens, starts)
+            if g is None:
+                raise ValueError(f"cannot cut {len(lens)} contig(s) of {total} sites into {n_shards} shards")
+        cuts.append(g)
+    cuts.append(total)
+    if any(b <= a for a, b in zip(cuts, cuts[1:])):
+        raise ValueError(f"cannot cut {len(lens)} contig(s) of {total} sites into {n_shards} shards")
+    plan = []
+    for a, b in zip(cuts, cuts[1:]):
+        segs = []
+        k = int(np.searchsorted(starts, a, side="right") - 1)
+        pos = a
+        while pos < b:
+            c0, c1 = int(starts[k]), int(starts[k + 1])
+            end = min(b, c1)
+            segs.append(SegmentSpec(contig=k, start=pos - c0, length=end - pos))
+            pos = end
+            k += 1
+        plan.append(segs)
+    return plan
+
+
+def _next_cut_after(g, lens, starts):
+    k = int(np.searchsorted(starts, g, side="right") - 1)
+    while k < len(lens):
+        c0, L = int(starts[k]), lens[k]
+        x = g - c0
+        last = (L // BUCKET - 1) * BUCKET
+        c = (x // BUCKET + 1) * BUCKET
+        if x < L and last >= BUCKET and max(c, BUCKET) <= last:
+            return c0 + max(c, BUCKET)
+        if c0 + L > g and k + 1 < len(lens):
+            return c0 + L
+        k += 1
+    return None
+
+
+def merged_row_starts(contig_lengths, plan) -> np.ndarray:
+    """Global merged-row index (rows of the concatenated per-contig benefit arrays, L//100 + 1 per contig:
+    reference.py:225,254) of each shard's first row, plus the total."""
+    lens = np.asarray(contig_lengths, dtype=np.int64)
+    o_row = np.concatenate(([0], np.cumsum(lens // BIN + 1)))
+    out = [int(o_row[segs[0].contig] + segs[0].start // BIN) for segs in plan]
+    out.append(int(o_row[-1]))
+    return np.asarray(out, dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------------------------------
+# exchange groups
+# ------------------------------------------------------------------------------------------------------
+_NP = {"i32": np.int32, "i64": np.int64, "u8": np.uint8, "f64": np.float64}
+
+
+def _view(t, kind: str):
+    import torch
+    return t.view({"i32": torch.int32, "i64": torch.int64, "u8": torch.uint8, "f64": torch.float64}[kind])
+
+
+class LocalGroup:
+    """All shards live in this process (engines on one device): exchanges are copies between their buffers."""
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        self.n_shards = len(self.engines)
+        self.shard_ids = list(range(self.n_shards))
+        self.rank, self.world = 0, 1
+
+    def allreduce(self, which: int, op: str, kind: str):
+        ts = [_view(e.exchange_tensor(which), kind) for e in self.engines]
+        acc = ts[0].clone()
+        for t in ts[1:]:
+            acc = (acc.maximum(t) if op == "max" else acc + t)
+        for t in ts:
+            t.copy_(acc)
+        return acc
+
+    def allgather_mask(self) -> None:
+        ts = [e.exchange_tensor(BUF_MASK) for e in self.engines]
+        stride = ts[0].numel() // self.n_shards
+        for s, src in enumerate(ts):
+            for d, dst in enumerate(ts):
+                if d != s:
+                    dst[s * stride:(s + 1) * stride].copy_(src[s * stride:(s + 1) * stride])
+
+    def exchange_halos(self) -> None:
+        send = [_view(e.exchange_tensor(BUF_HALO_SEND), "f64") for e in self.engines]
+        recv = [_view(e.exchange_tensor(BUF_HALO_RECV), "f64") for e in self.engines]
+        h = send[0].numel() // 2
+        for s in range(self.n_shards):
+            if s > 0:
+                recv[s][:h].copy_(send[s - 1][h:])          # left neighbour's last bins
+            if s + 1 < self.n_shards:
+                recv[s][h:].copy_(send[s + 1][:h])          # right neighbour's first bins
+
+    def gather_strat(self):
+        """[(shard id, bool array [rows][2][nb])] of every shard, on the host."""
+        return [(s, e.strat_host()) for s, e in zip(self.shard_ids, self.engines)]
+
+    def agree(self, ok: bool) -> bool:
+        return ok
+
+    def barrier(self) -> None:
+        pass
+
+
+class DistGroup:
+    """One shard per process; exchanges are torch.distributed collectives on tensors aliasing the engine's
+    buffers (CUDA memory with NCCL, host memory with gloo in the CPU tests)."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.engines = [engine]
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_shards = self.world
+        self.shard_ids = [self.rank]
+        self._gather_buf = None
+
+    def allreduce(self, which: int, op: str, kind: str):
+        t = _view(self.engines[0].exchange_tensor(which), kind)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allgather_mask(self) -> None:
+        t = self.engines[0].exchange_tensor(BUF_MASK)
+        stride = t.numel() // self.world
+        self.dist.all_gather_into_tensor(t, t[self.rank * stride:(self.rank + 1) * stride].clone(), group=self.group)
+
+    def exchange_halos(self) -> None:
+        dist = self.dist
+        send = _view(self.engines[0].exchange_tensor(BUF_HALO_SEND), "f64")
+        recv = _view(self.engines[0].exchange_tensor(BUF_HALO_RECV), "f64")
+        h = send.numel() // 2
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, send[:h].contiguous(), self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[:h], self.rank - 1, self.group))
+        if self.rank + 1 < self.world:
+            ops.append(dist.P2POp(dist.isend, send[h:].contiguous(), self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[h:], self.rank + 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def gather_strat(self):
+        """Rank 0 (the process that writes boss.npz) receives every shard's strategy rows; the other ranks get
+        their own only."""
+        import torch
+        own = self.engines[0].exchange_tensor(BUF_STRAT)
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=own.device)
+        sizes[self.rank] = own.numel()
+        self.dist.all_reduce(sizes, group=self.group)
+        sizes = [int(x) for x in sizes.tolist()]
+        mx = max(sizes)
+        if self._gather_buf is None or self._gather_buf[0].numel() != mx * self.world:
+            dev = torch.empty(mx * self.world, dtype=torch.uint8, device=own.device)
+            host = torch.empty(mx * self.world, dtype=torch.uint8, pin_memory=own.is_cuda)
+            pad = torch.zeros(mx, dtype=torch.uint8, device=own.device)
+            self._gather_buf = (dev, host, pad)
+        dev, host, pad = self._gather_buf
+        pad[:own.numel()].copy_(own)
+        self.dist.all_gather_into_tensor(dev, pad, group=self.group)
+        nb = self.engines[0].nb
+        if self.rank != 0:
+            return [(self.rank, self.engines[0].strat_host())]
+        host.copy_(dev, non_blocking=True)
+        if own.is_cuda:
+            torch.cuda.current_stream(own.device).synchronize()
+        arr = host.numpy().view(np.bool_)
+        return [(s, arr[s * mx: s * mx + sizes[s]].reshape(-1, 2, nb)) for s in range(self.world)]
+
+    def agree(self, ok: bool) -> bool:
+        import torch
+        dev = self.engines[0].exchange_tensor(BUF_SWITCH).device
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def barrier(self) -> None:
+        self.dist.barrier(group=self.group)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the sharded run
+# ------------------------------------------------------------------------------------------------------
+class _Pieces:
+    """Engine-shaped accessor for a contig whose sites may be spread over several local segments: what
+    `runs.Contig` fetches through (`coverage`, `scores`, `scores_ds`, `benefit`, `buckets`)."""
+
+    def __init__(self, run: "ShardedRun"):
+        self.run = run
+
+    def _cat(self, contig: int, fn):
+        pieces = self.run._pieces[contig]
+        if not pieces or not self.run._complete[contig]:
+            raise RuntimeError("this contig has segments on other ranks; per-site state is only assembled for local contigs")
+        parts = [fn(e, i) for e, i in pieces]
+        return parts[0] if len(parts) == 1 else tuple(np.concatenate(x) for x in zip(*parts)) if isinstance(parts[0], tuple) \
+            else np.concatenate(parts)
+
+    def coverage(self, contig):
+        return self._cat(contig, lambda e, i: e.coverage(i))
+
+    def scores(self, contig, entropy=False):
+        return self._cat(contig, lambda e, i: e.scores(i, entropy=entropy))
+
+    def scores_ds(self, contig):
+        return self._cat(contig, lambda e, i: e.scores_ds(i))
+
+    def benefit(self, contig, debug=False):
+        return self._cat(contig, lambda e, i: e.benefit(i, debug=debug))
+
+    def buckets(self, contig):
+        pieces = self.run._pieces[contig]
+        sw = np.concatenate([e.buckets(i)[0] for e, i in pieces])
+        return sw, np.full(self.run.nbarcodes, bool(sw.any()))
+
+
+class ShardedRun(BossRuns):
+    """`BossRuns` over N shards. In a torch.distributed job (one process per GPU) every rank constructs it with
+    the same arguments and calls the same methods with the same batch; rank 0 ends up with every contig's
+    `strat` (and writes boss.npz). With `n_virtual` it instead drives that many shards on one GPU."""
+
+    def __init__(self, *args, n_virtual: int | None = None, halo_bins: int = 2048, group=None,
+                 engine_factory=Engine, **kw):
+        self._n_virtual = n_virtual
+        self._halo_bins = int(halo_bins)
+        self._dist_group = group
+        self._engine_factory = engine_factory
+        super().__init__(*args, **kw)
+
+    # -- construction ----------------------------------------------------------------------------------
+    def _create_engine(self, device: int, stream) -> None:
+        lens = [c.length for c in self.contigs_filt.values()]
+        codes = [c.seq_int for c in self.contigs_filt.values()]
+        if self._n_virtual is not None:
+            n, mine = int(self._n_virtual), list(range(int(self._n_virtual)))
+        else:
+            import torch.distributed as dist
+            n, mine = dist.get_world_size(self._dist_group), [dist.get_rank(self._dist_group)]
+        self.plan = plan_shards(lens, n)
+        self.row_start = merged_row_starts(lens, self.plan)
+        for segs in self.plan:
+            for s in segs:
+                head, tail = s.start == 0, s.start + s.length == lens[s.contig]
+                if not head and not tail and s.length // BIN < self._halo_bins:
+                    raise ValueError("a shard lies strictly inside a contig and is shorter than the bin halo")
+        self.engines = []
+        for sid in mine:
+            segs = self.plan[sid]
+            e = self._engine_factory(contig_lengths=lens, ref_codes=[codes[s.contig][s.start:s.start + s.length] for s in segs],
+                                     n_barcodes=self.nbarcodes, ploidy=self.ploidy, n_sites_total=int(self.ref.n_sites),
+                                     device=device, stream=stream, segments=segs, halo_bins=self._halo_bins)
+            e.set_shards(n, sid, self.row_start)
+            self.engines.append(e)
+        self.engine = self.engines[0]
+        self.group = LocalGroup(self.engines) if self._n_virtual is not None else DistGroup(self.engines[0], self._dist_group)
+        # contig -> [(engine, local segment index)] in position order, and whether that covers the contig
+        self._pieces = {k: [] for k in range(len(lens))}
+        for e in self.engines:
+            for i, s in enumerate(e.segments):
+                self._pieces[s.contig].append((e, i))
+        self._complete = {k: sum(e.segments[i].length for e, i in p) == lens[k] for k, p in self._pieces.items()}
+        view = _Pieces(self)
+        for k, c in enumerate(self.contigs_filt.values()):
+            c._bind(view, k)
+
+    def local_sites(self) -> int:
+        return int(sum(s.length for e in self.engines for s in e.segments))
+
+    def sync_depth_totals(self) -> None:
+        """After loading counters directly (set_coverage / synth_coverage): make every shard's per-contig depth
+        totals global. Batches ingested later keep them global on their own."""
+        self.group.allreduce(BUF_COV_TOTAL, "sum", "i64")
+
+    def synth_coverage(self, **kw) -> None:
+        for e in self.engines:
+            e.synth_coverage(**kw)
+        self.sync_depth_totals()
+
+    # -- coverage ---------------------------------------------------------------------------------------
+    def _effect_increments(self, increments: PackedBatch) -> None:
+        b = increments
+        err = None
+        try:
+            for e in self.engines:
+                e.ingest_records_ptr(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
+                                     b.seq_ptr, b.seq_from, b.seq_to)
+        except (IndexError, AssertionError, ValueError) as ex:        # what upstream raises for a bad record
+            err = ex
+        if not self.group.agree(err is None):
+            raise err if err is not None else RuntimeError("another shard rejected the batch")
+
+    def count_read_starts(self, paf_dict) -> None:
+        wins, strands = self.read_starts.count_read_starts(paf_dict=paf_dict)
+        for e in self.engines:                      # the window counts are small and replicated on every shard
+            e.read_starts_add(wins, strands)
+
+    # -- update -----------------------------------------------------------------------------------------
+    def _phases(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None, fhat_scalars=None) -> UpdateOutcome:
+        g = self.group
+        ps = [e.params(approx_ccl, time_cost, bucket_threshold, debug=self.write_debug, fhat_windows=fhat_windows,
+                       fhat_scalars=fhat_scalars) for e in self.engines]
+        w_max = max(int(np.max(np.asarray(approx_ccl) // BIN)), 4)
+        if w_max - 1 > self._halo_bins and g.n_shards > 1:
+            raise ValueError(f"staircase window of {w_max} bins exceeds the bin halo ({self._halo_bins}) kept on shard edges")
+        for e, p in zip(self.engines, ps):
+            e.update_phase(0, p)
+            e.halo_pack()
+        g.exchange_halos()
+        for e in self.engines:
+            e.halo_unpack()
+        on = bool(g.allreduce(BUF_SWITCH, "max", "i32").max().item())
+        if on:
+            for e, p in zip(self.engines, ps):
+                e.update_phase(1, p)
+            g.allreduce(BUF_NORM, "max", "i64")          # non-negative doubles order like their bit patterns
+            for e, p in zip(self.engines, ps):
+                e.update_phase(2, p)
+            g.allreduce(BUF_HIST, "sum", "i64")          # integer limbs: exact, order-free
+            for e, p in zip(self.engines, ps):
+                e.update_phase(3, p)
+            g.allgather_mask()
+        outs = [e.update_phase(4, p) for e, p in zip(self.engines, ps)]
+        out = outs[0]
+        if len(outs) > 1:
+            out.n_accept = (sum(o.n_accept[0] for o in outs), sum(o.n_accept[1] for o in outs))
+        return out
+
+    def update_wrapper(self) -> None:
+        scalars = self.read_starts.pointmass_scalars()
+        time_cost = getattr(self.rl_dist, "time_cost", None)
+        out = self._phases(self.rl_dist.approx_ccl, np.float64("nan") if time_cost is None else time_cost,
+                           self.bucket_threshold, fhat_scalars=scalars)
+        self.last = out
+        self._pull_switches()
+        if out.switched_on:
+            if time_cost is None:
+                self.rl_dist.time_cost      # AttributeError, as upstream (Q14)
+            self.threshold = out.threshold
+            self._pull_strategies()
+            if self.group.rank == 0:
+                self._write_contig_strategies(self.ref.get_strategy_dict())
+
+    def device_update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None) -> UpdateOutcome:
+        self.last = self._phases(approx_ccl, time_cost, bucket_threshold, fhat_windows=fhat_windows)
+        return self.last
+
+    def ingest_device(self, d: dict) -> None:
+        raise NotImplementedError("sharded runs ingest through the text path (each shard routes the batch itself)")
+
+    def _pull_switches(self) -> None:
+        for k, c in enumerate(self.contigs_filt.values()):
+            if self._complete[k]:
+                sw, on = _Pieces(self).buckets(k)
+                c.bucket_switches[...] = sw
+                c.switched_on[...] = on
+
+    def _pull_strategies(self) -> None:
+        """Gather every shard's strategy rows (rank 0 in a distributed job) and point `Contig.strat` at them:
+        views for contigs inside one shard, a concatenation for the few that are split."""
+        got = dict(self.group.gather_strat())
+        parts: dict[int, list] = {}
+        for sid, arr in got.items():
+            row = 0
+            for s in self.plan[sid]:
+                L = int(self.engine.contig_lengths[s.contig])
+                tail = s.start + s.length == L
+                n = (L // BIN - s.start // BIN) if tail else s.length // BIN
+                parts.setdefault(s.contig, []).append((s.start, arr[row: row + n]))
+                row += n
+        for k, c in enumerate(self.contigs_filt.values()):
+            ps = sorted(parts.get(k, []), key=lambda x: x[0])
+            if sum(p[1].shape[0] for p in ps) != c.length // BIN:
+                continue                                 # rows on other ranks: this rank is not the writer
+            c.strat = ps[0][1] if len(ps) == 1 else np.concatenate([p[1] for p in ps])
+            rows = max(c.strat.shape[0], 1)
+            logging.info(f"{c.name}: {c.strat[:, 0].sum() / rows}, {c.strat[:, 1].sum() / rows}")

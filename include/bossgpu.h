@@ -117,7 +117,11 @@ int  bossgpu_synchronize(bossgpu_handle* h);
  *   handle's device and no copy is made).
  * ingest_records: text form, tokenised by the library's C++ tokenizer (regex + translate upstream:
  *   sequences.py:672,762-776). seq slices are given in ORIGINAL read orientation together with
- *   rev[i]; the library reverse-complements (boss/utils.py:85-95: ATGC<->TACG only).
+ *   rev[i]; the library reverse-complements (boss/utils.py:85-95: ATGC<->TACG only). `contig` is the GLOBAL
+ *   index in contigs_filt order. Every shard is handed the WHOLE batch: the library keeps the reads that overlap
+ *   one of its segments (a shard holds at most one segment per contig; the scatter clips at its edges, so a read
+ *   spanning a shard edge is counted in both shards, each its own part) and advances every contig's depth total
+ *   by the reference span of all the batch's reads on it, so the dropout rule sees contig-wide depth on every shard.
  * contig_cov_add[k] (may be NULL): number of reference positions this batch adds to GLOBAL contig k
  *   over all shards — needed by the dropout rule (reference.py:158,175-177) when a contig is split;
  *   NULL means "this shard sees every read of its contigs" and the library counts by itself.
@@ -213,6 +217,10 @@ int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_para
 #define BOSSGPU_BUF_MASK       3   /* uint8[...] merged mask, all shards allgather    */
 #define BOSSGPU_BUF_HALO_SEND  4
 #define BOSSGPU_BUF_HALO_RECV  5
+#define BOSSGPU_BUF_COV_TOTAL  7   /* uint64[n_contigs_total] depth total per contig: allreduce sum ONCE after
+                                      bossgpu_set_coverage / bossgpu_synth_coverage on split contigs (ingest keeps it global) */
+#define BOSSGPU_BUF_STRAT      6   /* uint8[strat rows * 2 * n_barcodes]: this shard's Contig.strat rows (gather to the
+                                      process that writes boss.npz) */
 int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_ptr, size_t* bytes);
 
 /* ---------------------------------------------------------------------------------------------
