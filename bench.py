@@ -239,7 +239,8 @@ def run_b200(args, spec):
         run = BossRuns(contigs=dict(zip(names, codes)), ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5,
                        device=local, strict_upstream_asserts=False)
     eng = run.engine
-    eng.synth_coverage(seed=11, mean_depth=spec["depth"], p_ref=0.90, p_del=0.04, frac_dropout=0.02, frac_deep=0.01)
+    synth_kw = dict(seed=11, mean_depth=spec["depth"], p_ref=0.90, p_del=0.04, frac_dropout=0.02, frac_deep=0.01)
+    (run if world > 1 else eng).synth_coverage(**synth_kw)
 
     # read batches: text form for the end-to-end leg, packed + device-resident for the kernel leg
     n_batches = 3
@@ -295,7 +296,10 @@ def run_b200(args, spec):
     for pd, seqs, rb in batches:
         inc = run.cc.convert_records(paf_dict=pd, seqs=seqs)
         packed = run.pack_for_device(inc)
-        dev_batches.append({k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in packed.items()})
+
+        def to_dev(d):
+            return {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+        dev_batches.append([to_dev(d) for d in packed] if isinstance(packed, list) else to_dev(packed))
     fhat_w = run.read_starts.update_f_pointmass()
     upd_kwargs = dict(approx_ccl=run.rl_dist.approx_ccl, time_cost=run.rl_dist.time_cost, bucket_threshold=run.bucket_threshold)
     run.device_update(fhat_windows=fhat_w, **upd_kwargs)        # uploads F-hat once; later calls reuse it

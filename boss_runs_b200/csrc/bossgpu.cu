@@ -407,7 +407,16 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
                                      const int64_t* contig_cov_add) {
     H_CHECK(h);
     if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
-    if (contig_cov_add) TRY(add_contig_totals(h, contig_cov_add));
+    if (contig_cov_add) {
+        if (on_device) {
+            k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
+                h->d_cov_total, (const unsigned long long*)contig_cov_add, h->n_contigs_total);
+            BOSS_KERNEL_CHECK();
+            h->launches++;
+        } else {
+            TRY(add_contig_totals(h, contig_cov_add));
+        }
+    }
     if (n_reads == 0) return 0;
     if (!seg || !tstart || !barcode || !cig_off || !cigar || !base_off || !bases) return fail(BOSSGPU_EINVAL, "null batch array");
     if (on_device) {

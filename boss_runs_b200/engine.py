@@ -143,10 +143,11 @@ class Engine:
         check(self.lib.bossgpu_ingest_packed(self.h, n, ptr(seg), ptr(tstart), ptr(barcode), ptr(cig_off), ptr(cigar),
                                              ptr(base_off), ptr(bases), int(ascii_bases), 0, ptr(add)))
 
-    def ingest_packed_device(self, n, seg, tstart, barcode, cig_off, cigar, base_off, bases, ascii_bases=False) -> None:
+    def ingest_packed_device(self, n, seg, tstart, barcode, cig_off, cigar, base_off, bases, ascii_bases=False,
+                             contig_cov_add=None) -> None:
         """Same with raw device pointers (ints); nothing is copied and the call does not synchronise."""
         check(self.lib.bossgpu_ingest_packed(self.h, int(n), seg, tstart, barcode, cig_off, cigar, base_off, bases,
-                                             int(ascii_bases), 1, None))
+                                             int(ascii_bases), 1, contig_cov_add))
 
     def ingest_records(self, contig, tstart, tend, barcode, rev, cig_off, cigar_text: bytes, seq_off, seq_text: bytes,
                        n_threads: int = 0) -> None:

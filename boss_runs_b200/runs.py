@@ -385,43 +385,53 @@ class BossRuns:
         """Sites held by this process' GPU."""
         return int(sum(s.length for s in self.engine.segments))
 
-    def pack_for_device(self, batch: PackedBatch) -> dict:
+    def pack_for_device(self, batch: PackedBatch, engine: Engine | None = None) -> dict:
         """Tokenise a batch on the host into libbossgpu's packed arrays (what `bossgpu_ingest_packed` takes),
-        e.g. to upload it ahead of time and ingest with `ingest_device`."""
+        e.g. to upload it ahead of time and ingest with `ingest_device`. With an `engine` that holds only part of
+        the genome, the reads overlapping its segments are kept and `cov_add` carries the batch's reference span
+        per contig (every shard needs the contig-wide depth totals)."""
         import ctypes as C
-        lib = self.engine.lib
-        n = len(batch)
-        b_cig_off, cigar_text, b_seq_off, seq_text = batch.texts()
-        cig_off = np.zeros(n + 1, dtype=np.int64)
-        ops = np.empty(len(cigar_text) // 2 + n + 1, dtype=np.uint32)
-        text = np.frombuffer(cigar_text, dtype=np.uint8)
-        seq = np.frombuffer(seq_text, dtype=np.uint8)
-        bases = np.empty(len(seq), dtype=np.uint8)
+        engine = engine or self.engine
+        lib = engine.lib
+        seg_of = {s.contig: (i, s.start, s.start + s.length) for i, s in enumerate(engine.segments)}
+        t0s, t1s = np.minimum(batch.tstart, batch.tend), np.maximum(batch.tstart, batch.tend)
+        cov_add = np.zeros(len(engine.contig_lengths), dtype=np.int64)
+        np.add.at(cov_add, batch.contig, t1s - t0s)
+        keep = [i for i in range(len(batch)) if batch.contig[i] in seg_of
+                and t1s[i] > seg_of[batch.contig[i]][1] and t0s[i] < seg_of[batch.contig[i]][2]]
+        n = len(keep)
+        cigs, seqs = batch.keep[0::2], batch.keep[1::2]
         comp = np.arange(256, dtype=np.uint8)
         for a, b in zip(b"ATGC", b"TACG"):
             comp[a] = b
+        cig_off = np.zeros(n + 1, dtype=np.int64)
+        base_off = np.zeros(n + 1, dtype=np.int64)
+        ops = np.empty(sum(len(cigs[i]) // 2 + 1 for i in keep) + 1, dtype=np.uint32)
+        bases = np.empty(int(sum(batch.seq_to[i] - batch.seq_from[i] for i in keep)) + 1, dtype=np.uint8)
         r, q = C.c_int64(), C.c_int64()
         w = 0
-        for i in range(n):
-            a, b = int(b_cig_off[i]), int(b_cig_off[i + 1])
-            k = lib.bossgpu_tokenize_cigar(text[a:b].tobytes(), b - a, ops[w:].ctypes.data, len(ops) - w, C.byref(r), C.byref(q))
+        for j, i in enumerate(keep):
+            text = cigs[i].encode("ascii", "replace")
+            k = lib.bossgpu_tokenize_cigar(text, len(text), ops[w:].ctypes.data, len(ops) - w, C.byref(r), C.byref(q))
             if k < 0:
                 raise ValueError("CIGAR tokenizer failed")
             w += k
-            cig_off[i + 1] = w
-            sa, sb = int(b_seq_off[i]), int(b_seq_off[i + 1])
-            if q.value != sb - sa or r.value != abs(int(batch.tend[i]) - int(batch.tstart[i])):
+            cig_off[j + 1] = w
+            sl = np.frombuffer(seqs[i][int(batch.seq_from[i]): int(batch.seq_to[i])].encode("ascii", "replace"), dtype=np.uint8)
+            if q.value != len(sl) or r.value != int(t1s[i] - t0s[i]):
                 raise AssertionError(f"read {i}: CIGAR does not span the aligned slice / target interval")
-            bases[sa:sb] = comp[seq[sa:sb][::-1]] if batch.rev[i] else seq[sa:sb]
-        return dict(n=n, seg=batch.contig.astype(np.int32), tstart=np.minimum(batch.tstart, batch.tend).astype(np.int64),
-                    barcode=batch.barcode.astype(np.int32), cig_off=cig_off, cigar=ops[:max(w, 1)].copy(),
-                    base_off=b_seq_off.astype(np.int64), bases=bases if len(bases) else np.zeros(1, np.uint8))
+            base_off[j + 1] = base_off[j] + len(sl)
+            bases[base_off[j]: base_off[j + 1]] = comp[sl[::-1]] if batch.rev[i] else sl
+        return dict(n=n, seg=np.array([seg_of[batch.contig[i]][0] for i in keep], dtype=np.int32),
+                    tstart=t0s[keep].astype(np.int64), barcode=batch.barcode[keep].astype(np.int32), cig_off=cig_off,
+                    cigar=ops[:max(w, 1)].copy(), base_off=base_off, bases=bases, cov_add=cov_add)
 
-    def ingest_device(self, d: dict) -> None:
+    def ingest_device(self, d: dict, engine: Engine | None = None) -> None:
         """`d`: the dict of `pack_for_device` with every array replaced by a CUDA tensor on this device."""
-        self.engine.ingest_packed_device(d["n"], d["seg"].data_ptr(), d["tstart"].data_ptr(), d["barcode"].data_ptr(),
-                                         d["cig_off"].data_ptr(), d["cigar"].data_ptr(), d["base_off"].data_ptr(),
-                                         d["bases"].data_ptr(), ascii_bases=True)
+        (engine or self.engine).ingest_packed_device(
+            d["n"], d["seg"].data_ptr(), d["tstart"].data_ptr(), d["barcode"].data_ptr(), d["cig_off"].data_ptr(),
+            d["cigar"].data_ptr(), d["base_off"].data_ptr(), d["bases"].data_ptr(), ascii_bases=True,
+            contig_cov_add=d["cov_add"].data_ptr())
 
     def device_update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None) -> UpdateOutcome:
         """The strategy update without the device->host copy of the masks."""

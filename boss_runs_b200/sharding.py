@@ -418,8 +418,13 @@ class ShardedRun(BossRuns):
         self.last = self._phases(approx_ccl, time_cost, bucket_threshold, fhat_windows=fhat_windows)
         return self.last
 
-    def ingest_device(self, d: dict) -> None:
-        raise NotImplementedError("sharded runs ingest through the text path (each shard routes the batch itself)")
+    def pack_for_device(self, batch: PackedBatch, engine=None):
+        """One packed dict per local shard (reads routed and clipped like the text path does)."""
+        return [super(ShardedRun, self).pack_for_device(batch, engine=e) for e in self.engines]
+
+    def ingest_device(self, ds, engine=None) -> None:
+        for e, d in zip(self.engines, ds):
+            super().ingest_device(d, engine=e)
 
     def _pull_switches(self) -> None:
         for k, c in enumerate(self.contigs_filt.values()):
