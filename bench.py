@@ -284,7 +284,9 @@ def run_b200(args, spec):
             e2e_parts.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
             # packed CIGAR ops (4 B each, ~1 per 2 text characters) + aligned read bases + per-read scalars
             h2d = int(inc.cigar_len.sum()) // 2 * 4 + int((inc.seq_to - inc.seq_from).sum()) + len(inc) * 40
-            d2h = int(sum(c.strat.size for c in run.contigs_filt.values())) + 128
+            # masks reach the host as the 4 KB chunks that changed (written by the distribution kernel into the
+            # pinned mirror Contig.strat views) + bucket switches + the result record
+            d2h = int(run.last.mirror_bytes) + int(sum(c.bucket_switches.size for c in run.contigs_filt.values())) + 256
     e2e_t = torch.tensor([float(np.mean(e2e_times))], device="cuda")
     if world > 1:
         import torch.distributed as dist
@@ -318,11 +320,13 @@ def run_b200(args, spec):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    mirror_steps = []
     for i in range(args.steps):
-        step(args.warmup + i)
+        out = step(args.warmup + i)
         t = eng.timing()
         score_ms.append(t["score_bin"])
         all_ms.append(t)
+        mirror_steps.append(int(out.mirror_bytes))
     ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -381,6 +385,8 @@ def run_b200(args, spec):
                      if pk.exists() else "fallback 6650 GB/s (of fallback)", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": int(alg_bytes)},
         "kernel_ms": mean_t,
+        "kernel_ms_steps": {k: [round(t[k], 3) for t in all_ms] for k in ("score_bin", "smooth", "hist", "distribute", "scatter", "update")},
+        "mirror_bytes_steps": mirror_steps,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "setup_s": setup_s,

@@ -53,7 +53,7 @@ class UpdateParams(C.Structure):
 class UpdateResult(C.Structure):
     _fields_ = [("switched_on", C.c_int32), ("strat_size", C.c_int32), ("threshold", C.c_double),
                 ("normaliser", C.c_double), ("ubar0", C.c_double), ("fhat_sum", C.c_double),
-                ("n_nonzero", C.c_int64), ("n_dropout", C.c_int64), ("n_accept", C.c_int64 * 2)]
+                ("n_nonzero", C.c_int64), ("n_dropout", C.c_int64), ("n_accept", C.c_int64 * 2), ("mirror_bytes", C.c_int64)]
 
 
 # every symbol include/bossgpu.h declares: name -> (restype, argtypes)
@@ -69,6 +69,10 @@ SYMBOLS = {
     "bossgpu_ingest_records": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
     "bossgpu_ingest_records_ptr": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
     "bossgpu_strat_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "bossgpu_buckets_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "bossgpu_set_strat_mirror": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
+    "bossgpu_host_register": (C.c_int, [_P, C.c_int64]),
+    "bossgpu_host_unregister": (C.c_int, [_P]),
     "bossgpu_get_seg_accept": (C.c_int, [_P, _P, C.c_int64]),
     "bossgpu_read_starts_add": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bossgpu_get_read_starts": (C.c_int, [_P, _P, C.c_int64]),

@@ -215,7 +215,8 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     A(dev_alloc(&h->d_bucket_sw, (size_t)sw * h->nb));
     A(dev_alloc(&h->d_fhat_w, (size_t)h->n_windows_total * 2));
     A(dev_alloc(&h->d_hist, (size_t)3 * HBINS + 4));
-    A(dev_alloc(&h->d_strat, (size_t)srows * 2 * h->nb));
+    A(dev_alloc(&h->d_strat_alloc, (size_t)srows * 2 * h->nb + 32));
+    h->d_strat = h->d_strat_alloc;
     A(dev_alloc(&h->d_seg_accept, (size_t)h->n_seg * 2));
     A(dev_alloc(&h->d_rs_counts, (size_t)h->n_windows_total * 2));
     A(dev_alloc(&h->d_upd, 1));
@@ -225,8 +226,12 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     if (rc != 0) { bossgpu_destroy(h); return rc; }
     BOSS_CUDA(cudaMallocHost((void**)&h->h_upd, sizeof(UpdateDev)));
     BOSS_CUDA(cudaMallocHost((void**)&h->h_ingest_err, sizeof(int32_t)));
-    BOSS_CUDA(cudaMallocHost((void**)&h->h_strat, std::max<size_t>(1, (size_t)srows * 2 * h->nb)));
+    BOSS_CUDA(cudaHostAlloc((void**)&h->h_strat_own, std::max<size_t>(16, (size_t)srows * 2 * h->nb), cudaHostAllocMapped | cudaHostAllocPortable));
+    h->h_strat = h->h_strat_own;
+    BOSS_CUDA(cudaHostGetDevicePointer((void**)&h->h_strat_dev, h->h_strat, 0));
     BOSS_CUDA(cudaMallocHost((void**)&h->h_seg_accept, sizeof(unsigned long long) * 2 * h->n_seg));
+    BOSS_CUDA(cudaMallocHost((void**)&h->h_bucket_sw, std::max<size_t>(1, (size_t)sw * h->nb)));
+    memset(h->h_bucket_sw, 0, (size_t)sw * h->nb);
     memset(h->h_strat, 1, (size_t)srows * 2 * h->nb);          // Contig.strat starts all-accept (reference.py:118)
     memset(h->h_seg_accept, 0, sizeof(unsigned long long) * 2 * h->n_seg);
     for (auto& ev : h->ev) BOSS_CUDA(cudaEventCreate(&ev));
@@ -329,13 +334,15 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
     void* ptrs[] = {h->d_segs, h->d_tile_start, h->d_row_start, h->d_srow_start, h->d_ref, h->d_cov, h->d_rowflag,
                     h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
                     h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
-                    h->d_hist, h->d_strat, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
+                    h->d_hist, h->d_strat_alloc, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
                     h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
-    if (h->h_strat) cudaFreeHost(h->h_strat);
+    if (h->h_strat_own) cudaFreeHost(h->h_strat_own);
+    if (h->reg_base) bossgpu_host_unregister(h->reg_base);
     if (h->h_seg_accept) cudaFreeHost(h->h_seg_accept);
+    if (h->h_bucket_sw) cudaFreeHost(h->h_bucket_sw);
     if (h->stage_h) cudaFreeHost(h->stage_h);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     delete h;
@@ -804,7 +811,7 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
 
 static int phase3_threshold(bossgpu_handle* h, const bossgpu_update_params* p) {
     EV_BEGIN(5);
-    k_threshold<<<1, 32, 0, h->stream>>>(h->d_hist, h->fhat_shift, p->tc, h->d_upd);
+    k_threshold<<<1, THR_THREADS, 0, h->stream>>>(h->d_hist, h->fhat_shift, p->tc, h->d_upd);
     BOSS_KERNEL_CHECK();
     h->launches++;
     EV_END(5);
@@ -817,15 +824,16 @@ static int phase4_distribute(bossgpu_handle* h, const uint8_t* merged_mask) {
     a.segs = h->d_segs; a.srow_start = h->d_srow_start; a.n_seg = h->n_seg; a.nb = h->nb; a.benefit = h->d_benefit;
     a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.merged_mask = merged_mask; a.bucket_sw = h->d_bucket_sw;
     a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards; a.mask_stride = h->mask_stride;
-    a.strat = h->d_strat; a.n_srows = h->n_srows; a.upd = h->d_upd; a.seg_accept = h->d_seg_accept;
+    a.strat = h->d_strat; a.strat_host = h->h_strat_dev; a.shift = h->strat_shift;
+    a.n_srows = h->n_srows; a.upd = h->d_upd; a.seg_accept = h->d_seg_accept;
     BOSS_CUDA(cudaMemsetAsync(h->d_seg_accept, 0, sizeof(unsigned long long) * 2 * h->n_seg, h->stream));
-    int64_t total = h->n_srows * 2 * h->nb;
-    unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-    k_distribute<<<grid, 256, 0, h->stream>>>(a);
+    const int64_t n_vec = ceil_div(h->n_srows * 2 * h->nb + h->strat_shift, DIST_VEC);
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_vec, DIST_THREADS), (int64_t)h->n_sm * 16));
+    if (h->nb == 1) k_distribute<true><<<grid, DIST_THREADS, 0, h->stream>>>(a);
+    else k_distribute<false><<<grid, DIST_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     h->launches++;
-    // refresh the pinned host mirror of every mask (what Contig.strat views) and the per-segment accept counts
-    BOSS_CUDA(cudaMemcpyAsync(h->h_strat, h->d_strat, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    // the kernel has refreshed the host mirror where masks changed; only the per-segment accept counts are copied
     BOSS_CUDA(cudaMemcpyAsync(h->h_seg_accept, h->d_seg_accept, sizeof(unsigned long long) * 2 * h->n_seg, cudaMemcpyDeviceToHost, h->stream));
     EV_END(6);
     return 0;
@@ -833,6 +841,7 @@ static int phase4_distribute(bossgpu_handle* h, const uint8_t* merged_mask) {
 
 static int fetch_result(bossgpu_handle* h, bossgpu_update_result* r) {
     BOSS_CUDA(cudaMemcpyAsync(h->h_upd, h->d_upd, sizeof(UpdateDev), cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaMemcpyAsync(h->h_bucket_sw, h->d_bucket_sw, (size_t)h->n_sw * h->nb, cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     h->last = *h->h_upd;
     for (int i = 0; i < BOSSGPU_N_TIMERS; ++i)
@@ -847,6 +856,7 @@ static int fetch_result(bossgpu_handle* h, bossgpu_update_result* r) {
         r->fhat_sum = h->last.fhat_sum;
         r->n_nonzero = (int64_t)h->last.n_nonzero;
         r->n_dropout = (int64_t)h->last.n_dropout;
+        r->mirror_bytes = (int64_t)h->last.mirror_bytes;
         for (int sg = 0; sg < h->n_seg; ++sg) {
             r->n_accept[0] += (int64_t)h->h_seg_accept[2 * sg];
             r->n_accept[1] += (int64_t)h->h_seg_accept[2 * sg + 1];
@@ -1188,6 +1198,7 @@ extern "C" int bossgpu_set_buckets(bossgpu_handle* h, int32_t seg, const uint8_t
     if (!switches || n != S.n_sw * h->nb) return fail(BOSSGPU_EINVAL, "bucket buffer must hold %lld entries", (long long)(S.n_sw * h->nb));
     BOSS_CUDA(cudaMemcpyAsync(h->d_bucket_sw + (size_t)S.sw_off * h->nb, switches, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(h->h_bucket_sw + (size_t)S.sw_off * h->nb, switches, (size_t)n);
     return 0;
 }
 
@@ -1255,6 +1266,69 @@ extern "C" int bossgpu_strat_host(bossgpu_handle* h, uint8_t** ptr, int64_t* byt
     if (!h || !ptr || !bytes) return fail(BOSSGPU_EINVAL, "null argument");
     *ptr = h->h_strat;
     *bytes = h->n_srows * 2 * h->nb;
+    return 0;
+}
+
+extern "C" int bossgpu_buckets_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes) {
+    if (!h || !ptr || !bytes) return fail(BOSSGPU_EINVAL, "null argument");
+    *ptr = h->h_bucket_sw;
+    *bytes = h->n_sw * h->nb;
+    return 0;
+}
+
+static void page_range(const void* p, size_t bytes, uintptr_t* lo, uintptr_t* hi) {
+    const uintptr_t page = 4096;
+    *lo = (uintptr_t)p & ~(page - 1);
+    *hi = ((uintptr_t)p + std::max<size_t>(bytes, 1) + page - 1) & ~(page - 1);
+}
+
+extern "C" int bossgpu_host_register(void* host_ptr, int64_t bytes) {
+    if (!host_ptr || bytes < 0) return fail(BOSSGPU_EINVAL, "bad host range");
+    uintptr_t lo, hi;
+    page_range(host_ptr, (size_t)bytes, &lo, &hi);       // shared-memory and malloc mappings cover whole pages
+    cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BOSSGPU_ECUDA, "cudaHostRegister(%zu bytes) failed: %s", (size_t)(hi - lo), cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_host_unregister(void* host_ptr) {
+    if (!host_ptr) return 0;
+    uintptr_t lo, hi;
+    page_range(host_ptr, 1, &lo, &hi);
+    cudaError_t e = cudaHostUnregister((void*)lo);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BOSSGPU_ECUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+extern "C" int bossgpu_set_strat_mirror(bossgpu_handle* h, void* host_ptr, int64_t bytes, int registered) {
+    H_CHECK(h);
+    const int64_t total = h->n_srows * 2 * h->nb;
+    if (!host_ptr || bytes != total) return fail(BOSSGPU_EINVAL, "the strategy mirror must hold exactly %lld bytes", (long long)total);
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    if (!registered) {
+        TRY(bossgpu_host_register(host_ptr, bytes));
+        if (h->reg_base) bossgpu_host_unregister(h->reg_base);
+        h->reg_base = host_ptr;
+    }
+    void* dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dev, host_ptr, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BOSSGPU_ECUDA, "cudaHostGetDevicePointer failed: %s (is the range registered?)", cudaGetErrorString(e)); }
+    // move the device copy so that both images are congruent mod 16 (vector stores on both sides)
+    const int shift = (int)((uintptr_t)host_ptr & 15);
+    if (shift != h->strat_shift) {
+        TRY(ensure_scratch(h, (size_t)total));
+        BOSS_CUDA(cudaMemcpy(h->scratch_d, h->d_strat, (size_t)total, cudaMemcpyDeviceToDevice));
+        h->d_strat = h->d_strat_alloc + shift;
+        h->strat_shift = shift;
+        BOSS_CUDA(cudaMemcpy(h->d_strat, h->scratch_d, (size_t)total, cudaMemcpyDeviceToDevice));
+    }
+    h->h_strat = (uint8_t*)host_ptr;
+    h->h_strat_dev = (uint8_t*)dev;
+    // the new mirror starts as an image of the current strategy
+    BOSS_CUDA(cudaMemcpy(h->h_strat, h->d_strat, (size_t)total, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -84,6 +84,7 @@ struct UpdateDev {
     unsigned long long n_dropout;
     unsigned long long n_accept[2];
     unsigned long long fsum_hi, fsum_lo;   // exact limbs of sum(fhat_exp)
+    unsigned long long mirror_bytes;       // bytes the distribution kernel wrote into the host mirror
     int32_t  error;                  // BOSSGPU_E* raised on the device
     int32_t  empty;
 };
@@ -147,10 +148,16 @@ struct bossgpu_handle {
     double2*  d_expected = nullptr;              // debug
     unsigned long long* d_bucket_sum = nullptr;  // [n_sw][nb]
     uint8_t*  d_bucket_sw = nullptr;             // [n_sw][nb]
+    uint8_t*  h_bucket_sw = nullptr;             // pinned image, refreshed at the end of every update
     double*   d_fhat_w = nullptr;                // [n_windows_total][2]
     unsigned long long* d_hist = nullptr;        // [3*HBINS + 4]
-    uint8_t*  d_strat = nullptr;                 // [n_srows][2][nb]
-    uint8_t*  h_strat = nullptr;                 // pinned host mirror of d_strat, refreshed by every update that derives a strategy
+    uint8_t*  d_strat = nullptr;                 // [n_srows][2][nb]; d_strat_alloc + strat_shift
+    uint8_t*  d_strat_alloc = nullptr;
+    int       strat_shift = 0;                   // keeps d_strat congruent to the host mirror mod 16
+    uint8_t*  h_strat = nullptr;                 // host mirror of d_strat (mapped pinned memory), kept current by k_distribute
+    uint8_t*  h_strat_dev = nullptr;             // the same memory as the device sees it
+    uint8_t*  h_strat_own = nullptr;             // the library's own allocation (NULL once an external mirror is set)
+    void*     reg_base = nullptr;                // page-aligned range registered for an external mirror
     unsigned long long* d_seg_accept = nullptr;  // [n_seg][2] accepted entries per segment and strand
     unsigned long long* h_seg_accept = nullptr;  // pinned
     unsigned long long* d_rs_counts = nullptr;   // [n_windows_total][2] read-start counts (readstartdist.py:26)

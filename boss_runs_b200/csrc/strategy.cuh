@@ -203,14 +203,28 @@ k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const i
 }
 
 // ---- exact limb arithmetic ---------------------------------------------------------------------------
-// v >= 0 and v < 2^63: hi = floor(v), lo = floor(frac(v) * 2^32)
+// A value v in [0, 2^63) is split into two signed integers, v ~= hi + lo * 2^-32 (lo carries 32 fractional bits,
+// what lies below is dropped), which are then summed as 64-bit integers: order-free and exact.
+// Below 2^51 the split uses the 2^52-magic-number rounding (a few fp64 adds instead of three 64-bit
+// conversions): hi = rint(v), lo = rint((v - hi) * 2^32), lo in [-2^31, 2^31]. Above, hi = floor(v).
+// Which branch is taken depends on v alone, so an element contributes the same limbs wherever it is summed.
 __device__ __forceinline__ void to_limbs(double v, unsigned long long& hi, unsigned long long& lo) {
-    hi = (unsigned long long)v;
-    lo = (unsigned long long)((v - (double)hi) * 4294967296.0);
+    if (v < 2251799813685248.0) {                                    // 2^51
+        const double M = 6755399441055744.0;                         // 2^52 + 2^51
+        const double t = __dadd_rn(v, M);
+        const long long h = __double_as_longlong(t) - __double_as_longlong(M);
+        const double rem = __dadd_rn(v, -__dadd_rn(t, -M));          // exact: |rem| <= 0.5
+        const double t2 = __dadd_rn(__dmul_rn(rem, 4294967296.0), M);
+        hi = (unsigned long long)h;
+        lo = (unsigned long long)(__double_as_longlong(t2) - __double_as_longlong(M));
+    } else {
+        hi = (unsigned long long)v;
+        lo = (unsigned long long)((v - (double)hi) * 4294967296.0);
+    }
 }
 __host__ __device__ inline double from_limbs(unsigned long long hi, unsigned long long lo, int shift) {
-    // hi + lo*2^-32, scaled back by 2^-shift
-    double v = (double)hi + (double)lo * (1.0 / 4294967296.0);
+    // hi + lo*2^-32 (both signed sums), scaled back by 2^-shift
+    double v = (double)(long long)hi + (double)(long long)lo * (1.0 / 4294967296.0);
     return ldexp(v, -shift);
 }
 
@@ -301,9 +315,38 @@ __device__ __forceinline__ int abs_exponent_of_ratio(double x, double norm, unsi
 constexpr int HIST_THREADS = 256;
 constexpr int HIST_ROWS_PER_THREAD = 32;
 
-// One thread walks rows base+t, base+t+256, ...; consecutive rows of a thread are 25.6 kb apart and mostly
-// fall into the same binary-exponent bin, so the current bin is accumulated in registers and only written
-// to the CTA's shared histogram (integer atomics) when the bin changes.
+// Adds one element per lane (bin e < 0 = nothing) to the CTA's shared histogram. Lanes hold neighbouring rows,
+// whose smoothed benefits mostly share a binary exponent, so the warp first groups its lanes by bin and sums each
+// group with warp reductions; only the group's leader touches shared memory (64-bit shared atomics are CAS
+// loops, and 32 lanes hitting one bin would serialise 32-fold). Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_hist_add(int e, unsigned long long h, unsigned long long l, unsigned* s_cnt,
+                                              unsigned long long* s_hi, unsigned long long* s_lo) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    // h < 2^63 in three 21-bit pieces; l in [-2^31, 2^31] biased to [0, 2^32] in a 16- and a 17-bit piece
+    const unsigned long long lb = l + 0x80000000ull;
+    unsigned remaining = __ballot_sync(FULL, e >= 0);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int le = __shfl_sync(FULL, e, leader);
+        const bool mine = e == le;
+        const unsigned grp = __ballot_sync(FULL, mine);
+        const unsigned c0 = __reduce_add_sync(FULL, mine ? (unsigned)(h & 0x1FFFFFull) : 0u);
+        const unsigned c1 = __reduce_add_sync(FULL, mine ? (unsigned)((h >> 21) & 0x1FFFFFull) : 0u);
+        const unsigned c2 = __reduce_add_sync(FULL, mine ? (unsigned)(h >> 42) : 0u);
+        const unsigned c3 = __reduce_add_sync(FULL, mine ? (unsigned)(lb & 0xFFFFull) : 0u);
+        const unsigned c4 = __reduce_add_sync(FULL, mine ? (unsigned)(lb >> 16) : 0u);
+        if (lane == leader) {
+            const unsigned n = __popc(grp);
+            atomicAdd(&s_cnt[le], n);
+            atomicAdd(&s_hi[le], (unsigned long long)c0 + ((unsigned long long)c1 << 21) + ((unsigned long long)c2 << 42));
+            atomicAdd(&s_lo[le], (unsigned long long)c3 + ((unsigned long long)c4 << 16) - ((unsigned long long)n << 31));
+        }
+        remaining &= ~grp;
+    }
+}
+
+// One thread walks rows base+t, base+t+256, ... (coalesced 16-byte loads); a warp holds 32 neighbouring rows.
 __global__ void __launch_bounds__(HIST_THREADS)
 k_hist(HistArgs a) {
     __shared__ unsigned s_cnt[HBINS];
@@ -324,46 +367,45 @@ k_hist(HistArgs a) {
     const bool ue_ok = ue > -1000 && ue < 1000;
     const double two_ue = ue_ok ? ldexp(1.0, ue) : 0.0;
     const int b = blockIdx.y;
-    const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail
+    const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail (adjust_length pads)
     unsigned long long u_hi = 0, u_lo = 0, nnz = 0;
-    int cur = -1;
-    unsigned c_cnt = 0;
-    unsigned long long c_hi = 0, c_lo = 0;
+    const double2* ben = a.benefit + (size_t)b * a.n_rows;
 
     const int64_t base = (int64_t)blockIdx.x * (HIST_THREADS * HIST_ROWS_PER_THREAD);
-#pragma unroll 1
-    for (int k = 0; k < HIST_ROWS_PER_THREAD; ++k) {
-        const int64_t i = base + (int64_t)k * HIST_THREADS + threadIdx.x;
-        if (i >= a.n_rows) break;
-        const int64_t r = a.R0 + i;
-        const double2 v = a.benefit[(size_t)b * a.n_rows + i];
-        if (v.x == 0.0 && v.y == 0.0) continue;                   // np.nonzero (sequences.py:585)
-#pragma unroll 1
-        for (int rep = 0; rep < 2; ++rep) {
-            int64_t rr = r;
-            if (rep == 0) { if (r >= a.target) continue; }
-            else { if (!(extra > 0 && r >= a.M - extra)) break; rr = r + extra; }
-            const int64_t win = fhat_window_of_row(a.fg, rr);
+    // pass 0: every row below `target`; pass 1 (only when adjust_length pads, core.py:179-181 with reject refs):
+    // the last `extra` merged rows once more, at their appended positions
+    const int n_pass = (extra > 0 && a.R0 + base + HIST_THREADS * HIST_ROWS_PER_THREAD > a.M - extra) ? 2 : 1;
+    for (int pass = 0; pass < n_pass; ++pass) {
+#pragma unroll 2
+        for (int k = 0; k < HIST_ROWS_PER_THREAD; ++k) {
+            const int64_t i0 = base + (int64_t)k * HIST_THREADS;              // block-uniform
+            if (i0 >= a.n_rows) break;
+            const int64_t i = i0 + threadIdx.x;
+            const int64_t r = a.R0 + i;
+            bool live = i < a.n_rows && (pass == 0 ? r < a.target : r >= a.M - extra);
+            double2 v = make_double2(0.0, 0.0);
+            if (live) v = ben[i];
+            live = live && !(v.x == 0.0 && v.y == 0.0);                       // np.nonzero (sequences.py:585)
+            const int64_t win = live ? fhat_window_of_row(a.fg, pass == 0 ? r : r + extra) : 0;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const double x = s == 0 ? v.x : v.y;
-                if (x == 0.0) continue;
-                const double f = a.fw[2 * win + s] * scale;               // np.multiply(fhat_exp, normalizer)
-                const int e = abs_exponent_of_ratio(x, norm, nbits);
-                unsigned long long h, l;
-                to_limbs(f * two_shift, h, l);
-                if (e != cur) {
-                    if (c_cnt) { atomicAdd(&s_cnt[cur], c_cnt); atomicAdd(&s_hi[cur], c_hi); atomicAdd(&s_lo[cur], c_lo); }
-                    cur = e; c_cnt = 0; c_hi = 0; c_lo = 0;
+                const bool on = live && x != 0.0;
+                int e = -1;
+                unsigned long long h = 0, l = 0;
+                if (on) {
+                    const double f = a.fw[2 * win + s] * scale;               // np.multiply(fhat_exp, normalizer)
+                    e = abs_exponent_of_ratio(x, norm, nbits);
+                    to_limbs(f * two_shift, h, l);
+                    const double t = f * x;                                   // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
+                    unsigned long long uh, ul;
+                    to_limbs(ue_ok ? t * two_ue : ldexp(t, ue), uh, ul);
+                    u_hi += uh; u_lo += ul; nnz++;
                 }
-                c_cnt += 1; c_hi += h; c_lo += l;
-                const double t = f * x;                                   // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
-                to_limbs(ue_ok ? t * two_ue : ldexp(t, ue), h, l);
-                u_hi += h; u_lo += l; nnz++;
+                warp_hist_add(e, h, l, s_cnt, s_hi, s_lo);
             }
         }
     }
-    if (c_cnt) { atomicAdd(&s_cnt[cur], c_cnt); atomicAdd(&s_hi[cur], c_hi); atomicAdd(&s_lo[cur], c_lo); }
     for (int o = 16; o > 0; o >>= 1) {
         u_hi += __shfl_down_sync(0xFFFFFFFFu, u_hi, o);
         u_lo += __shfl_down_sync(0xFFFFFFFFu, u_lo, o);
@@ -382,50 +424,86 @@ k_hist(HistArgs a) {
 }
 
 // ---- threshold from the histogram: two cumulative sums and an argmax (sequences.py:607-646) ----------------
-// One thread: at most 1076 occupied bins, and the cumulative sums are sequential by definition.
-__global__ void k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, UpdateDev* upd) {
+// One CTA. The per-bin terms (limb -> double, ldexp, divisions) are formed by all threads; the two cumulative
+// sums stay one thread's sequential loop over the occupied bins (np.cumsum's order, <= 1076 dependent adds);
+// the ratios are again formed by all threads and the first maximum is picked like np.argmax does.
+constexpr int THR_THREADS = 256;
+__global__ void __launch_bounds__(THR_THREADS)
+k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, UpdateDev* upd) {
+    __shared__ double s_u[HBINS], s_t[HBINS];        // per-bin terms, then (compacted) cumulative sums, then s_u = ratio
     __shared__ int s_exp[HBINS];
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ int s_nocc;
     const double norm = __longlong_as_double((long long)upd->norm_bits);
-    upd->normaliser = norm;
-    upd->n_nonzero = hist[3 * HBINS + 2];
-    if (upd->norm_bits == 0ull || hist[3 * HBINS + 2] == 0ull) {       // np.max of an empty array upstream
-        upd->empty = 1;
-        upd->threshold = 0.0;
-        upd->strat_size = 0;
+    const unsigned long long nnz = hist[3 * HBINS + 2];
+    if (upd->norm_bits == 0ull || nnz == 0ull) {                          // np.max of an empty array upstream
+        if (threadIdx.x == 0) {
+            upd->normaliser = norm; upd->n_nonzero = nnz;
+            upd->empty = 1; upd->threshold = 0.0; upd->strat_size = 0;
+        }
         return;
     }
     int norm_e;
     frexp(norm, &norm_e);
     const double ubar0 = from_limbs(hist[3 * HBINS], hist[3 * HBINS + 1], shift - norm_e);
-    upd->ubar0 = ubar0;
     const double tbar0 = 3.0 + 3.0 + 4.0;                               // alpha + rho + mu in bins (sequences.py:578-580,630)
-    double cs_u = 0.0, cs_t = 0.0, best = 0.0;
-    int best_i = -1, n_occ = 0;
-    for (int e = 0; e < HBINS; ++e) {
+    for (int e = threadIdx.x; e < HBINS; e += THR_THREADS) {
         const unsigned long long cnt = hist[e];
-        if (!cnt) continue;                                             // np.nonzero(bincounts) (sequences.py:607)
-        s_exp[n_occ] = e;
-        const double counts = (double)(long long)cnt;
-        const double f_grid = from_limbs(hist[HBINS + e], hist[2 * HBINS + e], shift);
-        const double f_mean = f_grid / counts;
-        const double bin = ldexp(1.0, -e) * norm;                       // np.power(2.0, -e) * normaliser
-        cs_u += (bin * f_mean) * counts;                                // np.cumsum(benefit_bin * f_grid_mean * counts)
-        cs_t += (tc * counts) * f_mean;                                 // np.cumsum(tc * counts * f_grid_mean)
-        const double peak = (cs_u + ubar0) / (cs_t + tbar0);
-        // np.argmax: first maximum, and the first NaN beats everything
-        const bool best_nan = best != best;
-        if (best_i < 0 || (!best_nan && (peak > best || peak != peak))) { best = peak; best_i = n_occ; }
-        ++n_occ;
+        double tu = 0.0, tt = 0.0;
+        if (cnt) {
+            const double counts = (double)(long long)cnt;
+            const double f_grid = from_limbs(hist[HBINS + e], hist[2 * HBINS + e], shift);
+            const double f_mean = f_grid / counts;
+            const double bin = ldexp(1.0, -e) * norm;                   // np.power(2.0, -e) * normaliser
+            tu = (bin * f_mean) * counts;                               // benefit_bin * f_grid_mean * counts
+            tt = (tc * counts) * f_mean;                                // tc * counts * f_grid_mean
+        }
+        s_u[e] = tu; s_t[e] = tt;
     }
-    // threshold = bin[argmax + 1], or the last bin when argmax is the last (sequences.py:643-646)
-    const int k = best_i + 1;
-    const int e_thr = k < n_occ ? s_exp[k] : s_exp[n_occ - 1];
-    upd->strat_size = k;
-    upd->threshold = ldexp(1.0, -e_thr) * norm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cs_u = 0.0, cs_t = 0.0;
+        int n_occ = 0;
+        for (int e = 0; e < HBINS; ++e) {
+            if (!hist[e]) continue;                                     // np.nonzero(bincounts) (sequences.py:607)
+            cs_u += s_u[e];                                             // np.cumsum: sequential, in bin order
+            cs_t += s_t[e];
+            s_u[n_occ] = cs_u; s_t[n_occ] = cs_t; s_exp[n_occ] = e;     // n_occ <= e: never overtakes the reads
+            ++n_occ;
+        }
+        s_nocc = n_occ;
+    }
+    __syncthreads();
+    const int n_occ = s_nocc;
+    for (int i = threadIdx.x; i < n_occ; i += THR_THREADS) s_u[i] = (s_u[i] + ubar0) / (s_t[i] + tbar0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // np.argmax: first maximum, and the first NaN beats everything
+        double best = s_u[0];
+        int best_i = 0;
+        for (int i = 1; i < n_occ && best == best; ++i) {
+            const double p = s_u[i];
+            if (p > best || p != p) { best = p; best_i = i; }
+        }
+        // threshold = bin[argmax + 1], or the last bin when argmax is the last (sequences.py:643-646)
+        const int k = best_i + 1;
+        const int e_thr = k < n_occ ? s_exp[k] : s_exp[n_occ - 1];
+        upd->normaliser = norm;
+        upd->n_nonzero = nnz;
+        upd->ubar0 = ubar0;
+        upd->strat_size = k;
+        upd->threshold = ldexp(1.0, -e_thr) * norm;
+    }
 }
 
 // ---- mask + bucket-gated distribution (sequences.py:648, core.py:125-155) ---------------------------------
+// The strategy lives twice: in HBM (d_strat, the state the next update gates against) and in a host mirror
+// that Contig.strat views (pinned memory of the library, or caller-provided shared memory handed over with
+// bossgpu_set_strat_mirror). The mirror is kept current by the kernel itself: where the new bytes differ from
+// the old ones the warp writes its 512 bytes through the mapped host pointer (posted PCIe writes). A
+// steady-state update moves a few percent of the 62 MB a 3.1 Gb genome holds instead of copying all of it.
+constexpr int DIST_THREADS = 256;
+constexpr int DIST_VEC = 16;          // strategy bytes per thread and step; a warp owns 512 contiguous bytes
+
 struct DistArgs {
     const SegDev* segs;
     const int64_t* srow_start;    // [n_seg+1]
@@ -439,60 +517,130 @@ struct DistArgs {
     int n_shards;
     int64_t mask_stride;
     const uint8_t* bucket_sw;     // [n_sw][nb]
-    uint8_t* strat;               // [n_srows][2][nb]
+    uint8_t* strat;               // [n_srows][2][nb]; (strat - shift) is 16-byte aligned
+    uint8_t* strat_host;          // device-visible alias of the host mirror, congruent to `strat` mod 16
+    int shift;
     int64_t n_srows;
-    const UpdateDev* upd;
+    UpdateDev* upd;
     unsigned long long* seg_accept; // [n_seg][2]
 };
 
-__global__ void __launch_bounds__(256)
+// A thread forms 16 consecutive bytes of the flattened [row][strand][barcode] strategy (8 rows without
+// barcodes: eight 16-byte benefit loads), compares them with the old bytes in one 16-byte load and rewrites
+// HBM where they differ. If any lane of the warp saw a change, the warp's 512 bytes are also written through
+// the mapped host pointer, so the host mirror follows the device state chunk by chunk.
+template <bool NB1>
+__global__ void __launch_bounds__(DIST_THREADS)
 k_distribute(DistArgs a) {
-    const int64_t total = a.n_srows * 2 * a.nb;
+    __shared__ unsigned long long s_acc[2];
+    __shared__ int s_sg;
+    const int nb = NB1 ? 1 : a.nb;
+    const int64_t total = a.n_srows * 2 * nb;
     const double thr = a.upd->threshold;
-    // accepted entries per (segment, strand) for the per-contig log line (core.py:152-154); a thread keeps the
-    // count of its current segment in a register and flushes when the segment changes
+    const int64_t n_vec = (total + a.shift + DIST_VEC - 1) / DIST_VEC;    // virtual byte axis: v = i + shift
+    // every CTA owns one contiguous run of vectors, so a thread stays inside one segment (contig) for long
+    // stretches: segment geometry lives in registers and the per-segment accept counters see few atomics
+    const int64_t per_cta = ((n_vec + gridDim.x - 1) / gridDim.x + DIST_THREADS - 1) / DIST_THREADS * DIST_THREADS;
+    const int64_t v_begin = blockIdx.x * per_cta;
+    const int64_t v_end = v_begin + per_cta;                             // whole warps stay in the loop (votes)
+    // accepted entries per (segment, strand) for the per-contig log line (core.py:152-154)
     int cur_sg = -1;
     unsigned acc0 = 0, acc1 = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i % a.nb);
-        const int s = (int)((i / a.nb) & 1);
-        const int64_t dl = i / (2 * a.nb);                 // local strategy row
-        const int sg = find_segment(a.srow_start, a.n_seg, dl);
-        const SegDev S = a.segs[sg];
-        const int64_t j = dl - S.srow_off;                 // row within the segment
-        uint8_t cur = a.strat[i];
-        if (a.bucket_sw[(size_t)(S.sw_off + j / (BUCKET / BIN)) * a.nb + b]) {
-            const int64_t r = a.D0 + dl;                   // Q2: strategy row d reads merged row d
-            bool m;
-            if (a.merged_mask) {
-                const int sh = find_segment(a.shard_row_start, a.n_shards, r);
-                const int64_t bit = ((r - a.shard_row_start[sh]) * 2 + s) * a.nb + b;
-                m = (a.merged_mask[(size_t)sh * a.mask_stride + (bit >> 3)] >> (bit & 7)) & 1;
-            } else {
-                const double2 v = a.benefit[(size_t)b * a.n_rows + (r - a.R0)];
-                m = (s == 0 ? v.x : v.y) >= thr;
+    unsigned long long moved = 0;
+    int sg = -1;
+    int64_t row_lo = 0, row_hi = -1, sw_off = 0;                         // rows [row_lo, row_hi) belong to segment sg
+    if (threadIdx.x == 0) { s_acc[0] = 0; s_acc[1] = 0; s_sg = -2; }
+    __syncthreads();
+    for (int64_t vi = v_begin + threadIdx.x; vi < v_end; vi += DIST_THREADS) {
+        const int64_t i0 = vi * DIST_VEC - a.shift;
+        const bool whole = i0 >= 0 && i0 + DIST_VEC <= total;
+        const bool part = !whole && i0 + DIST_VEC > 0 && i0 < total;
+        uint32_t w[4] = {0, 0, 0, 0};
+        bool changed = false;
+        if (whole || part) {
+            uint4 ov = make_uint4(0, 0, 0, 0);
+            if (whole) ov = *reinterpret_cast<const uint4*>(a.strat + i0);
+            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+            int64_t row_cached = -1;
+            double2 v = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < DIST_VEC; ++q) {
+                const int64_t i = i0 + q;
+                uint32_t cur = 0;
+                if (whole || (i >= 0 && i < total)) {
+                    int b, s;
+                    int64_t dl;
+                    if (NB1) { b = 0; s = (int)(i & 1); dl = i >> 1; }
+                    else { b = (int)(i % nb); s = (int)((i / nb) & 1); dl = i / (2 * nb); }
+                    if (dl >= row_hi || dl < row_lo) {
+                        sg = find_segment(a.srow_start, a.n_seg, dl);
+                        row_lo = a.srow_start[sg]; row_hi = a.srow_start[sg + 1]; sw_off = a.segs[sg].sw_off;
+                    }
+                    const uint32_t j = (uint32_t)(dl - row_lo);         // row within the segment
+                    cur = whole ? (ow[q >> 2] >> (8 * (q & 3))) & 0xFFu : a.strat[i];
+                    if (a.bucket_sw[(size_t)(sw_off + j / (BUCKET / BIN)) * nb + b]) {
+                        const int64_t r = a.D0 + dl;                   // Q2: strategy row d reads merged row d
+                        bool m;
+                        if (a.merged_mask) {
+                            const int sh = find_segment(a.shard_row_start, a.n_shards, r);
+                            const int64_t bit = ((r - a.shard_row_start[sh]) * 2 + s) * nb + b;
+                            m = (a.merged_mask[(size_t)sh * a.mask_stride + (bit >> 3)] >> (bit & 7)) & 1;
+                        } else {
+                            if (!NB1 || dl != row_cached) { v = a.benefit[(size_t)b * a.n_rows + (r - a.R0)]; row_cached = dl; }
+                            m = (s == 0 ? v.x : v.y) >= thr;
+                        }
+                        cur = m ? 1u : 0u;
+                    }
+                    if (sg != cur_sg) {
+                        if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
+                        if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
+                        cur_sg = sg; acc0 = 0; acc1 = 0;
+                    }
+                    if (s == 0) acc0 += cur; else acc1 += cur;
+                    if (!whole && cur != a.strat[i]) { a.strat[i] = (uint8_t)cur; changed = true; }
+                }
+                w[q >> 2] |= cur << (8 * (q & 3));
             }
-            cur = m ? 1 : 0;
-            a.strat[i] = cur;
+            if (whole) {
+                changed = (w[0] != ow[0]) | (w[1] != ow[1]) | (w[2] != ow[2]) | (w[3] != ow[3]);
+                if (changed) *reinterpret_cast<uint4*>(a.strat + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        if (sg != cur_sg) {
-            if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
-            if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
-            cur_sg = sg; acc0 = 0; acc1 = 0;
+        if (__any_sync(0xFFFFFFFFu, changed)) {
+            // something in this warp's 512 bytes changed: refresh their image in the host mirror
+            if (whole) {
+                *reinterpret_cast<uint4*>(a.strat_host + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+                moved += DIST_VEC;
+            } else if (part) {
+                for (int q = 0; q < DIST_VEC; ++q) {
+                    const int64_t i = i0 + q;
+                    if (i >= 0 && i < total) { a.strat_host[i] = (uint8_t)((w[q >> 2] >> (8 * (q & 3))) & 0xFFu); ++moved; }
+                }
+            }
         }
-        if (s == 0) acc0 += cur; else acc1 += cur;
     }
-    // most warps sit inside one segment: one atomic per warp instead of 32
-    const bool uniform = __all_sync(0xFFFFFFFFu, cur_sg == __shfl_sync(0xFFFFFFFFu, cur_sg, 0));
-    if (uniform) {
-        acc0 = __reduce_add_sync(0xFFFFFFFFu, acc0);
-        acc1 = __reduce_add_sync(0xFFFFFFFFu, acc1);
-        if ((threadIdx.x & 31) != 0) { acc0 = 0; acc1 = 0; }
-    }
-    if (cur_sg >= 0) {
+    // a CTA usually ends inside one segment: its counts go through shared memory and leave as two atomics
+    if (threadIdx.x == 0) s_sg = cur_sg;
+    __syncthreads();
+    const bool with_cta = cur_sg == s_sg && cur_sg >= 0;
+    if (with_cta) {
+        const unsigned m = __match_any_sync(__activemask(), 1);
+        const unsigned t0 = __reduce_add_sync(m, acc0), t1 = __reduce_add_sync(m, acc1);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+            if (t0) atomicAdd(&s_acc[0], (unsigned long long)t0);
+            if (t1) atomicAdd(&s_acc[1], (unsigned long long)t1);
+        }
+    } else if (cur_sg >= 0) {
         if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
         if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sg >= 0) {
+        if (s_acc[0]) atomicAdd(&a.seg_accept[2 * s_sg], s_acc[0]);
+        if (s_acc[1]) atomicAdd(&a.seg_accept[2 * s_sg + 1], s_acc[1]);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xFFFFFFFFu, moved, o);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&a.upd->mirror_bytes, moved);
 }
 
 // F-hat per window from the read-start counts kept on the device (readstartdist.py:96-115):

@@ -33,6 +33,7 @@ class UpdateOutcome:
     n_nonzero: int
     n_dropout: int
     n_accept: tuple[int, int]
+    mirror_bytes: int = 0
 
 
 def staircase_mult() -> np.ndarray:
@@ -207,7 +208,7 @@ class Engine:
     @staticmethod
     def _outcome(r) -> UpdateOutcome:
         return UpdateOutcome(bool(r.switched_on), r.threshold, r.strat_size, r.normaliser, r.ubar0, r.fhat_sum,
-                             r.n_nonzero, r.n_dropout, (r.n_accept[0], r.n_accept[1]))
+                             r.n_nonzero, r.n_dropout, (r.n_accept[0], r.n_accept[1]), r.mirror_bytes)
 
     def update(self, approx_ccl, time_cost, bucket_threshold, fhat_windows=None, debug: bool = False,
                fhat_scalars=None) -> UpdateOutcome:
@@ -283,6 +284,35 @@ class Engine:
         raw = (C.c_uint8 * n.value).from_address(p.value)
         raw._owner = self                      # numpy's base chain -> this ctypes block -> the engine
         return np.frombuffer(raw, dtype=np.bool_).reshape(-1, 2, self.nb)
+
+    def buckets_host(self) -> list[np.ndarray]:
+        """Zero-copy views of the pinned image of every segment's bucket switches: bool [n_sw][nb] per segment."""
+        p, n = C.c_void_p(), C.c_int64()
+        check(self.lib.bossgpu_buckets_host(self.h, C.byref(p), C.byref(n)))
+        raw = (C.c_uint8 * max(n.value, 1)).from_address(p.value)
+        raw._owner = self
+        flat = np.frombuffer(raw, dtype=np.bool_)[: n.value].reshape(-1, self.nb)
+        out, row = [], 0
+        for i in range(len(self.segments)):
+            k = self.seg_switches(i)
+            out.append(flat[row: row + k])
+            row += k
+        return out
+
+    def set_strat_mirror(self, buf: np.ndarray, registered: bool = False) -> None:
+        """Make `buf` (uint8/bool, C-contiguous, exactly this shard's strategy bytes — typically a slice of a
+        shared-memory array) the host mirror the distribution kernel maintains."""
+        assert buf.flags.c_contiguous and buf.dtype.itemsize == 1
+        check(self.lib.bossgpu_set_strat_mirror(self.h, buf.ctypes.data, buf.size, int(registered)))
+        self._mirror = buf
+
+    def host_register(self, buf: np.ndarray) -> None:
+        """Page-lock and map a host array for this process' CUDA context (once per array; slices of it can then
+        be handed to `set_strat_mirror(..., registered=True)` of several engines)."""
+        check(self.lib.bossgpu_host_register(buf.ctypes.data, buf.size * buf.dtype.itemsize))
+
+    def host_unregister(self, buf: np.ndarray) -> None:
+        check(self.lib.bossgpu_host_unregister(buf.ctypes.data))
 
     def seg_accept(self) -> np.ndarray:
         out = np.empty((len(self.segments), 2), dtype=np.int64)

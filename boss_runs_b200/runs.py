@@ -281,6 +281,7 @@ class BossRuns:
         self._create_engine(device=device, stream=stream)
         self.batch = 0
         self._strat_views = None
+        self._switch_views = None
         self.threshold: float | None = None
         self.last: UpdateOutcome | None = None
         if self.out_dir is not None:
@@ -340,10 +341,15 @@ class BossRuns:
                              "pull_switches": (t3 - t2) * 1e3, "pull_strategies": (t4 - t3) * 1e3}
 
     def _pull_switches(self) -> None:
-        for i, c in enumerate(self.contigs_filt.values()):
-            sw, on = self.engine.buckets(i)
-            c.bucket_switches[...] = sw
-            c.switched_on[...] = on
+        """`Contig.bucket_switches` are views of the library's pinned image (refreshed by the update);
+        `switched_on` follows reference.py:203-207: any switch of any barcode flags the whole contig."""
+        if self._switch_views is None:
+            self._switch_views = self.engine.buckets_host()
+            for c, v in zip(self.contigs_filt.values(), self._switch_views):
+                c.bucket_switches = v
+        for c, v in zip(self.contigs_filt.values(), self._switch_views):
+            if not c.switched_on.all() and v.any():
+                c.switched_on[...] = True
 
     def _pull_strategies(self) -> None:
         """`Contig.strat` of every contig is a view into the library's pinned host mirror, which the update has

@@ -163,9 +163,11 @@ class LocalGroup:
             if s + 1 < self.n_shards:
                 recv[s][h:].copy_(send[s + 1][:h])          # right neighbour's first bins
 
-    def gather_strat(self):
-        """[(shard id, bool array [rows][2][nb])] of every shard, on the host."""
-        return [(s, e.strat_host()) for s, e in zip(self.shard_ids, self.engines)]
+    def shared_mirror(self, nbytes: int) -> np.ndarray:
+        """Host array every shard's distribution kernel writes its slice of (here: ordinary process memory,
+        page-locked by each engine)."""
+        self._mirror = np.ones(nbytes, dtype=np.uint8)
+        return self._mirror
 
     def agree(self, ok: bool) -> bool:
         return ok
@@ -214,32 +216,36 @@ class DistGroup:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
-    def gather_strat(self):
-        """Rank 0 (the process that writes boss.npz) receives every shard's strategy rows; the other ranks get
-        their own only."""
-        import torch
-        own = self.engines[0].exchange_tensor(BUF_STRAT)
-        sizes = torch.zeros(self.world, dtype=torch.int64, device=own.device)
-        sizes[self.rank] = own.numel()
-        self.dist.all_reduce(sizes, group=self.group)
-        sizes = [int(x) for x in sizes.tolist()]
-        mx = max(sizes)
-        if self._gather_buf is None or self._gather_buf[0].numel() != mx * self.world:
-            dev = torch.empty(mx * self.world, dtype=torch.uint8, device=own.device)
-            host = torch.empty(mx * self.world, dtype=torch.uint8, pin_memory=own.is_cuda)
-            pad = torch.zeros(mx, dtype=torch.uint8, device=own.device)
-            self._gather_buf = (dev, host, pad)
-        dev, host, pad = self._gather_buf
-        pad[:own.numel()].copy_(own)
-        self.dist.all_gather_into_tensor(dev, pad, group=self.group)
-        nb = self.engines[0].nb
+    def shared_mirror(self, nbytes: int) -> np.ndarray:
+        """ONE POSIX shared-memory array for the whole node: rank 0 creates it, every rank maps it, and each
+        rank's GPU writes its own slice (bossgpu_set_strat_mirror). No gather of masks is ever needed: after
+        the barrier that ends an update every process sees every contig's strategy."""
+        from multiprocessing import resource_tracker, shared_memory
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 1))
+            np.frombuffer(self._shm.buf, dtype=np.uint8)[:nbytes] = 1          # Contig.strat starts all-accept
+            name[0] = self._shm.name
+        self.dist.broadcast_object_list(name, src=0, group=self.group)
         if self.rank != 0:
-            return [(self.rank, self.engines[0].strat_host())]
-        host.copy_(dev, non_blocking=True)
-        if own.is_cuda:
-            torch.cuda.current_stream(own.device).synchronize()
-        arr = host.numpy().view(np.bool_)
-        return [(s, arr[s * mx: s * mx + sizes[s]].reshape(-1, 2, nb)) for s in range(self.world)]
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:                                             # the creator owns the segment's lifetime
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.dist.barrier(group=self.group)
+        return np.frombuffer(self._shm.buf, dtype=np.uint8)[:nbytes]
+
+    def close(self) -> None:
+        shm = getattr(self, "_shm", None)
+        if shm is not None:
+            self._shm = None
+            try:
+                shm.close()
+                if self.rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
 
     def agree(self, ok: bool) -> bool:
         import torch
@@ -327,6 +333,17 @@ class ShardedRun(BossRuns):
             self.engines.append(e)
         self.engine = self.engines[0]
         self.group = LocalGroup(self.engines) if self._n_virtual is not None else DistGroup(self.engines[0], self._dist_group)
+        # one host array holds every contig's strategy; each shard's kernel keeps its slice current
+        srow = np.concatenate(([0], np.cumsum(np.asarray(lens, dtype=np.int64) // BIN)))
+        per_row = 2 * self.nbarcodes
+        self._strat_global = self.group.shared_mirror(int(srow[-1]) * per_row)
+        self.engine.host_register(self._strat_global)          # once per process: the shards' slices share pages
+        for sid, e in zip(mine, self.engines):
+            s0 = self.plan[sid][0]
+            off = (int(srow[s0.contig]) + s0.start // BIN) * per_row
+            e.set_strat_mirror(self._strat_global[off: off + e.seg_strat_rows(-1) * per_row], registered=True)
+        flat = self._strat_global.view(np.bool_).reshape(-1, 2, self.nbarcodes)
+        self._global_views = [flat[int(srow[k]): int(srow[k + 1])] for k in range(len(lens))]
         # contig -> [(engine, local segment index)] in position order, and whether that covers the contig
         self._pieces = {k: [] for k in range(len(lens))}
         for e in self.engines:
@@ -397,6 +414,7 @@ class ShardedRun(BossRuns):
         out = outs[0]
         if len(outs) > 1:
             out.n_accept = (sum(o.n_accept[0] for o in outs), sum(o.n_accept[1] for o in outs))
+            out.mirror_bytes = sum(o.mirror_bytes for o in outs)
         return out
 
     def update_wrapper(self) -> None:
@@ -427,29 +445,32 @@ class ShardedRun(BossRuns):
             super().ingest_device(d, engine=e)
 
     def _pull_switches(self) -> None:
+        if self._switch_views is None:
+            per_engine = {id(e): e.buckets_host() for e in self.engines}
+            self._switch_views = {k: [per_engine[id(e)][i] for e, i in p] for k, p in self._pieces.items()}
         for k, c in enumerate(self.contigs_filt.values()):
-            if self._complete[k]:
-                sw, on = _Pieces(self).buckets(k)
-                c.bucket_switches[...] = sw
-                c.switched_on[...] = on
+            if not self._complete[k]:
+                continue                                 # switches of contigs with segments on other ranks stay there
+            vs = self._switch_views[k]
+            c.bucket_switches = vs[0] if len(vs) == 1 else np.concatenate(vs)
+            if not c.switched_on.all() and c.bucket_switches.any():
+                c.switched_on[...] = True
 
     def _pull_strategies(self) -> None:
-        """Gather every shard's strategy rows (rank 0 in a distributed job) and point `Contig.strat` at them:
-        views for contigs inside one shard, a concatenation for the few that are split."""
-        got = dict(self.group.gather_strat())
-        parts: dict[int, list] = {}
-        for sid, arr in got.items():
-            row = 0
-            for s in self.plan[sid]:
-                L = int(self.engine.contig_lengths[s.contig])
-                tail = s.start + s.length == L
-                n = (L // BIN - s.start // BIN) if tail else s.length // BIN
-                parts.setdefault(s.contig, []).append((s.start, arr[row: row + n]))
-                row += n
-        for k, c in enumerate(self.contigs_filt.values()):
-            ps = sorted(parts.get(k, []), key=lambda x: x[0])
-            if sum(p[1].shape[0] for p in ps) != c.length // BIN:
-                continue                                 # rows on other ranks: this rank is not the writer
-            c.strat = ps[0][1] if len(ps) == 1 else np.concatenate([p[1] for p in ps])
-            rows = max(c.strat.shape[0], 1)
-            logging.info(f"{c.name}: {c.strat[:, 0].sum() / rows}, {c.strat[:, 1].sum() / rows}")
+        """Every shard's kernel has written its changed chunks into the shared host array; once all shards are
+        done (barrier) each contig's strategy — split across shards or not — is a contiguous view of it."""
+        self.group.barrier()
+        for c, v in zip(self.contigs_filt.values(), self._global_views):
+            c.strat = v
+
+    def close(self) -> None:
+        for e in getattr(self, "engines", []):
+            e.close()
+        if getattr(self, "_strat_global", None) is not None:
+            try:
+                self.engine.host_unregister(self._strat_global)
+            except Exception:
+                pass
+            self._strat_global = None
+        if hasattr(self.group, "close"):
+            self.group.close()

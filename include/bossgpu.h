@@ -195,6 +195,7 @@ typedef struct bossgpu_update_result {
     int64_t n_nonzero;        /* benefit entries entering the histogram */
     int64_t n_dropout;        /* site rows zeroed by the dropout rule (reference.py:160) */
     int64_t n_accept[2];      /* accepted bins per strand over all contigs (core.py:152-153 log) */
+    int64_t mirror_bytes;     /* bytes of the host strategy mirror rewritten by this update (only 512-byte pieces that changed move) */
 } bossgpu_update_result;
 
 /* single-shard update: all phases back to back on the handle's stream, one host sync at the end */
@@ -235,10 +236,22 @@ int bossgpu_get_strat_all(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
 int bossgpu_get_strat_packed(bossgpu_handle* h, uint8_t* out, int64_t out_bytes);
 int64_t bossgpu_strat_rows(bossgpu_handle* h, int32_t seg);   /* seg = -1: all segments */
 
-/* Pinned host mirror of every segment's strategy, back to back in the layout of bossgpu_get_strat_all. The
- * library refreshes it at the end of every update that derives a strategy, so callers can wrap it once
- * (zero-copy) instead of copying masks out after each update. Valid until bossgpu_destroy. */
+/* Host mirror of every segment's strategy, back to back in the layout of bossgpu_get_strat_all (what
+ * Contig.strat views, reference.py:118). The distribution kernel keeps it current by itself: it writes the 512-byte
+ * pieces whose bytes changed straight into this (mapped, pinned) memory, so after bossgpu_update returns the
+ * mirror equals the device state and callers wrap it once, zero-copy. Valid until bossgpu_destroy. */
 int bossgpu_strat_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes);
+/* Use caller-provided host memory as that mirror instead (exactly bossgpu_strat_rows(h,-1)*2*n_barcodes bytes).
+ * With one process per GPU every shard is given its slice of ONE shared-memory array, so the process that writes
+ * boss.npz sees all masks without any gather (core.py:59-69). registered == 0: the library page-locks and maps
+ * the pages around the range itself; != 0: the caller has done so for a range containing it (bossgpu_host_register,
+ * once per process — slices of one array share pages). The current strategy is copied into it; the memory must
+ * outlive the handle. */
+int bossgpu_set_strat_mirror(bossgpu_handle* h, void* host_ptr, int64_t bytes, int registered);
+/* cudaHostRegister (mapped, portable) / cudaHostUnregister of the pages around a host range, for callers without
+ * a CUDA binding of their own */
+int bossgpu_host_register(void* host_ptr, int64_t bytes);
+int bossgpu_host_unregister(void* host_ptr);
 /* accepted entries per segment and strand after the last update, int64 [n_segments][2]
  * (numerators of the per-contig log line, core.py:152-154) */
 int bossgpu_get_seg_accept(bossgpu_handle* h, int64_t* out, int64_t n);
@@ -265,6 +278,9 @@ int bossgpu_get_benefit(bossgpu_handle* h, int32_t seg, double* additional, doub
 /* Contig.bucket_switches bool [len//20000+1][n_barcodes] and switched_on bool [n_barcodes] */
 int bossgpu_get_buckets(bossgpu_handle* h, int32_t seg, uint8_t* switches, int64_t n, uint8_t* switched_on);
 int bossgpu_set_buckets(bossgpu_handle* h, int32_t seg, const uint8_t* switches, int64_t n);
+/* pinned host image of every segment's switches back to back ([n_sw][n_barcodes] each), refreshed at the end of
+ * every update: wrap once, zero-copy */
+int bossgpu_buckets_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes);
 /* exponent histogram of the last update: counts int64[HIST_BINS], f_grid float64[HIST_BINS]
  * (sequences.py:593-624, before the empty bins are dropped) */
 int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_grid);

@@ -68,6 +68,7 @@ def main():
         assert n_upd >= 2
         print(f"SHARDED-OK case={a.case} world={dist.get_world_size()} plan={[[(s.contig, s.start, s.length) for s in segs] for segs in run.plan]}")
     dist.barrier()
+    run.close()
     dist.destroy_process_group()
 
 

@@ -34,6 +34,11 @@ def _model(ploidy):
 
 
 def _limbs(v: float) -> tuple[int, int]:
+    """v ~= hi + lo * 2^-32 as the CUDA kernels split it (strategy.cuh:to_limbs): below 2^51 hi = rint(v) and a
+    signed lo = rint((v - hi) * 2^32); above, hi = floor(v) and lo = floor of the scaled remainder."""
+    if v < 2.0 ** 51:
+        hi = int(np.rint(v))
+        return hi, int(np.rint((v - float(hi)) * 4294967296.0))
     hi = int(v)
     return hi, int((v - float(hi)) * 4294967296.0)
 
@@ -97,6 +102,9 @@ class NumpyShardEngine:
         s = self.segments[i]
         L = int(self.contig_lengths[s.contig])
         return (L // BIN - s.start // BIN) if self.seg_is_tail(i) else s.length // BIN
+
+    def seg_strat_rows(self, i):
+        return int(sum(self.n_srows)) if i < 0 else self.n_srows[i]
 
     def seg_switches(self, i):
         s = self.segments[i]
@@ -364,6 +372,8 @@ class NumpyShardEngine:
                         cur = self._strat[dl0: dl0 + n, st, b]
                         cur[gate[:, b]] = m[gate[:, b]].astype(bool)
                 dl0 += n
+        if getattr(self, "_mirror", None) is not None:
+            self._mirror[...] = self._strat
         acc = (int(self._strat[:, 0].sum()), int(self._strat[:, 1].sum()))
         return UpdateOutcome(on, self.threshold if on else 0.0, self.strat_size if on else 0,
                              float(self.buf[BUF_NORM].view(np.float64)[0]), getattr(self, "ubar0", 0.0), getattr(self, "fhat_sum", 0.0),
@@ -372,6 +382,22 @@ class NumpyShardEngine:
     # ---- results --------------------------------------------------------------------------------------
     def strat_host(self):
         return self._strat
+
+    def buckets_host(self):
+        return self.sw
+
+    def host_register(self, buf):
+        pass
+
+    def host_unregister(self, buf):
+        pass
+
+    def set_strat_mirror(self, buf, registered=False):
+        self._mirror = buf.view(np.bool_).reshape(-1, 2, self.nb)
+        self._mirror[...] = self._strat
+
+    def close(self):
+        pass
 
     def coverage(self, i):
         return self.cov[i]

@@ -52,7 +52,7 @@ def test_struct_layouts(tmp_path):
         "bossgpu_update_params": ["w", "mult", "tc", "bucket_threshold", "fhat_windows", "write_debug", "fhat_from_counts",
                                   "rs_alpha", "rs_denom", "rs_zero_value"],
         "bossgpu_update_result": ["switched_on", "strat_size", "threshold", "normaliser", "ubar0", "fhat_sum", "n_nonzero",
-                                  "n_dropout", "n_accept"],
+                                  "n_dropout", "n_accept", "mirror_bytes"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{REPO}/include/bossgpu.h"', "int main(void){"]
     for st, fs in fields.items():
