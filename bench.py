@@ -282,8 +282,8 @@ def run_b200(args, spec):
         if it >= args.warmup:
             e2e_times.append(dt)
             e2e_parts.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
-            # packed CIGAR ops (4 B each, ~1 per 2 text characters) + aligned read bases + per-read scalars
-            h2d = int(inc.cigar_len.sum()) // 2 * 4 + int((inc.seq_to - inc.seq_from).sum()) + len(inc) * 40
+            # what the library staged and copied: per-read scalars + CIGAR op slots (4 B) + read bases packed 2 bits each
+            h2d = sum(e.ingest_bytes() for e in getattr(run, "engines", [eng]))
             # masks reach the host as the 4 KB chunks that changed (written by the distribution kernel into the
             # pinned mirror Contig.strat views) + bucket switches + the result record
             d2h = int(run.last.mirror_bytes) + int(sum(c.bucket_switches.size for c in run.contigs_filt.values())) + 256

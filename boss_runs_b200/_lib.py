@@ -99,6 +99,7 @@ SYMBOLS = {
     "bossgpu_pattern_rank": (C.c_int64, [_P]),
     "bossgpu_timing": (C.c_int, [_P, _P]),
     "bossgpu_launch_count": (C.c_int64, [_P]),
+    "bossgpu_ingest_bytes": (C.c_int64, [_P]),
     "bossgpu_synth_coverage": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
 }
 

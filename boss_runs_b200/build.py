@@ -66,5 +66,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def fastconv_path() -> Path:
+    import sysconfig
+    return PKG / ("_fastconv" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_fastconv(force: bool = False) -> Path:
+    """Compile csrc/fastconv.c (CPython helper walking the batch's Python objects; plain gcc, no CUDA)."""
+    import sysconfig
+    src, out = CSRC / "fastconv.c", fastconv_path()
+    stamp = PKG / ".fastconv.stamp"
+    digest = hashlib.sha256(src.read_bytes()).hexdigest()
+    if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        return out
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for _fastconv")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-Wall", f"-I{sysconfig.get_paths()['include']}", str(src), "-o", str(out)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("building _fastconv failed")
+    stamp.write_text(digest)
+    return out
+
+
 if __name__ == "__main__":
+    build_fastconv(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

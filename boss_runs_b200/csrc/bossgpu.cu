@@ -4,6 +4,7 @@
 #include <cstring>
 #include <algorithm>
 #include <thread>
+#include <atomic>
 #include <chrono>
 
 #include "common.cuh"
@@ -361,8 +362,9 @@ extern "C" int bossgpu_synchronize(bossgpu_handle* h) {
 static int launch_scatter(bossgpu_handle* h, int64_t n_reads, const int32_t* d_seg, const int64_t* d_tstart,
                           const int32_t* d_bc, const int64_t* d_cig_off, const int64_t* d_cig_end, const uint32_t* d_cig,
                           const int64_t* d_base_off, const uint8_t* d_bases, const uint8_t* d_rev, int ascii, bool count_totals,
-                          bool check_spans = true) {
-    BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
+                          bool check_spans = true, PackedBases pk = PackedBases{nullptr, nullptr, nullptr, nullptr, nullptr},
+                          bool record_begin = true) {
+    if (record_begin) BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (check_spans) {
         k_check_spans<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_cig_off, d_cig_end, d_cig, d_base_off,
                                                                               h->d_ingest_err);
@@ -371,7 +373,7 @@ static int launch_scatter(bossgpu_handle* h, int64_t n_reads, const int32_t* d_s
     }
     unsigned grid = (unsigned)std::min<int64_t>(n_reads, 1 << 20);
     k_scatter<<<grid, SC_THREADS, 0, h->stream>>>(n_reads, d_seg, d_tstart, d_bc, d_cig_off, d_cig_end, d_cig, d_base_off, d_bases,
-                                                  d_rev, ascii, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
+                                                  d_rev, ascii, pk, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
                                                   count_totals ? 1 : 0, h->d_ingest_err);
     BOSS_KERNEL_CHECK();
     BOSS_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -509,113 +511,187 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         sel.push_back(i);
     }
     const int64_t n_reads = (int64_t)sel.size();
-    int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(hw > 2 ? hw - 1 : hw, 32u);   // one thread keeps issuing copies
     if (n_reads < 64) T = 1;
     T = (int)std::max<int64_t>(1, std::min<int64_t>(T, n_reads));
-    // ---- staging blob: every read gets its worst-case CIGAR slot (an op needs >= 2 characters), so one
-    //      parallel pass tokenises in place and copies the slices; no counting pass, no compaction ----------
-    std::vector<int64_t> n_ops(n_reads), rspan(n_reads), qspan(n_reads);
-    std::vector<int64_t> cut(T + 1, 0);
-    int64_t total_chars = 0, ops_cap = 0, total_bases = 0;
+    // The batch is cut into G groups of consecutive reads; the worker threads tokenise and pack group after
+    // group while the copy engine already moves the finished groups to the GPU, so the PCIe transfer hides
+    // behind the host work instead of following it.
+    const int G = n_reads >= 512 ? 4 : 1;
+    // ---- staging blob (pinned host image = device image): per-read scalars | CIGAR text | read bases packed 2 bits
+    //      each, every read's run starting on its own byte. The host only copies and packs; the CIGARs are
+    //      tokenised on the GPU (k_tokenize) into op slots that never cross PCIe. ------------------------------
+    int64_t total_chars = 0, ops_cap = 0, total_text = 0, total_packed = 0;
     for (int64_t j = 0; j < n_reads; ++j) {
         const TextRead& R = all_reads[sel[j]];
         total_chars += R.cigar_len + R.seq_len;
         ops_cap += R.cigar_len / 2 + 1;
-        total_bases += R.seq_len;
+        total_text += R.cigar_len;
+        total_packed += (R.seq_len + 3) / 4;
     }
+    // task (g, t) = reads [cut[g*T+t], cut[g*T+t+1]): equal shares of characters
+    std::vector<int64_t> cut((size_t)G * T + 1, n_reads);
     {
-        // split by characters so long reads do not pile up in one thread
-        int64_t per = total_chars / T + 1, acc = 0;
-        int t = 1;
-        for (int64_t j = 0; j < n_reads && t < T; ++j) {
+        const int64_t parts = (int64_t)G * T;
+        const int64_t per = total_chars / parts + 1;
+        int64_t acc = 0;
+        int64_t t = 1;
+        cut[0] = 0;
+        for (int64_t j = 0; j < n_reads && t < parts; ++j) {
             acc += all_reads[sel[j]].cigar_len + all_reads[sel[j]].seq_len;
-            if (acc >= per * t) cut[t++] = j + 1;
+            while (t < parts && acc >= per * t) cut[t++] = j + 1;
         }
-        for (; t <= T; ++t) cut[t] = n_reads;
     }
     const int64_t nr1 = std::max<int64_t>(n_reads, 1);
     size_t o_seg = 0;
     size_t o_bc = o_seg + round_up(sizeof(int32_t) * nr1, 16);
     size_t o_ts = o_bc + round_up(sizeof(int32_t) * nr1, 16);
-    size_t o_co = o_ts + round_up(sizeof(int64_t) * nr1, 16);
-    size_t o_ce = o_co + round_up(sizeof(int64_t) * nr1, 16);
-    size_t o_bo = o_ce + round_up(sizeof(int64_t) * nr1, 16);
-    size_t o_rv = o_bo + round_up(sizeof(int64_t) * (nr1 + 1), 16);
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * nr1, 16);          // first op slot of each read
+    size_t o_to = o_co + round_up(sizeof(int64_t) * nr1, 16);          // CIGAR text offsets [n+1]
+    size_t o_sp = o_to + round_up(sizeof(int64_t) * (nr1 + 1), 16);    // reference span tend - tstart
+    size_t o_bo = o_sp + round_up(sizeof(int64_t) * nr1, 16);          // base offsets [n+1] (slice lengths)
+    size_t o_po = o_bo + round_up(sizeof(int64_t) * (nr1 + 1), 16);    // byte offset of each read's packed bases
+    size_t o_rv = o_po + round_up(sizeof(int64_t) * nr1, 16);
     size_t o_ca = o_rv + round_up((size_t)nr1, 16);
-    size_t o_cg = o_ca + round_up(sizeof(unsigned long long) * h->n_contigs_total, 16);
-    size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
-    size_t total = o_bs + round_up(std::max<int64_t>(total_bases, 1), 16);
+    size_t o_tx = o_ca + round_up(sizeof(unsigned long long) * h->n_contigs_total, 16);
+    const size_t small_bytes = o_tx;
+    size_t o_pk = o_tx + round_up((size_t)std::max<int64_t>(total_text, 1), 16);
+    size_t total = o_pk + round_up(std::max<int64_t>(total_packed, 1), 16);
     TRY(ensure_stage(h, total));
+    // device-only: op slots + where each read's ops end
+    const size_t x_ops = 0, x_end = round_up(sizeof(uint32_t) * std::max<int64_t>(ops_cap, 1), 16);
+    const size_t x_exc = x_end + round_up(sizeof(int64_t) * nr1, 16);
+    TRY(ensure_scratch(h, x_exc));
     char* hs = (char*)h->stage_h;
+    char* ds = (char*)h->stage_d;
     int32_t* s_seg = (int32_t*)(hs + o_seg);
     int32_t* s_bc = (int32_t*)(hs + o_bc);
     int64_t* s_ts = (int64_t*)(hs + o_ts);
     int64_t* s_co = (int64_t*)(hs + o_co);
-    int64_t* s_ce = (int64_t*)(hs + o_ce);
+    int64_t* s_to = (int64_t*)(hs + o_to);
+    int64_t* s_sp = (int64_t*)(hs + o_sp);
     int64_t* s_bo = (int64_t*)(hs + o_bo);
+    int64_t* s_po = (int64_t*)(hs + o_po);
     uint8_t* s_rv = (uint8_t*)(hs + o_rv);
-    uint32_t* s_cg = (uint32_t*)(hs + o_cg);
-    uint8_t* s_bs = (uint8_t*)(hs + o_bs);
+    char* s_tx = hs + o_tx;
+    uint8_t* s_pk = (uint8_t*)(hs + o_pk);
     memcpy(hs + o_ca, cov_add.data(), sizeof(unsigned long long) * h->n_contigs_total);
     {
-        int64_t co = 0, bo = 0;
+        int64_t co = 0, bo = 0, po = 0, to = 0;
         for (int64_t j = 0; j < n_reads; ++j) {
             const int64_t i = sel[j];
             s_seg[j] = seg_of_contig[contig[i]];
             s_bc[j] = barcode[i];
             s_ts[j] = std::min(tstart[i], tend[i]);
+            s_sp[j] = std::max(tstart[i], tend[i]) - s_ts[j];
             s_rv[j] = rev[i] ? 1 : 0;
             s_co[j] = co;
+            s_to[j] = to;
             s_bo[j] = bo;
+            s_po[j] = po;
             co += all_reads[i].cigar_len / 2 + 1;
+            to += all_reads[i].cigar_len;
             bo += all_reads[i].seq_len;
+            po += (all_reads[i].seq_len + 3) / 4;
         }
         s_bo[n_reads] = bo;
+        s_to[n_reads] = to;
     }
+    BOSS_CUDA(cudaMemcpyAsync(ds, hs, small_bytes, cudaMemcpyHostToDevice, h->stream));
     const double ms_layout = ms_since(t_begin);
-    auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t j = lo; j < hi; ++j) {
-            const TextRead& R = all_reads[sel[j]];
-            n_ops[j] = tokenize_cigar(R.cigar, R.cigar_len, s_cg + s_co[j], R.cigar_len / 2 + 1, &rspan[j], &qspan[j]);
-            s_ce[j] = s_co[j] + std::max<int64_t>(n_ops[j], 0);
-            // slices stay in sequencing orientation; the scatter kernel reverse-complements on the fly
-            memcpy(s_bs + s_bo[j], R.seq, (size_t)R.seq_len);
+    struct Exc { int64_t read; int32_t pos; uint8_t ch; };
+    std::vector<std::vector<Exc>> exc((size_t)T);
+    std::vector<std::atomic<int>> done((size_t)G);
+    for (auto& d : done) d.store(0);
+    auto work = [&](int t) {
+        for (int g = 0; g < G; ++g) {
+            for (int64_t j = cut[(size_t)g * T + t]; j < cut[(size_t)g * T + t + 1]; ++j) {
+                const TextRead& R = all_reads[sel[j]];
+                memcpy(s_tx + s_to[j], R.cigar, (size_t)R.cigar_len);
+                // slices stay in sequencing orientation; the scatter kernel reverse-complements on the fly
+                pack_bases((const unsigned char*)R.seq, R.seq_len, s_pk + s_po[j],
+                           [&](int64_t pos, unsigned char ch) { exc[t].push_back(Exc{j, (int32_t)pos, ch}); });
+            }
+            done[g].fetch_add(1, std::memory_order_release);
         }
     };
-    if (T == 1) work(0, n_reads);
-    else {
+    auto ship = [&](int g) -> int {
+        // reads of group g are tasks (g, 0..T-1): one run of CIGAR text and one run of packed bases
+        const int64_t r0 = cut[(size_t)g * T], r1 = cut[(size_t)(g + 1) * T];
+        if (r1 <= r0) return 0;
+        const size_t c0 = (size_t)s_to[r0], c1 = (size_t)s_to[r1];
+        const size_t p0 = (size_t)s_po[r0], p1 = (size_t)(r1 < n_reads ? s_po[r1] : total_packed);
+        if (c1 > c0) BOSS_CUDA(cudaMemcpyAsync(ds + o_tx + c0, hs + o_tx + c0, c1 - c0, cudaMemcpyHostToDevice, h->stream));
+        if (p1 > p0) BOSS_CUDA(cudaMemcpyAsync(ds + o_pk + p0, hs + o_pk + p0, p1 - p0, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    };
+    if (T == 1) {
+        work(0);
+        for (int g = 0; g < G; ++g) TRY(ship(g));
+    } else {
         std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) if (cut[t + 1] > cut[t]) pool.emplace_back(work, cut[t], cut[t + 1]);
+        for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+        int rc_ship = 0;
+        for (int g = 0; g < G; ++g) {
+            while (done[g].load(std::memory_order_acquire) < T) std::this_thread::yield();
+            if (rc_ship == 0) rc_ship = ship(g);
+        }
         for (auto& th : pool) th.join();
-    }
-    // validate like upstream before anything reaches the counters
-    for (int64_t j = 0; j < n_reads; ++j) {
-        const int64_t i = sel[j];
-        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
-        if (n_ops[j] < 0) return fail(BOSSGPU_EINVAL, "read %lld: malformed CIGAR", (long long)i);
-        if (qspan[j] != all_reads[i].seq_len)
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR consumes %lld read bases but the aligned slice has %lld",
-                        (long long)i, (long long)qspan[j], (long long)all_reads[i].seq_len);
-        if (rspan[j] != t1 - t0)
-            return fail(BOSSGPU_ESHAPE, "read %lld: CIGAR spans %lld reference positions but tend-tstart is %lld",
-                        (long long)i, (long long)rspan[j], (long long)(t1 - t0));
+        if (rc_ship != 0) return rc_ship;
     }
     const double ms_pass2 = ms_since(t_begin);
-    BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
-    char* ds = (char*)h->stage_d;
-    k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total, (const unsigned long long*)(ds + o_ca),
-                                                                                 h->n_contigs_total);
+    char* xs = (char*)h->scratch_d;
+    PackedBases pk{(const uint8_t*)(ds + o_pk), (const int64_t*)(ds + o_po), nullptr, nullptr, nullptr};
+    size_t n_exc = 0;
+    for (auto& v : exc) n_exc += v.size();
+    std::vector<char> exc_blob;
+    if (n_exc) {
+        // characters outside ACGT (rare): [exc_off i64[n+1] | pos i32[n_exc] | ch u8[n_exc]]
+        const size_t e_pos = round_up(sizeof(int64_t) * (n_reads + 1), 16), e_ch = e_pos + round_up(sizeof(int32_t) * n_exc, 16);
+        exc_blob.assign(e_ch + round_up(n_exc, 16), 0);
+        int64_t* eo = (int64_t*)exc_blob.data();
+        int32_t* ep = (int32_t*)(exc_blob.data() + e_pos);
+        uint8_t* ec = (uint8_t*)(exc_blob.data() + e_ch);
+        std::vector<Exc> all;
+        all.reserve(n_exc);
+        for (auto& v : exc) all.insert(all.end(), v.begin(), v.end());
+        std::sort(all.begin(), all.end(), [](const Exc& a, const Exc& b) { return a.read != b.read ? a.read < b.read : a.pos < b.pos; });
+        size_t x = 0;
+        for (int64_t j = 0; j <= n_reads; ++j) {
+            while (x < all.size() && all[x].read < j) ++x;
+            eo[j] = (int64_t)x;
+        }
+        for (size_t q = 0; q < all.size(); ++q) { ep[q] = all[q].pos; ec[q] = all[q].ch; }
+        TRY(ensure_scratch(h, x_exc + exc_blob.size()));
+        xs = (char*)h->scratch_d;
+        BOSS_CUDA(cudaMemcpyAsync(xs + x_exc, exc_blob.data(), exc_blob.size(), cudaMemcpyHostToDevice, h->stream));
+        pk.exc_off = (const int64_t*)(xs + x_exc);
+        pk.exc_pos = (const int32_t*)(xs + x_exc + e_pos);
+        pk.exc_char = (const uint8_t*)(xs + x_exc + e_ch);
+    }
+    if (n_reads > 0) {
+        BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        k_tokenize<<<(unsigned)std::min<int64_t>(n_reads, 1 << 20), TK_THREADS, 0, h->stream>>>(
+            n_reads, ds + o_tx, (const int64_t*)(ds + o_to), (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_bo),
+            (const int64_t*)(ds + o_sp), (uint32_t*)(xs + x_ops), (int64_t*)(xs + x_end), h->d_ingest_err);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
+    k_add_u64_if_ok<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
+        h->d_cov_total, (const unsigned long long*)(ds + o_ca), h->n_contigs_total, h->d_ingest_err);
     BOSS_KERNEL_CHECK();
     h->launches++;
     if (n_reads > 0)
         TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
-                           (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_ce), (const uint32_t*)(ds + o_cg),
-                           (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), (const uint8_t*)(ds + o_rv), /*ascii=*/1,
-                           /*count_totals=*/false, /*check_spans=*/false));
-    int rc = check_ingest_error(h);
+                           (const int64_t*)(ds + o_co), (const int64_t*)(xs + x_end), (const uint32_t*)(xs + x_ops),
+                           (const int64_t*)(ds + o_bo), nullptr, (const uint8_t*)(ds + o_rv), /*ascii=*/1,
+                           /*count_totals=*/false, /*check_spans=*/false, pk, /*record_begin=*/false));
+    int rc = check_ingest_error(h);       // synchronises: exc_blob, the staging buffer and the scratch are free again
+    h->last_ingest_h2d = (int64_t)(small_bytes + (size_t)total_text + (size_t)total_packed + exc_blob.size());
     if (trace)
-        fprintf(stderr, "[bossgpu] ingest %lld of %lld reads, %d threads (hw %u): layout %.2f ms, tokenise+copy %.2f, h2d+scatter %.2f; %zu B\n",
-                (long long)n_reads, (long long)n_all, T, std::thread::hardware_concurrency(), ms_layout, ms_pass2 - ms_layout,
+        fprintf(stderr, "[bossgpu] ingest %lld of %lld reads, %d threads x %d groups (hw %u): layout %.2f ms, copy+pack (h2d overlapped) %.2f, tokenise + scatter on the GPU %.2f; %zu B staged\n",
+                (long long)n_reads, (long long)n_all, T, G, std::thread::hardware_concurrency(), ms_layout, ms_pass2 - ms_layout,
                 ms_since(t_begin) - ms_pass2, total);
     return rc;
 }
@@ -1243,6 +1319,7 @@ extern "C" int bossgpu_timing(bossgpu_handle* h, float ms[BOSSGPU_N_TIMERS]) {
 }
 
 extern "C" int64_t bossgpu_launch_count(bossgpu_handle* h) { return h ? h->launches : -1; }
+extern "C" int64_t bossgpu_ingest_bytes(bossgpu_handle* h) { return h ? h->last_ingest_h2d : -1; }
 
 extern "C" int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double mean_depth, double p_ref, double p_del,
                                       double frac_dropout, double frac_deep) {

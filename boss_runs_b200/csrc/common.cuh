@@ -174,6 +174,7 @@ struct bossgpu_handle {
     float ms[BOSSGPU_N_TIMERS] = {0};
     bool  ev_valid[BOSSGPU_N_TIMERS] = {false};
     int64_t launches = 0;
+    int64_t last_ingest_h2d = 0;                // bytes the last text ingest moved to the device
     int phase_done = -1;
     int n_sm = 148;
     bool score_kernel_ldg = false;

@@ -10,6 +10,13 @@ __global__ void k_add_u64(unsigned long long* __restrict__ dst, const unsigned l
     if (i < n) dst[i] += src[i];
 }
 
+// the same, unless an earlier stage of the ingest rejected the batch (nothing may reach the state then)
+__global__ void k_add_u64_if_ok(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, int n,
+                                const int32_t* __restrict__ err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && *err == 0) dst[i] += src[i];
+}
+
 // device planes [b][base][site]  ->  reference layout [site][base][b] (reference.py:77)
 __global__ void k_cov_to_ref_layout(SegDev S, int nb, int64_t P, const uint16_t* __restrict__ cov, uint16_t* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

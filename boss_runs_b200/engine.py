@@ -393,6 +393,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bossgpu_launch_count(self.h))
 
+    def ingest_bytes(self) -> int:
+        """Host->device bytes of the last text ingest."""
+        return int(self.lib.bossgpu_ingest_bytes(self.h))
+
     def synth_coverage(self, seed: int = 11, mean_depth: float = 8.0, p_ref: float = 0.90, p_del: float = 0.04,
                        frac_dropout: float = 0.02, frac_deep: float = 0.01) -> None:
         check(self.lib.bossgpu_synth_coverage(self.h, seed, mean_depth, p_ref, p_del, frac_dropout, frac_deep))

@@ -84,6 +84,23 @@ class CoverageConverter:
 
     def convert_records(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
                         barcodes: dict[str, int] | None = None) -> PackedBatch:
+        """Same walk as upstream's loop (sequences.py:694-738). Runs in the `_fastconv` C helper when it has been
+        built (`__graft_entry__.build()` / `python -m boss_runs_b200.build`), else in `_convert_records_py`; both
+        produce identical batches (tests/test_hostmodel.py)."""
+        fc = _fastconv()
+        if fc is None:
+            return self._convert_records_py(paf_dict, seqs)
+        n = len(paf_dict)
+        contig, bc = np.empty(n, np.int32), np.empty(n, np.int32)
+        tstart, tend, cl, sf, st = (np.empty(n, np.int64) for _ in range(5))
+        rev = np.empty(n, np.uint8)
+        cp, sp = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        keep: list = []
+        used, skipped = fc.convert(paf_dict, seqs, self.contig_index, best_record, (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st), keep)
+        return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
+                           sf[:used], st[:used], keep, skipped)
+
+    def _convert_records_py(self, paf_dict, seqs: dict[str, str]) -> PackedBatch:
         contig, tstart, tend, bc, rev, cp, cl, sp, sf, st, keep = [], [], [], [], [], [], [], [], [], [], []
         skipped = 0
         index = self.contig_index
@@ -121,6 +138,21 @@ class CoverageConverter:
                            np.asarray(rev, dtype=np.uint8), np.asarray(cp, dtype=np.uint64), np.asarray(cl, dtype=np.int64),
                            np.asarray(sp, dtype=np.uint64), np.asarray(sf, dtype=np.int64), np.asarray(st, dtype=np.int64),
                            keep, skipped)
+
+
+_FASTCONV = False
+
+
+def _fastconv():
+    """The compiled helper, or None when it has not been built (host glue only: the CUDA path has no fallback)."""
+    global _FASTCONV
+    if _FASTCONV is False:
+        try:
+            from . import _fastconv as mod
+            _FASTCONV = mod
+        except ImportError:
+            _FASTCONV = None
+    return _FASTCONV
 
 
 class Contig:

@@ -115,8 +115,10 @@ int  bossgpu_synchronize(bossgpu_handle* h);
  *   Positions outside the segment are clipped (a read spanning a shard edge is given to both shards).
  *   All pointers are HOST pointers unless on_device != 0 (then they are device pointers on the
  *   handle's device and no copy is made).
- * ingest_records: text form, tokenised by the library's C++ tokenizer (regex + translate upstream:
- *   sequences.py:672,762-776). seq slices are given in ORIGINAL read orientation together with
+ * ingest_records: text form. Host threads only copy the CIGAR text and pack the read bases 2 bits each into pinned
+ *   staging (copies to the device overlap that work); the CIGARs are tokenised on the GPU (regex + translate
+ *   upstream: sequences.py:672,762-776) and checked against tend-tstart and the slice length before any counter is
+ *   touched (upstream's asserts, sequences.py:732-733,785 -> BOSSGPU_ESHAPE). seq slices are given in ORIGINAL read orientation together with
  *   rev[i]; the library reverse-complements (boss/utils.py:85-95: ATGC<->TACG only). `contig` is the GLOBAL
  *   index in contigs_filt order. Every shard is handed the WHOLE batch: the library keeps the reads that overlap
  *   one of its segments (a shard holds at most one segment per contig; the scatter clips at its edges, so a read
@@ -296,6 +298,8 @@ int64_t bossgpu_pattern_rank(const uint16_t c[5]);
 int bossgpu_timing(bossgpu_handle* h, float ms[BOSSGPU_N_TIMERS]);
 /* algorithmic launches issued so far (kernels of this library only) */
 int64_t bossgpu_launch_count(bossgpu_handle* h);
+/* host->device bytes of the last text ingest (per-read scalars + 4-byte CIGAR ops + read bases packed 2 bits each) */
+int64_t bossgpu_ingest_bytes(bossgpu_handle* h);
 
 /* Bench/test support: fill the coverage of every segment with a synthetic sequencing state on the
  * device (depth ~ Poisson(mean_depth) split over bases with p_ref, uniform errors, p_del; a fraction

@@ -1,0 +1,149 @@
+"""GPU edge cases of the coverage update and the strategy update, each against the oracle or against upstream's
+documented behaviour: empty batches, characters outside ACGT (aligned -> IndexError, inside an insertion -> ignored),
+CIGAR/interval mismatches, untracked contigs, barcode fallback (Q11), uint16 wrap (Q13), staircase windows < 1,
+a missing time_cost (Q14), the packed and the text ingest agreeing, and the mirror following the device state."""
+import io
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import boss_oracle as bo
+from boss_runs_b200 import synth
+from boss_runs_b200.hostmodel import parse_PAF
+
+pytestmark = pytest.mark.gpu
+
+
+def make_run(lengths, seed=5, **kw):
+    from boss_runs_b200.runs import BossRuns
+    contigs = synth.random_contigs(lengths, seed=seed)
+    return contigs, BossRuns(contigs=contigs, write_debug=True, **kw)
+
+
+def paf_line(rid, read, qs, qe, strand, tname, tlen, ts, te, cigar):
+    return "\t".join(map(str, (rid, len(read), qs, qe, strand, tname, tlen, ts, te, te - ts, te - ts, 60, "AS:i:100", "tp:A:P", "s1:i:50",
+                               f"cg:Z:{cigar}"))) + "\n"
+
+
+def test_empty_batch_and_untracked_contigs(lib):
+    contigs, run = make_run({"a": 120_000, "b": 100_000}, bucket_threshold=0)
+    run.rl_dist.update({"x": 5000})
+    run.process_batch_runs({}, {})                                   # nothing mapped: still a full update
+    assert run.last.switched_on and (run.contigs["a"].coverage == 0).all()
+    read = contigs["a"][1000:1300]
+    pd = parse_PAF(io.StringIO(paf_line("r1", read, 0, 300, "+", "elsewhere", 500_000, 1000, 1300, "300M")))
+    run.process_batch_runs(pd, {"r1": read})                         # reads on contigs nobody tracks are dropped (core.py:83-86)
+    assert (run.contigs["a"].coverage == 0).all() and (run.contigs["b"].coverage == 0).all()
+
+
+def test_non_acgt_characters(lib):
+    contigs, run = make_run({"a": 120_000}, bucket_threshold=0)
+    ref = contigs["a"]
+    # an N inside an INSERTION is never looked at upstream (the column is dropped): the counts must match the oracle
+    read = ref[5000:5100] + "NN" + ref[5100:5200]
+    pd = parse_PAF(io.StringIO(paf_line("ins", read, 0, 202, "+", "a", 120_000, 5000, 5200, "100M2I100M")))
+    orc = H.oracle_run(list(contigs.items()), 1, [], None, 0)
+    orc.ingest(pd, {"ins": read})
+    run._effect_increments(run.cc.convert_records(pd, {"ins": read}))
+    assert np.array_equal(run.contigs["a"].coverage, orc.contigs["a"].coverage)
+    # the same on the reverse strand (walked backwards, complemented)
+    rc = read.translate(str.maketrans("ATGC", "TACG"))[::-1]
+    pd = parse_PAF(io.StringIO(paf_line("insr", rc, 0, 202, "-", "a", 120_000, 5000, 5200, "100M2I100M")))
+    orc.ingest(pd, {"insr": rc})
+    run._effect_increments(run.cc.convert_records(pd, {"insr": rc}))
+    assert np.array_equal(run.contigs["a"].coverage, orc.contigs["a"].coverage)
+    # an N in an ALIGNED column indexes outside the five counters upstream: IndexError (reference.py:138-140)
+    bad = ref[7000:7050] + "N" + ref[7051:7100]
+    pd = parse_PAF(io.StringIO(paf_line("bad", bad, 0, 100, "+", "a", 120_000, 7000, 7100, "100M")))
+    with pytest.raises(IndexError):
+        run._effect_increments(run.cc.convert_records(pd, {"bad": bad}))
+    # characters '0'..'4' translate to codes 0..4 upstream (ord - 48): '4' lands in the deletion column
+    odd = ref[9000:9010] + "4" + ref[9011:9020]
+    pd = parse_PAF(io.StringIO(paf_line("odd", odd, 0, 20, "+", "a", 120_000, 9000, 9020, "20M")))
+    before = run.contigs["a"].coverage[9010].copy()
+    run._effect_increments(run.cc.convert_records(pd, {"odd": odd}))
+    after = run.contigs["a"].coverage[9010]
+    assert after[4, 0] == before[4, 0] + 1
+
+
+def test_shape_mismatches_raise_like_upstream(lib):
+    contigs, run = make_run({"a": 120_000}, bucket_threshold=0)
+    read = contigs["a"][100:300]
+    for cigar, qe, te in (("150M", 200, 300),        # CIGAR consumes fewer read bases than the slice holds
+                          ("200M", 200, 290),        # CIGAR spans more reference than tend - tstart
+                          ("100M5D100M", 200, 300)): # deletion makes the reference span too long
+        pd = parse_PAF(io.StringIO(paf_line("r", read, 0, qe, "+", "a", 120_000, 100, te, cigar)))
+        with pytest.raises(AssertionError):
+            run._effect_increments(run.cc.convert_records(pd, {"r": read}))
+    assert (run.contigs["a"].coverage == 0).all(), "a rejected batch must not touch the counters"
+
+
+def test_barcode_fallback_and_u16_wrap(lib):
+    contigs, run = make_run({"a": 100_000}, bucket_threshold=0, barcodes=["barcode01", "barcode02"])
+    read = contigs["a"][2000:2100]
+    pd = parse_PAF(io.StringIO(paf_line("r", read, 0, 100, "+", "a", 100_000, 2000, 2100, "100M")))
+    for rec in pd["r"]:
+        rec.barcode = 99                                             # unclassified: index 0 (Q11)
+    run._effect_increments(run.cc.convert_records(pd, {"r": read}))
+    cov = run.contigs["a"].coverage
+    assert cov[2000:2100, :, 0].sum() == 100 and cov[:, :, 1].sum() == 0
+    # counters are uint16 and wrap (Q13)
+    full = np.zeros((100_000, 5, 2), dtype=np.uint16)
+    full[2000:2100, :, 0] = 65535
+    run.engine.set_coverage(0, full)
+    run._effect_increments(run.cc.convert_records(pd, {"r": read}))
+    cov = run.contigs["a"].coverage
+    codes = np.frombuffer(read.encode(), dtype=np.uint8)
+    lut = np.zeros(256, np.uint8); lut[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+    want = full.copy()
+    want[np.arange(2000, 2100), lut[codes], 0] += np.uint16(1)       # NumPy wraps the same way
+    assert np.array_equal(cov, want)
+
+
+def test_update_argument_errors(lib):
+    contigs, run = make_run({"a": 120_000}, bucket_threshold=0)
+    with pytest.raises(ValueError):                                  # bn.move_sum rejects windows < 1 (reference.py:259-260)
+        run.engine.update(approx_ccl=np.array([50, 200, 300, 400, 500, 600, 700, 800, 900, 1000]), time_cost=5000.0, bucket_threshold=0,
+                          fhat_scalars=(1.0, 100.0, 0.01))
+    # Q14: no read-length update yet -> no time_cost -> AttributeError once a bucket is on
+    with pytest.raises(AttributeError):
+        run.update_wrapper()
+
+
+def test_packed_and_text_ingest_agree(lib):
+    contigs, run_text = make_run({"a": 150_000, "b": 110_000}, bucket_threshold=0)
+    _, run_packed = make_run({"a": 150_000, "b": 110_000}, bucket_threshold=0)
+    rb = synth.read_batch(contigs, n_reads=700, seed=77, mean_len=2500.0, min_len=300, max_len=9000)
+    pd = parse_PAF(io.StringIO(rb.paf_text))
+    inc = run_text.cc.convert_records(pd, rb.seqs)
+    run_text._effect_increments(inc)
+    d = run_packed.pack_for_device(inc)
+    run_packed.engine.ingest_packed(d["seg"], d["tstart"], d["barcode"], d["cig_off"], d["cigar"], d["base_off"], d["bases"],
+                                    ascii_bases=True)
+    orc = H.oracle_run(list(contigs.items()), 1, [], None, 0)
+    orc.ingest(pd, rb.seqs)
+    for name in contigs:
+        assert np.array_equal(run_text.contigs[name].coverage, orc.contigs[name].coverage)
+        assert np.array_equal(run_packed.contigs[name].coverage, orc.contigs[name].coverage)
+    assert 0 < run_text.engine.ingest_bytes() < sum(len(s) for s in rb.seqs.values())    # 2-bit bases + 4-byte ops < the text
+
+
+def test_mirror_follows_device_state(lib):
+    contigs, run = make_run({"a": 180_000, "b": 120_000}, bucket_threshold=0)
+    moved = []
+    for b in range(4):
+        rb = synth.read_batch(contigs, n_reads=400, seed=300 + b, mean_len=2500.0, min_len=300, max_len=9000)
+        pd = parse_PAF(io.StringIO(rb.paf_text))
+        run.rl_dist.update({rid: recs[0].qlen for rid, recs in pd.items()})
+        run.process_batch_runs(pd, rb.seqs)
+        dev = run.engine.strat_all()                                 # explicit device->host copy
+        row = 0
+        for c in run.contigs_filt.values():
+            n = c.length // 100
+            assert np.array_equal(c.strat, dev[row: row + n]), f"batch {b}: mirror of {c.name} is stale"
+            row += n
+        moved.append(run.last.mirror_bytes)
+        packed = np.unpackbits(run.engine.strat_packed(), bitorder="little")[: dev.size].astype(bool)
+        assert np.array_equal(packed, dev.reshape(-1))
+    assert moved[0] > 0 and all(m <= dev.size + 1024 for m in moved)
