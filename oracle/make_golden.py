@@ -148,8 +148,9 @@ def run_reference(spec, names, seqs, kinds, batches, workdir: Path):
             out[p + "updated"] = np.bool_(bool(captured))
             if captured:
                 out[p + "threshold"] = np.float64(captured["threshold"])
-                out[p + "benefit_adj"] = captured["benefit"]
-                out[p + "fhat_adj"] = captured["fhat"]
+                if bi == len(batches) - 1 or spec.get("full_dump", True):
+                    out[p + "benefit_adj"] = captured["benefit"]
+                    out[p + "fhat_adj"] = captured["fhat"]
                 out[p + "merged_strat"] = np.packbits(captured["strat"].ravel())
                 out[p + "merged_strat_shape"] = np.array(captured["strat"].shape)
             last = bi == len(batches) - 1
@@ -166,14 +167,15 @@ def run_reference(spec, names, seqs, kinds, batches, workdir: Path):
                 # a strided sample of the per-site arrays at every batch, the full arrays at the last one
                 out[q + "scores_sample"] = c.scores[::97].copy()
                 out[q + "coverage_sample"] = c.coverage[::97].copy()
-                if last and cname == next(iter(exp.contigs_filt)):
+                if last and cname == next(iter(exp.contigs_filt)) and spec.get("full_dump", True):
                     out[q + "coverage"] = c.coverage.copy()
                     out[q + "scores"] = c.scores.copy()
                 if captured:
                     out[q + "scores_ds"] = c.scores_ds.copy()
-                    out[q + "smu"] = c.smu.copy()
-                    out[q + "expected_benefit"] = c.expected_benefit.copy()
                     out[q + "additional_benefit"] = c.additional_benefit.copy()
+                    if last or spec.get("full_dump", True):
+                        out[q + "smu"] = c.smu.copy()
+                        out[q + "expected_benefit"] = c.expected_benefit.copy()
         out["n_sites"] = np.int64(exp.ref.n_sites)
         out["score0"] = np.float64(exp.scoring.score0[0])
         out["contig_score0"] = np.float64(next(iter(exp.contigs_filt.values())).score0[0])
@@ -289,17 +291,73 @@ def make_kats():
     print("kats.npz", {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(out.items())[:6]})
 
 
+def real_case_inputs(n_batches=3, reads_per_batch=700):
+    """BASELINE config 1 on the reference's own data (data/BOSS_test_data): the two zymo contigs most of the
+    ERR3152366 reads map to (+ one contig under 100 kb that the loader drops), and the real reads with their real
+    minimap2 records (PAF file order, primary and secondary lines alike; some map to contigs outside this reduced
+    reference, as in a real run with `reject`-free references)."""
+    data = REFERENCE / "data" / "BOSS_test_data"
+    want = {"NZ_CP041014.1": "trk", "NZ_VFAG01000001.1": "trk", "NZ_VFAF01000001.1": "short"}
+    seqs, name, buf = {}, None, []
+    for line in open(data / "zymo.fa"):
+        if line.startswith(">"):
+            if name in want:
+                seqs[name] = "".join(buf)
+            name, buf = line[1:].split()[0], []
+        else:
+            buf.append(line.strip())
+    if name in want:
+        seqs[name] = "".join(buf)
+    names = [n for n in want if n in seqs]
+    kinds = {n: want[n] for n in names}
+    order, lines = [], {}
+    with open(data / "ERR3152366_10k.paf") as fh:
+        for line in fh:
+            rid = line.split("\t", 1)[0]
+            if rid not in lines:
+                if len(order) >= n_batches * reads_per_batch:
+                    continue
+                order.append(rid)
+                lines[rid] = []
+            lines[rid].append(line)
+    reads = {}
+    need = set(order)
+    with open(data / "ERR3152366_10k.fq") as fh:
+        while True:
+            head = fh.readline()
+            if not head:
+                break
+            seq = fh.readline().strip()
+            fh.readline(); fh.readline()
+            rid = head[1:].split()[0]
+            if rid in need:
+                reads[rid] = seq
+    batches = []
+    for b in range(n_batches):
+        rids = order[b * reads_per_batch: (b + 1) * reads_per_batch]
+        batches.append(synth.ReadBatch("".join("".join(lines[r]) for r in rids), {r: reads[r] for r in rids}, {}, 0))
+    spec = dict(ploidy=1, nb=0, bucket_threshold=0, tracked=[len(seqs[n]) for n in names if kinds[n] == "trk"], rejected=[],
+                dropped=[len(seqs[n]) for n in names if kinds[n] == "short"], n_batches=n_batches, reads=reads_per_batch, seed=0,
+                full_dump=False)
+    return spec, names, seqs, kinds, batches
+
+
 def main(which=None):
     GOLDEN.mkdir(parents=True, exist_ok=True)
     import logging
     logging.disable(logging.CRITICAL)
     if which is None or "kats" in which:
         make_kats()
-    for name, spec in CASES.items():
+    cases = dict(CASES)
+    cases["real_zymo"] = None
+    for name, spec in cases.items():
         if which is not None and name not in which:
             continue
-        names, seqs, kinds = build_inputs(spec)
-        batches = make_batches(spec, names, seqs, kinds)
+        if name == "real_zymo":
+            spec, names, seqs, kinds, batches = real_case_inputs()
+        else:
+            names, seqs, kinds = build_inputs(spec)
+            batches = make_batches(spec, names, seqs, kinds)
         with tempfile.TemporaryDirectory() as td:
             ref_out = run_reference(spec, names, seqs, kinds, batches, Path(td))
         d = pack_inputs(spec, names, seqs, kinds, batches)

@@ -7,7 +7,7 @@ from pathlib import Path
 import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = ("hap_nb1", "dip_nb1", "hap_nb3", "dip_nb2", "hap_pad")
+CASES = ("hap_nb1", "dip_nb1", "hap_nb3", "dip_nb2", "hap_pad", "real_zymo")
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 

@@ -11,7 +11,7 @@ from test_sharding import _torchrun
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case,n_virtual", [("hap_nb1", 2), ("hap_nb1", 3), ("dip_nb1", 4), ("hap_nb3", 3), ("dip_nb2", 2), ("hap_pad", 2)])
+@pytest.mark.parametrize("case,n_virtual", [("hap_nb1", 2), ("hap_nb1", 3), ("dip_nb1", 4), ("hap_nb3", 3), ("dip_nb2", 2), ("hap_pad", 2), ("real_zymo", 3)])
 def test_virtual_shards_match_oracle(case, n_virtual, lib):
     from boss_runs_b200.sharding import ShardedRun
     g = load_case(case)

@@ -34,8 +34,9 @@ def test_oracle_reproduces_reference(case):
         n_updated += updated
         if updated:
             assert orc.threshold == float(g.ref(p + "threshold"))
-            assert np.array_equal(orc.benefit_adj, g.ref(p + "benefit_adj"))
-            assert np.array_equal(orc.fhat_adj, g.ref(p + "fhat_adj"))
+            if g.has(p + "benefit_adj"):
+                assert np.array_equal(orc.benefit_adj, g.ref(p + "benefit_adj"))
+                assert np.array_equal(orc.fhat_adj, g.ref(p + "fhat_adj"))
             shape = tuple(g.ref(p + "merged_strat_shape"))
             want = np.unpackbits(g.ref(p + "merged_strat"))[: int(np.prod(shape))].reshape(shape).astype(bool)
             assert np.array_equal(orc.merged_strat, want)
@@ -55,7 +56,8 @@ def test_oracle_reproduces_reference(case):
                 assert np.array_equal(c.scores, g.ref(q + "scores"))
             if updated:
                 for name in ("scores_ds", "smu", "expected_benefit", "additional_benefit"):
-                    assert np.array_equal(getattr(c, name), g.ref(q + name)), f"{case} {q}{name}"
+                    if g.has(q + name):
+                        assert np.array_equal(getattr(c, name), g.ref(q + name)), f"{case} {q}{name}"
     assert n_updated >= 2, "a golden case must exercise the strategy branch more than once"
 
 
