@@ -818,16 +818,18 @@ static int phase1_smooth(bossgpu_handle* h, const bossgpu_update_params* p) {
     }
     a.wmax = wmax;
     a.R0 = h->R0; a.target_rows = h->target_rows; a.upd = h->d_upd;
-    // levels: as many power-of-two widths as the largest increment needs and shared memory allows
+    // levels: as many power-of-two widths as the largest increment needs and shared memory allows (at least the
+    // 4-bin level S_mu reads); up to 72 KB keeps three CTAs on an SM
     const size_t span = SM_TILE + 2 * (size_t)(wmax - 1);
-    int levels = 1;
-    while (levels < SM_MAX_LEVELS && (1 << levels) <= dmax && (size_t)(levels + 1) * span * sizeof(double) <= 160 * 1024) ++levels;
-    const bool planned = plan_smoothing(p->w, levels, a);
+    int levels = 3;
+    while (levels < SM_MAX_LEVELS && (1 << levels) <= dmax && (size_t)(levels + 1) * span * sizeof(double) <= 72 * 1024) ++levels;
+    const bool fits = (size_t)levels * span * sizeof(double) <= 200 * 1024 && span * (size_t)levels < (size_t)1 << 30;
+    const bool planned = fits && plan_smoothing(p->w, levels, (int)span, a);
     dim3 grid((unsigned)t, (unsigned)h->nb);
     if (planned) {
         a.n_levels = levels;
         size_t smem = sizeof(double) * span * levels;
-        k_smooth<<<grid, SM_TILE, smem, h->stream>>>(a, h->d_sm_tile_start);
+        k_smooth<<<grid, SM_THREADS, smem, h->stream>>>(a, h->d_sm_tile_start);
     } else {
         // very long staircase: bin-by-bin sums; windows go through scratch (behind the tile table)
         size_t smem = sizeof(double) * span;
@@ -836,7 +838,7 @@ static int phase1_smooth(bossgpu_handle* h, const bossgpu_update_params* p) {
         int32_t* d_w = (int32_t*)h->scratch_d;
         BOSS_CUDA(cudaMemcpyAsync(d_w, p->w, sizeof(int32_t) * NSTEPS, cudaMemcpyHostToDevice, h->stream));
         a.n_levels = 1;
-        k_smooth_direct<<<grid, SM_TILE, smem, h->stream>>>(a, h->d_sm_tile_start, d_w);
+        k_smooth_direct<<<grid, SM_THREADS, smem, h->stream>>>(a, h->d_sm_tile_start, d_w);
     }
     BOSS_KERNEL_CHECK();
     h->launches++;

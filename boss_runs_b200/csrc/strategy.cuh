@@ -19,7 +19,9 @@
 
 namespace boss {
 
-constexpr int SM_TILE = 256;   // output bins per CTA in the smoothing kernel
+constexpr int SM_TILE = 1024;      // output bins per CTA in the smoothing kernels
+constexpr int SM_THREADS = 256;
+constexpr int SM_OUT = SM_TILE / SM_THREADS;   // outputs per thread (t, t+256, ...): piece offsets are fetched once for all of them
 
 constexpr int SM_MAX_PIECES = 192;
 constexpr int SM_MAX_LEVELS = 14;
@@ -36,26 +38,27 @@ struct SmoothArgs {
     double mult[NSTEPS];
     int32_t wmax;                 // max(w[9], 4)
     int32_t n_levels;             // sliding power-of-two sums kept in shared memory: widths 1, 2, ..., 2^(n_levels-1)
-    // the ten nested boxes as a list of power-of-two pieces: piece p adds the 2^lvl[p] bins starting off[p] bins
-    // ahead (forward strand) / ending off[p] bins behind (reverse strand); step i ends before piece step_end[i]
+    // the ten nested boxes as a list of power-of-two pieces: piece p adds the 2^lvl bins starting `off` bins ahead
+    // (forward strand) / ending `off` bins behind (reverse strand); both are stored as element offsets into the
+    // level arrays (lvl * span + off, lvl * span - off - 2^lvl + 1). Step i ends before piece step_end[i].
     int32_t step_end[NSTEPS];
-    int16_t piece_off[SM_MAX_PIECES];
-    int8_t  piece_lvl[SM_MAX_PIECES];
+    int32_t piece_f[SM_MAX_PIECES];
+    int32_t piece_r[SM_MAX_PIECES];
     int64_t R0, target_rows;      // rows >= target are cut by adjust_length (core.py:179-181)
     UpdateDev* upd;
 };
 
 // Host side: split the increments between consecutive staircase windows into power-of-two pieces.
-inline bool plan_smoothing(const int32_t w[NSTEPS], int max_levels, SmoothArgs& a) {
+inline bool plan_smoothing(const int32_t w[NSTEPS], int max_levels, int span, SmoothArgs& a) {
     int n = 0, prev = 0;
     for (int i = 0; i < NSTEPS; ++i) {
         int off = prev, d = w[i] - prev;
         while (d > 0) {
             int k = 0;
             while (k + 1 < max_levels && (2 << k) <= d) ++k;     // largest kept width <= d
-            if (n >= SM_MAX_PIECES || off > 32767) return false;
-            a.piece_off[n] = (int16_t)off;
-            a.piece_lvl[n] = (int8_t)k;
+            if (n >= SM_MAX_PIECES) return false;
+            a.piece_f[n] = k * span + off;
+            a.piece_r[n] = k * span - off - (1 << k) + 1;
             ++n;
             off += 1 << k;
             d -= 1 << k;
@@ -70,7 +73,7 @@ inline bool plan_smoothing(const int32_t w[NSTEPS], int max_levels, SmoothArgs& 
 // Dynamic smem: n_levels * (SM_TILE + 2*(wmax-1)) doubles. Level k holds, for every position, the sum of the
 // 2^k bins starting there (built by doubling), so a box of width w costs popcount-many loads instead of w.
 // Every window is still summed from the bins themselves — no running accumulator, no cancellation.
-__global__ void __launch_bounds__(SM_TILE)
+__global__ void __launch_bounds__(SM_THREADS)
 k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
     extern __shared__ double s_lv[];
     __shared__ unsigned long long s_max;
@@ -84,7 +87,7 @@ k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
     if (threadIdx.x == 0) s_max = 0ull;
     // stage ds[j0-halo, j0+SM_TILE+halo); outside the contig (or the exchanged halo) the box sums see 0,
     // which is what min_count=1 partial windows amount to
-    for (int i = threadIdx.x; i < span; i += SM_TILE) {
+    for (int i = threadIdx.x; i < span; i += SM_THREADS) {
         int64_t j = j0 - halo + i;
         double v = 0.0;
         if (j >= -(int64_t)S.halo_l && j < S.n_bins + S.halo_r) v = src[j];
@@ -95,44 +98,50 @@ k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
         const double* lo = s_lv + (size_t)(k - 1) * span;
         double* hi = s_lv + (size_t)k * span;
         const int half = 1 << (k - 1);
-        for (int i = threadIdx.x; i + 2 * half <= span; i += SM_TILE) hi[i] = lo[i] + lo[i + half];
+        for (int i = threadIdx.x; i + 2 * half <= span; i += SM_THREADS) hi[i] = lo[i] + lo[i + half];
         __syncthreads();
     }
-    const int64_t j = j0 + threadIdx.x;
-    unsigned long long mybits = 0ull;
-    if (j < S.n_bins) {
-        const int c = halo + threadIdx.x;
-        const double* A0 = s_lv + c;
-        // S_mu: 4-bin forward / backward box (reference.py:233-237)
-        const double smu_f = ((A0[0] + A0[1]) + A0[2]) + A0[3];
-        const double smu_r = ((A0[0] + A0[-1]) + A0[-2]) + A0[-3];
-        // staircase: sum_i mult_i * box_{w_i}; the boxes are nested, so one running sum per strand
-        double run_f = 0.0, run_r = 0.0, eb_f = 0.0, eb_r = 0.0;
-        int p = 0;
+    const double* base = s_lv + halo + threadIdx.x;            // this thread's outputs sit at base[256 * m]
+    double run_f[SM_OUT], run_r[SM_OUT], eb_f[SM_OUT], eb_r[SM_OUT];
+#pragma unroll
+    for (int m = 0; m < SM_OUT; ++m) { run_f[m] = 0.0; run_r[m] = 0.0; eb_f[m] = 0.0; eb_r[m] = 0.0; }
+    // staircase: sum_i mult_i * box_{w_i}; the boxes are nested, so one running sum per strand and output
+    int p = 0;
 #pragma unroll 1
-        for (int i = 0; i < NSTEPS; ++i) {
-            const int pe = a.step_end[i];
-            for (; p < pe; ++p) {
-                const int off = a.piece_off[p], k = a.piece_lvl[p];
-                const double* L = s_lv + (size_t)k * span + c;
-                run_f += L[off];
-                run_r += L[-off - (1 << k) + 1];
-            }
-            eb_f += run_f * a.mult[i];
-            eb_r += run_r * a.mult[i];
+    for (int i = 0; i < NSTEPS; ++i) {
+        const int pe = a.step_end[i];
+#pragma unroll 2
+        for (; p < pe; ++p) {
+            const double* Lf = base + a.piece_f[p];
+            const double* Lr = base + a.piece_r[p];
+#pragma unroll
+            for (int m = 0; m < SM_OUT; ++m) { run_f[m] += Lf[SM_THREADS * m]; run_r[m] += Lr[SM_THREADS * m]; }
         }
-        double ad_f = eb_f - smu_f, ad_r = eb_r - smu_r;
+        const double mu = a.mult[i];
+#pragma unroll
+        for (int m = 0; m < SM_OUT; ++m) { eb_f[m] += run_f[m] * mu; eb_r[m] += run_r[m] * mu; }
+    }
+    unsigned long long mybits = 0ull;
+    const double* L2 = base + 2 * span;                        // sums of 4 bins starting at a position (n_levels >= 3)
+#pragma unroll
+    for (int m = 0; m < SM_OUT; ++m) {
+        const int64_t j = j0 + threadIdx.x + SM_THREADS * m;
+        if (j >= S.n_bins) continue;
+        // S_mu: 4-bin forward / backward box (reference.py:233-237)
+        const double smu_f = L2[SM_THREADS * m], smu_r = L2[SM_THREADS * m - 3];
+        double ad_f = eb_f[m] - smu_f, ad_r = eb_r[m] - smu_r;
         if (ad_f < 0.0) ad_f = 0.0;                   // reference.py:267-269
         if (ad_r < 0.0) ad_r = 0.0;
         const size_t o = (size_t)b * a.n_rows + S.row_off + j;
         a.benefit[o] = make_double2(ad_f, ad_r);
         if (a.smu) a.smu[o] = make_double2(smu_f, smu_r);
-        if (a.expected) a.expected[o] = make_double2(eb_f, eb_r);
+        if (a.expected) a.expected[o] = make_double2(eb_f[m], eb_r[m]);
         if (a.R0 + S.row_off + j < a.target_rows) {
             // non-negative doubles order like their bit patterns; NaN would sort above everything
             unsigned long long bf = (unsigned long long)__double_as_longlong(ad_f);
             unsigned long long br = (unsigned long long)__double_as_longlong(ad_r);
-            mybits = bf > br ? bf : br;
+            const unsigned long long mx = bf > br ? bf : br;
+            mybits = mx > mybits ? mx : mybits;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -146,7 +155,7 @@ k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
 
 // Fallback for very long staircases (ultra-long reads) whose piece list or level arrays do not fit:
 // every box is summed bin by bin from one staged copy of the tile.
-__global__ void __launch_bounds__(SM_TILE)
+__global__ void __launch_bounds__(SM_THREADS)
 k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const int32_t* __restrict__ w) {
     extern __shared__ double s_lv[];
     __shared__ unsigned long long s_max;
@@ -158,19 +167,21 @@ k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const i
     const int span = SM_TILE + 2 * halo;
     const double* src = a.ds + (size_t)b * a.ds_len + S.ds_off;
     if (threadIdx.x == 0) s_max = 0ull;
-    for (int i = threadIdx.x; i < span; i += SM_TILE) {
+    for (int i = threadIdx.x; i < span; i += SM_THREADS) {
         int64_t j = j0 - halo + i;
         double v = 0.0;
         if (j >= -(int64_t)S.halo_l && j < S.n_bins + S.halo_r) v = src[j];
         s_lv[i] = v;
     }
     __syncthreads();
-    const int64_t j = j0 + threadIdx.x;
     unsigned long long mybits = 0ull;
-    if (j < S.n_bins) {
-        const double* c = s_lv + halo + threadIdx.x;
-        const double smu_f = ((c[0] + c[1]) + c[2]) + c[3];
-        const double smu_r = ((c[0] + c[-1]) + c[-2]) + c[-3];
+#pragma unroll 1
+    for (int m = 0; m < SM_OUT; ++m) {
+        const int64_t j = j0 + threadIdx.x + SM_THREADS * m;
+        if (j >= S.n_bins) continue;
+        const double* c = s_lv + halo + threadIdx.x + SM_THREADS * m;
+        const double smu_f = (c[0] + c[1]) + (c[2] + c[3]);
+        const double smu_r = (c[-3] + c[-2]) + (c[-1] + c[0]);
         double run_f = 0.0, run_r = 0.0, eb_f = 0.0, eb_r = 0.0;
         int k = 0;
 #pragma unroll 1
@@ -190,7 +201,8 @@ k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const i
         if (a.R0 + S.row_off + j < a.target_rows) {
             unsigned long long bf = (unsigned long long)__double_as_longlong(ad_f);
             unsigned long long br = (unsigned long long)__double_as_longlong(ad_r);
-            mybits = bf > br ? bf : br;
+            const unsigned long long mx = bf > br ? bf : br;
+            mybits = mx > mybits ? mx : mybits;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
