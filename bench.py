@@ -234,7 +234,7 @@ def run_b200(args, spec):
     t_setup = time.time()
     if world > 1:
         run = ShardedRun(contigs=dict(zip(names, codes)), ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5,
-                         device=local, strict_upstream_asserts=False)
+                         device=local, strict_upstream_asserts=False, exchange=args.exchange, fabric_timeout_s=30.0)
     else:
         run = BossRuns(contigs=dict(zip(names, codes)), ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5,
                        device=local, strict_upstream_asserts=False)
@@ -373,7 +373,8 @@ def run_b200(args, spec):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["name"], "sites": int(sum(lengths)), "barcodes": spec["nb"], "ploidy": spec["ploidy"],
                    "reads_per_batch": spec["reads"], "l2": "inputs (counters >= 46 MB ... 31 GB) exceed L2; 3 batches cycled",
-                   "sharding": f"genome axis split over {world} GPU(s)"},
+                   "sharding": f"genome axis split over {world} GPU(s)",
+                   "exchange": getattr(run, "exchange_mode", "none")},
         "e2e": {"value": total_sites / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
                 "host_ms": dict(zip(("convert_records", "ingest", "update_wrapper"),
@@ -403,6 +404,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fabric", "phases"],
+                    help="N>1: peer-memory fabric inside the update's kernels, or NCCL collectives between phases")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     spec = workload_spec(args.workload, args.scale)

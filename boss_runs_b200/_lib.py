@@ -17,12 +17,16 @@ ABI_VERSION = 1
 BIN, BUCKET, RSD_WINDOW, FREEZE = 100, 20_000, 2000, 30
 N_PATTERNS, N_STEPS, HIST_BINS, N_TIMERS = 278_256, 10, 1088, 8
 
-OK, EINVAL, ECUDA, ENOMEM, EBASE, ESHAPE, ESTATE, EEMPTY = 0, -1, -2, -3, -4, -5, -6, -7
+OK, EINVAL, ECUDA, ENOMEM, EBASE, ESHAPE, ESTATE, EEMPTY, EPEER = 0, -1, -2, -3, -4, -5, -6, -7, -8
 BUF_SWITCH, BUF_NORM, BUF_HIST, BUF_MASK, BUF_HALO_SEND, BUF_HALO_RECV, BUF_STRAT, BUF_COV_TOTAL = range(8)
 
 
 class BossGpuError(RuntimeError):
     """CUDA / resource failure inside libbossgpu."""
+
+
+class PeerTimeout(BossGpuError):
+    """A peer shard did not reach an exchange step of the sharded update (BOSSGPU_EPEER)."""
 
 
 class Segment(C.Structure):
@@ -83,6 +87,12 @@ SYMBOLS = {
     "bossgpu_halo_pack": (C.c_int, [_P]),
     "bossgpu_halo_unpack": (C.c_int, [_P]),
     "bossgpu_exchange_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "bossgpu_fabric_info": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t), _P]),
+    "bossgpu_ipc_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "bossgpu_ipc_close": (C.c_int, [C.c_int, _P]),
+    "bossgpu_fabric_attach": (C.c_int, [_P, C.c_int32, _P, C.c_double]),
+    "bossgpu_update_fused_begin": (C.c_int, [_P, C.POINTER(UpdateParams)]),
+    "bossgpu_update_fused_end": (C.c_int, [_P, C.POINTER(UpdateResult)]),
     "bossgpu_get_strat": (C.c_int, [_P, C.c_int32, _P, C.c_int64]),
     "bossgpu_get_strat_all": (C.c_int, [_P, _P, C.c_int64]),
     "bossgpu_get_strat_packed": (C.c_int, [_P, _P, C.c_int64]),
@@ -145,6 +155,8 @@ def check(rc: int) -> None:
         raise ValueError(msg)
     if rc == ENOMEM:
         raise MemoryError(msg)
+    if rc == EPEER:
+        raise PeerTimeout(msg)
     raise BossGpuError(f"libbossgpu error {rc}: {msg}")
 
 

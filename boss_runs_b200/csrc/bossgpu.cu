@@ -12,6 +12,7 @@
 #include "scatter.cuh"
 #include "score_pass.cuh"
 #include "strategy.cuh"
+#include "fabric.cuh"
 #include "synth.cuh"
 #include "tokenizer.h"
 
@@ -336,7 +337,8 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
                     h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
                     h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
                     h->d_hist, h->d_strat_alloc, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
-                    h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts};
+                    h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts,
+                    h->d_mask_ptrs, h->d_fabric, h->d_peer_ptrs, h->d_fab_mask_ptrs};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
@@ -896,12 +898,12 @@ static int phase3_threshold(bossgpu_handle* h, const bossgpu_update_params* p) {
     return 0;
 }
 
-static int phase4_distribute(bossgpu_handle* h, const uint8_t* merged_mask) {
+static int phase4_distribute(bossgpu_handle* h, const uint8_t* const* mask_ptrs) {
     EV_BEGIN(6);
     DistArgs a;
     a.segs = h->d_segs; a.srow_start = h->d_srow_start; a.n_seg = h->n_seg; a.nb = h->nb; a.benefit = h->d_benefit;
-    a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.merged_mask = merged_mask; a.bucket_sw = h->d_bucket_sw;
-    a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards; a.mask_stride = h->mask_stride;
+    a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.mask_ptrs = mask_ptrs; a.bucket_sw = h->d_bucket_sw;
+    a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards;
     a.strat = h->d_strat; a.strat_host = h->h_strat_dev; a.shift = h->strat_shift;
     a.n_srows = h->n_srows; a.upd = h->d_upd; a.seg_accept = h->d_seg_accept;
     BOSS_CUDA(cudaMemsetAsync(h->d_seg_accept, 0, sizeof(unsigned long long) * 2 * h->n_seg, h->stream));
@@ -974,7 +976,8 @@ extern "C" int bossgpu_update(bossgpu_handle* h, const bossgpu_update_params* p,
     return fetch_result(h, r);
 }
 
-static int pack_own_mask(bossgpu_handle* h);
+static int pack_own_mask(bossgpu_handle* h, uint8_t* dst);
+static int point_masks_at_own_copy(bossgpu_handle* h);
 
 extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_params* p, bossgpu_update_result* r) {
     H_CHECK(h);
@@ -986,7 +989,7 @@ extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_
         case 0: EV_BEGIN(7); TRY(phase0_scores(h, p)); break;
         case 1: TRY(upload_fhat(h, p)); TRY(phase1_smooth(h, p)); break;
         case 2: TRY(phase2_hist(h, p)); break;
-        case 3: TRY(phase3_threshold(h, p)); TRY(pack_own_mask(h)); break;
+        case 3: TRY(phase3_threshold(h, p)); TRY(pack_own_mask(h, h->d_mask_all + (size_t)h->shard_index * h->mask_stride)); break;
         case 4:
             // upstream raises on an all-zero benefit before touching any strategy (sequences.py:588); the flag is
             // the same on every shard because the histogram it derives from has been allreduced
@@ -1004,7 +1007,7 @@ extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_
                 fetch_result(h, r);
                 return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
             }
-            TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_all : nullptr));
+            TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_ptrs : nullptr));
             EV_END(7);
             TRY(fetch_result(h, r));
             break;
@@ -1032,6 +1035,21 @@ extern "C" int bossgpu_set_shards(bossgpu_handle* h, int32_t n_shards, int32_t s
     if (h->d_shard_row_start) cudaFree(h->d_shard_row_start);
     TRY(dev_alloc(&h->d_mask_all, (size_t)h->mask_stride * n_shards));
     TRY(dev_alloc(&h->d_shard_row_start, (size_t)n_shards + 1));
+    if (h->d_mask_ptrs) cudaFree(h->d_mask_ptrs);
+    TRY(dev_alloc(&h->d_mask_ptrs, (size_t)n_shards));
+    TRY(point_masks_at_own_copy(h));
+    // exchange block of the peer-memory fabric (fabric.cuh); mapped by the peers after bossgpu_fabric_attach
+    if (h->d_fabric) cudaFree(h->d_fabric);
+    if (h->d_peer_ptrs) cudaFree(h->d_peer_ptrs);
+    if (h->d_fab_mask_ptrs) cudaFree(h->d_fab_mask_ptrs);
+    h->d_fabric = nullptr; h->d_peer_ptrs = nullptr; h->d_fab_mask_ptrs = nullptr; h->fabric_attached = false; h->fabric_epoch = 0;
+    if (n_shards <= FAB_MAX_SHARDS) {
+        const FabricLayout FL = fabric_layout(n_shards, h->nb, h->halo_bins, h->mask_stride);
+        TRY(dev_alloc(&h->d_fabric, FL.bytes));
+        h->fabric_bytes = FL.bytes;
+        TRY(dev_alloc(&h->d_peer_ptrs, (size_t)n_shards));
+        TRY(dev_alloc(&h->d_fab_mask_ptrs, (size_t)n_shards));
+    }
     BOSS_CUDA(cudaMemcpy(h->d_shard_row_start, row_start, sizeof(int64_t) * (n_shards + 1), cudaMemcpyHostToDevice));
     // halo staging: [left send | right send | left recv | right recv], each halo_bins * nb doubles
     if (h->d_halo) cudaFree(h->d_halo);
@@ -1039,11 +1057,19 @@ extern "C" int bossgpu_set_shards(bossgpu_handle* h, int32_t n_shards, int32_t s
     return 0;
 }
 
-static int pack_own_mask(bossgpu_handle* h) {
+// phase API: every shard's mask is gathered (by the caller's collective) into this handle's d_mask_all
+static int point_masks_at_own_copy(bossgpu_handle* h) {
+    std::vector<const uint8_t*> ptrs((size_t)h->n_shards);
+    for (int s = 0; s < h->n_shards; ++s) ptrs[s] = h->d_mask_all + (size_t)s * h->mask_stride;
+    BOSS_CUDA(cudaMemcpy(h->d_mask_ptrs, ptrs.data(), sizeof(uint8_t*) * h->n_shards, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int pack_own_mask(bossgpu_handle* h, uint8_t* dst) {
     if (h->n_shards <= 1) return 0;
     int64_t n_bits = h->n_rows * 2 * h->nb;
     k_pack_mask<<<(unsigned)ceil_div(ceil_div(n_bits, 8), 256), 256, 0, h->stream>>>(
-        h->d_benefit, h->n_rows, h->nb, h->R0, h->target_rows, h->d_upd, h->d_mask_all + (size_t)h->shard_index * h->mask_stride, n_bits);
+        h->d_benefit, h->n_rows, h->nb, h->R0, h->target_rows, h->d_upd, dst, n_bits);
     BOSS_KERNEL_CHECK();
     h->launches++;
     return 0;
@@ -1113,6 +1139,126 @@ extern "C" int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_
         case BOSSGPU_BUF_STRAT: *dev_ptr = h->d_strat; *bytes = (size_t)h->n_srows * 2 * h->nb; break;
         default: return fail(BOSSGPU_EINVAL, "unknown exchange buffer %d", which);
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory fabric: the exchanges of the sharded update done by the GPUs (fabric.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int bossgpu_fabric_info(bossgpu_handle* h, void** dev_ptr, size_t* bytes, unsigned char ipc_handle[64]) {
+    H_CHECK(h);
+    if (!h->d_fabric) return fail(BOSSGPU_ESTATE, "no exchange block: call bossgpu_set_shards first (at most %d shards)", FAB_MAX_SHARDS);
+    if (dev_ptr) *dev_ptr = h->d_fabric;
+    if (bytes) *bytes = h->fabric_bytes;
+    if (ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t mh;
+        BOSS_CUDA(cudaIpcGetMemHandle(&mh, h->d_fabric));
+        memcpy(ipc_handle, &mh, 64);
+    }
+    return 0;
+}
+
+extern "C" int bossgpu_ipc_open(int device, const unsigned char ipc_handle[64], void** dev_ptr) {
+    if (!ipc_handle || !dev_ptr) return fail(BOSSGPU_EINVAL, "null argument");
+    BOSS_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, ipc_handle, 64);
+    *dev_ptr = nullptr;
+    BOSS_CUDA(cudaIpcOpenMemHandle(dev_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int bossgpu_ipc_close(int device, void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    BOSS_CUDA(cudaSetDevice(device));
+    BOSS_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+extern "C" int bossgpu_fabric_attach(bossgpu_handle* h, int32_t n_shards, const uint64_t* peer_ptrs, double timeout_s) {
+    H_CHECK(h);
+    if (!h->d_fabric) return fail(BOSSGPU_ESTATE, "no exchange block: call bossgpu_set_shards first");
+    if (n_shards != h->n_shards || !peer_ptrs) return fail(BOSSGPU_EINVAL, "peer table must hold %d pointers", h->n_shards);
+    if (peer_ptrs[h->shard_index] != (uint64_t)(uintptr_t)h->d_fabric)
+        return fail(BOSSGPU_EINVAL, "peer table entry %d must be this handle's own exchange block", h->shard_index);
+    const FabricLayout FL = fabric_layout(h->n_shards, h->nb, h->halo_bins, h->mask_stride);
+    std::vector<char*> pp((size_t)n_shards);
+    std::vector<const uint8_t*> mp((size_t)n_shards);
+    for (int s = 0; s < n_shards; ++s) {
+        if (!peer_ptrs[s]) return fail(BOSSGPU_EINVAL, "null peer pointer for shard %d", s);
+        pp[s] = (char*)(uintptr_t)peer_ptrs[s];
+        mp[s] = (const uint8_t*)(pp[s] + FL.o_mask);
+    }
+    BOSS_CUDA(cudaMemcpy(h->d_peer_ptrs, pp.data(), sizeof(char*) * n_shards, cudaMemcpyHostToDevice));
+    BOSS_CUDA(cudaMemcpy(h->d_fab_mask_ptrs, mp.data(), sizeof(uint8_t*) * n_shards, cudaMemcpyHostToDevice));
+    BOSS_CUDA(cudaMemset(h->d_fabric, 0, FL.o_sw));           // flags: no epoch seen yet
+    if (timeout_s > 0) h->fabric_timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    h->fabric_epoch = 0;
+    h->fabric_attached = true;
+    return 0;
+}
+
+static FabricArgs fabric_args(bossgpu_handle* h) {
+    FabricArgs a;
+    a.peer = h->d_peer_ptrs;
+    a.L = fabric_layout(h->n_shards, h->nb, h->halo_bins, h->mask_stride);
+    a.n = h->n_shards; a.me = h->shard_index;
+    a.epoch = h->fabric_epoch;
+    a.timeout_ns = h->fabric_timeout_ns;
+    a.upd = h->d_upd;
+    a.ds = h->d_ds; a.ds_len = h->ds_len; a.nb = h->nb; a.halo_bins = h->halo_bins;
+    const SegDev& F = h->segs.front();
+    const SegDev& L = h->segs.back();
+    a.first_ds_off = F.ds_off; a.first_n_bins = F.n_bins;
+    a.last_ds_off = L.ds_off; a.last_n_bins = L.n_bins;
+    a.send_left = F.start > 0; a.send_right = !L.is_tail;
+    a.hist = h->d_hist;
+    return a;
+}
+
+// All kernels of one sharded update, exchanges included, enqueued without a host round trip. Kernels of the
+// strategy half return at once while every bucket of every shard is still off (core.py:172).
+extern "C" int bossgpu_update_fused_begin(bossgpu_handle* h, const bossgpu_update_params* p) {
+    H_CHECK(h);
+    TRY(validate_params(p));
+    if (!h->fabric_attached) return fail(BOSSGPU_ESTATE, "bossgpu_fabric_attach has not been called");
+    if (h->fused_open) return fail(BOSSGPU_ESTATE, "previous bossgpu_update_fused_begin has no matching _end");
+    if (!p->fhat_from_counts && !p->fhat_windows && !h->have_fhat) return fail(BOSSGPU_ESTATE, "no F-hat uploaded yet");
+    h->fabric_epoch++;
+    const FabricArgs fa = fabric_args(h);
+    EV_BEGIN(7);
+    TRY(phase0_scores(h, p));
+    k_fabric_switch_halo<<<1, FAB_THREADS, 0, h->stream>>>(fa);
+    BOSS_KERNEL_CHECK();
+    TRY(upload_fhat(h, p));
+    TRY(phase1_smooth(h, p));
+    k_fabric_norm<<<1, FAB_THREADS, 0, h->stream>>>(fa);
+    BOSS_KERNEL_CHECK();
+    TRY(phase2_hist(h, p));
+    k_fabric_hist<<<1, FAB_THREADS, 0, h->stream>>>(fa);
+    BOSS_KERNEL_CHECK();
+    TRY(phase3_threshold(h, p));
+    TRY(pack_own_mask(h, (uint8_t*)(h->d_fabric + fa.L.o_mask)));
+    k_fabric_mask_ready<<<1, FAB_THREADS, 0, h->stream>>>(fa);
+    BOSS_KERNEL_CHECK();
+    h->launches += 4;
+    TRY(phase4_distribute(h, h->d_fab_mask_ptrs));
+    EV_END(7);
+    h->fused_open = true;
+    h->phase_done = -1;
+    return 0;
+}
+
+extern "C" int bossgpu_update_fused_end(bossgpu_handle* h, bossgpu_update_result* r) {
+    H_CHECK(h);
+    if (!h->fused_open) return fail(BOSSGPU_ESTATE, "bossgpu_update_fused_end without _begin");
+    h->fused_open = false;
+    TRY(fetch_result(h, r));
+    if (h->last.fabric_err) return fail(BOSSGPU_EPEER, "shard %d of %d: a peer did not reach an exchange step of update %u within %.1f s",
+                                        h->shard_index, h->n_shards, h->fabric_epoch, h->fabric_timeout_ns * 1e-9);
+    if (h->last.switched_on && h->last.empty)
+        return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
     return 0;
 }
 

@@ -85,8 +85,10 @@ struct UpdateDev {
     unsigned long long n_accept[2];
     unsigned long long fsum_hi, fsum_lo;   // exact limbs of sum(fhat_exp)
     unsigned long long mirror_bytes;       // bytes the distribution kernel wrote into the host mirror
-    int32_t  error;                  // BOSSGPU_E* raised on the device
-    int32_t  empty;
+    int32_t  empty;                  // every benefit is zero (upstream: np.max of an empty array raises)
+    int32_t  fabric_err;             // BOSSGPU_EPEER: a peer shard did not show up at an exchange step (fabric.cuh)
+    int32_t  error;                  // BOSSGPU_E* raised on the device; survives the per-update reset
+    int32_t  pad_;
 };
 
 struct Timers {
@@ -184,6 +186,17 @@ struct bossgpu_handle {
     std::vector<int64_t> shard_row_start;
     int64_t mask_stride = 0;
     uint8_t* d_mask_all = nullptr;           // [n_shards][mask_stride] packed masks of every shard's merged rows
+    const uint8_t** d_mask_ptrs = nullptr;   // [n_shards] where each shard's packed mask is read from (phase API: slices
+                                             // of d_mask_all; fabric: the mask inside each peer's exchange block)
+    // peer-memory fabric (fabric.cuh): this shard's exchange block and the peers' blocks as this device sees them
+    char*    d_fabric = nullptr;
+    size_t   fabric_bytes = 0;
+    char**   d_peer_ptrs = nullptr;          // [n_shards]
+    const uint8_t** d_fab_mask_ptrs = nullptr; // [n_shards] each peer block's packed mask
+    bool     fabric_attached = false;
+    unsigned fabric_epoch = 0;
+    unsigned long long fabric_timeout_ns = 2000000000ull;
+    bool     fused_open = false;             // bossgpu_update_fused_begin without its _end
     int64_t* d_shard_row_start = nullptr;    // [n_shards+1]
     double*  d_halo = nullptr;               // [send L | send R | recv L | recv R] x halo_bins x nb
     bool have_fhat = false;

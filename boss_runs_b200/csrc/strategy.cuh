@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(SM_THREADS)
 k_smooth(SmoothArgs a, const int64_t* __restrict__ sm_tile_start) {
     extern __shared__ double s_lv[];
     __shared__ unsigned long long s_max;
+    if (!a.upd->switched_on) return;           // every bucket still off: the strategy half is skipped (core.py:172)
     const int b = blockIdx.y;
     const int sg = find_segment(sm_tile_start, a.n_seg, blockIdx.x);
     const SegDev S = a.segs[sg];
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(SM_THREADS)
 k_smooth_direct(SmoothArgs a, const int64_t* __restrict__ sm_tile_start, const int32_t* __restrict__ w) {
     extern __shared__ double s_lv[];
     __shared__ unsigned long long s_max;
+    if (!a.upd->switched_on) return;
     const int b = blockIdx.y;
     const int sg = find_segment(sm_tile_start, a.n_seg, blockIdx.x);
     const SegDev S = a.segs[sg];
@@ -365,6 +367,7 @@ k_hist(HistArgs a) {
     __shared__ unsigned long long s_hi[HBINS];
     __shared__ unsigned long long s_lo[HBINS];
     __shared__ unsigned long long s_u[3];
+    if (!a.upd->switched_on) return;
     for (int i = threadIdx.x; i < HBINS; i += blockDim.x) { s_cnt[i] = 0; s_hi[i] = 0; s_lo[i] = 0; }
     if (threadIdx.x < 3) s_u[threadIdx.x] = 0;
     __syncthreads();
@@ -445,6 +448,7 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, U
     __shared__ double s_u[HBINS], s_t[HBINS];        // per-bin terms, then (compacted) cumulative sums, then s_u = ratio
     __shared__ int s_exp[HBINS];
     __shared__ int s_nocc;
+    if (!upd->switched_on) return;
     const double norm = __longlong_as_double((long long)upd->norm_bits);
     const unsigned long long nnz = hist[3 * HBINS + 2];
     if (upd->norm_bits == 0ull || nnz == 0ull) {                          // np.max of an empty array upstream
@@ -523,11 +527,11 @@ struct DistArgs {
     const double2* benefit;       // [nb][n_rows], local merged rows
     int64_t n_rows;
     int64_t R0, D0;
-    const uint8_t* merged_mask;   // multi-shard: [n_shards][mask_stride] packed masks, bit (i*2+s)*nb+b for the
-                                  // shard-local merged row i; NULL: single shard, benefit is compared directly
+    const uint8_t* const* mask_ptrs; // multi-shard: [n_shards] packed mask of every shard, bit (i*2+s)*nb+b for the
+                                  // shard-local merged row i (own HBM or a peer's exchange block);
+                                  // NULL: single shard, benefit is compared directly
     const int64_t* shard_row_start;
     int n_shards;
-    int64_t mask_stride;
     const uint8_t* bucket_sw;     // [n_sw][nb]
     uint8_t* strat;               // [n_srows][2][nb]; (strat - shift) is 16-byte aligned
     uint8_t* strat_host;          // device-visible alias of the host mirror, congruent to `strat` mod 16
@@ -548,6 +552,7 @@ k_distribute(DistArgs a) {
     __shared__ int s_sg;
     const int nb = NB1 ? 1 : a.nb;
     const int64_t total = a.n_srows * 2 * nb;
+    if (!a.upd->switched_on || a.upd->empty) return;      // strategy left as it is (core.py:172; sequences.py:588 raises)
     const double thr = a.upd->threshold;
     const int64_t n_vec = (total + a.shift + DIST_VEC - 1) / DIST_VEC;    // virtual byte axis: v = i + shift
     // every CTA owns one contiguous run of vectors, so a thread stays inside one segment (contig) for long
@@ -593,10 +598,10 @@ k_distribute(DistArgs a) {
                     if (a.bucket_sw[(size_t)(sw_off + j / (BUCKET / BIN)) * nb + b]) {
                         const int64_t r = a.D0 + dl;                   // Q2: strategy row d reads merged row d
                         bool m;
-                        if (a.merged_mask) {
+                        if (a.mask_ptrs) {
                             const int sh = find_segment(a.shard_row_start, a.n_shards, r);
                             const int64_t bit = ((r - a.shard_row_start[sh]) * 2 + s) * nb + b;
-                            m = (a.merged_mask[(size_t)sh * a.mask_stride + (bit >> 3)] >> (bit & 7)) & 1;
+                            m = (__ldcg(a.mask_ptrs[sh] + (bit >> 3)) >> (bit & 7)) & 1;
                         } else {
                             if (!NB1 || dl != row_cached) { v = a.benefit[(size_t)b * a.n_rows + (r - a.R0)]; row_cached = dl; }
                             m = (s == 0 ? v.x : v.y) >= thr;
@@ -677,7 +682,7 @@ __global__ void k_count_read_starts(int64_t n, const int64_t* __restrict__ win, 
 __global__ void k_pack_mask(const double2* __restrict__ benefit, int64_t n_rows, int nb, int64_t R0, int64_t target,
                             const UpdateDev* upd, uint8_t* __restrict__ out_bits, int64_t n_bits) {
     int64_t byte = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (byte * 8 >= n_bits) return;
+    if (byte * 8 >= n_bits || !upd->switched_on) return;
     const double thr = upd->threshold;
     unsigned v = 0;
     for (int k = 0; k < 8; ++k) {

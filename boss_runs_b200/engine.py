@@ -242,6 +242,38 @@ class Engine:
         d._owner = self
         return torch.as_tensor(d, device=torch.device("cuda", self.device))
 
+    # -- peer-memory fabric (csrc/fabric.cuh) ------------------------------------------------------
+    def fabric_info(self) -> tuple[int, int, bytes]:
+        """(device pointer, bytes, 64-byte CUDA IPC handle) of this shard's exchange block."""
+        p, n = C.c_void_p(), C.c_size_t()
+        hbuf = (C.c_ubyte * 64)()
+        check(self.lib.bossgpu_fabric_info(self.h, C.byref(p), C.byref(n), C.cast(hbuf, C.c_void_p)))
+        return int(p.value), int(n.value), bytes(hbuf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        """Map a peer process' exchange block on this engine's device; returns the device pointer."""
+        assert len(handle) == 64
+        hbuf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        check(self.lib.bossgpu_ipc_open(self.device, C.cast(hbuf, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, dev_ptr: int) -> None:
+        check(self.lib.bossgpu_ipc_close(self.device, C.c_void_p(dev_ptr)))
+
+    def fabric_attach(self, peer_ptrs, timeout_s: float = 0.0) -> None:
+        pp = as_c(peer_ptrs, np.uint64)
+        check(self.lib.bossgpu_fabric_attach(self.h, len(pp), ptr(pp), float(timeout_s)))
+
+    def update_fused_begin(self, params) -> None:
+        """Enqueue every kernel of one sharded update, exchanges included (no host synchronisation)."""
+        check(self.lib.bossgpu_update_fused_begin(self.h, C.byref(params)))
+
+    def update_fused_end(self) -> UpdateOutcome:
+        r = _lib.UpdateResult()
+        check(self.lib.bossgpu_update_fused_end(self.h, C.byref(r)))
+        return self._outcome(r)
+
     def set_shards(self, n_shards: int, shard_index: int, row_start) -> None:
         row_start = as_c(row_start, np.int64)
         assert row_start.shape == (n_shards + 1,)

@@ -136,13 +136,21 @@ class LocalGroup:
         self.shard_ids = list(range(self.n_shards))
         self.rank, self.world = 0, 1
 
+    def _sync(self) -> None:
+        """The copies below run on torch's current stream; virtual shards may each run on their own."""
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def allreduce(self, which: int, op: str, kind: str):
+        self._sync()
         ts = [_view(e.exchange_tensor(which), kind) for e in self.engines]
         acc = ts[0].clone()
         for t in ts[1:]:
             acc = (acc.maximum(t) if op == "max" else acc + t)
         for t in ts:
             t.copy_(acc)
+        self._sync()
         return acc
 
     def allgather_mask(self) -> None:
@@ -168,6 +176,17 @@ class LocalGroup:
         page-locked by each engine)."""
         self._mirror = np.ones(nbytes, dtype=np.uint8)
         return self._mirror
+
+    def setup_fabric(self, timeout_s: float = 0.0) -> bool:
+        """Virtual shards share one address space: every engine is handed the others' exchange blocks by
+        address. Each engine must run on its OWN stream (a shard spins on the device until its peers' kernels
+        have run; on one stream they would queue behind the spin)."""
+        if not all(hasattr(e, "fabric_info") for e in self.engines):
+            return False
+        ptrs = [e.fabric_info()[0] for e in self.engines]
+        for e in self.engines:
+            e.fabric_attach(ptrs, timeout_s)
+        return True
 
     def agree(self, ok: bool) -> bool:
         return ok
@@ -216,14 +235,56 @@ class DistGroup:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def setup_fabric(self, timeout_s: float = 0.0) -> bool:
+        """One process per GPU: every rank exports its exchange block as a CUDA IPC handle, maps the others'
+        (peer access over NVLink) and attaches. Returns False — on EVERY rank — if any rank could not (no
+        peer access, not NCCL, ...); the caller then keeps the collective-based phase protocol."""
+        e = self.engines[0]
+        ok, mine = True, None
+        try:
+            if self.dist.get_backend(self.group) != "nccl" or not hasattr(e, "fabric_info"):
+                raise RuntimeError("peer-memory fabric needs CUDA shards")
+            mine = e.fabric_info()
+        except Exception as ex:                    # noqa: BLE001 - any failure means "use the phase protocol"
+            logging.info("fabric unavailable on rank %d: %s", self.rank, ex)
+            ok = False
+        infos = [None] * self.world
+        self.dist.all_gather_object(infos, (ok, mine[2] if mine else None), group=self.group)
+        ok = all(i[0] for i in infos)
+        self._ipc = []
+        if ok:
+            try:
+                ptrs = []
+                for r, (_, handle) in enumerate(infos):
+                    if r == self.rank:
+                        ptrs.append(mine[0])
+                    else:
+                        ptrs.append(e.ipc_open(handle))
+                        self._ipc.append(ptrs[-1])
+                e.fabric_attach(ptrs, timeout_s)
+            except Exception as ex:                # noqa: BLE001
+                logging.warning("fabric attach failed on rank %d: %s", self.rank, ex)
+                ok = False
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok, group=self.group)
+        self.dist.barrier(group=self.group)        # every block has been zeroed before anybody's first push
+        return all(flags)
+
+    _CTL_SLOTS = 64
+
     def shared_mirror(self, nbytes: int) -> np.ndarray:
         """ONE POSIX shared-memory array for the whole node: rank 0 creates it, every rank maps it, and each
         rank's GPU writes its own slice (bossgpu_set_strat_mirror). No gather of masks is ever needed: after
-        the barrier that ends an update every process sees every contig's strategy."""
+        the barrier that ends an update every process sees every contig's strategy. The segment's tail holds
+        2 x 64 control words: the per-update host barrier / agreement between the ranks is a spin on those
+        (about a microsecond) instead of a collective."""
         from multiprocessing import resource_tracker, shared_memory
         name = [None]
+        ctl_off = (max(nbytes, 1) + 63) // 64 * 64
+        total = ctl_off + 2 * self._CTL_SLOTS * 8
         if self.rank == 0:
-            self._shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 1))
+            self._shm = shared_memory.SharedMemory(create=True, size=total)
+            np.frombuffer(self._shm.buf, dtype=np.int64, offset=ctl_off, count=2 * self._CTL_SLOTS)[:] = 0
             np.frombuffer(self._shm.buf, dtype=np.uint8)[:nbytes] = 1          # Contig.strat starts all-accept
             name[0] = self._shm.name
         self.dist.broadcast_object_list(name, src=0, group=self.group)
@@ -234,9 +295,35 @@ class DistGroup:
             except Exception:
                 pass
         self.dist.barrier(group=self.group)
+        if self.world <= self._CTL_SLOTS:
+            self._ctl = np.frombuffer(self._shm.buf, dtype=np.int64, offset=ctl_off, count=2 * self._CTL_SLOTS).reshape(2, -1)
+            self._ctl_seq = 0
         return np.frombuffer(self._shm.buf, dtype=np.uint8)[:nbytes]
 
+    def _ctl_round(self, ok: bool, timeout_s: float = 60.0) -> bool:
+        """All ranks post (sequence number, ok) and wait for each other; slots alternate by sequence parity so
+        a rank that is already one round ahead cannot overwrite a word somebody still has to read."""
+        import time
+        self._ctl_seq += 1
+        seq, row = self._ctl_seq, self._ctl[self._ctl_seq & 1]
+        row[self.rank] = seq * 2 + (1 if ok else 0)
+        t0 = time.perf_counter()
+        while True:
+            vals = row[: self.world]
+            if (vals >= seq * 2).all():
+                return bool((vals & 1).all())
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"rank {self.rank}: peers did not reach host round {seq}")
+
     def close(self) -> None:
+        e = self.engines[0] if self.engines else None
+        for p in getattr(self, "_ipc", []):
+            try:
+                e.ipc_close(p)
+            except Exception:
+                pass
+        self._ipc = []
+        self._ctl = None
         shm = getattr(self, "_shm", None)
         if shm is not None:
             self._shm = None
@@ -248,6 +335,8 @@ class DistGroup:
                 pass
 
     def agree(self, ok: bool) -> bool:
+        if getattr(self, "_ctl", None) is not None:
+            return self._ctl_round(ok)
         import torch
         dev = self.engines[0].exchange_tensor(BUF_SWITCH).device
         t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
@@ -255,6 +344,9 @@ class DistGroup:
         return bool(t.item())
 
     def barrier(self) -> None:
+        if getattr(self, "_ctl", None) is not None:
+            self._ctl_round(True)
+            return
         self.dist.barrier(group=self.group)
 
 
@@ -300,7 +392,16 @@ class ShardedRun(BossRuns):
     `strat` (and writes boss.npz). With `n_virtual` it instead drives that many shards on one GPU."""
 
     def __init__(self, *args, n_virtual: int | None = None, halo_bins: int = 2048, group=None,
-                 engine_factory=Engine, **kw):
+                 engine_factory=Engine, exchange: str = "auto", fabric_timeout_s: float = 0.0, **kw):
+        """`exchange`: "fabric" = the GPUs exchange over peer memory inside the update (csrc/fabric.cuh; no host
+        round trip), "phases" = the host runs a collective after each phase (NCCL / gloo / copies between
+        virtual shards), "auto" = fabric between processes when every rank can map its peers, else phases;
+        virtual shards default to phases (they share one stream unless fabric is asked for)."""
+        if exchange not in ("auto", "fabric", "phases"):
+            raise ValueError("exchange must be 'auto', 'fabric' or 'phases'")
+        self._exchange = exchange
+        self._fabric_timeout_s = float(fabric_timeout_s)
+        self._fabric = False
         self._n_virtual = n_virtual
         self._halo_bins = int(halo_bins)
         self._dist_group = group
@@ -324,11 +425,18 @@ class ShardedRun(BossRuns):
                 if not head and not tail and s.length // BIN < self._halo_bins:
                     raise ValueError("a shard lies strictly inside a contig and is shorter than the bin halo")
         self.engines = []
+        self._streams = []
+        want_fabric_local = self._n_virtual is not None and self._exchange == "fabric"
         for sid in mine:
             segs = self.plan[sid]
+            st = stream
+            if want_fabric_local:
+                import torch
+                self._streams.append(torch.cuda.Stream(device=device))     # one stream per virtual shard
+                st = self._streams[-1].cuda_stream
             e = self._engine_factory(contig_lengths=lens, ref_codes=[codes[s.contig][s.start:s.start + s.length] for s in segs],
                                      n_barcodes=self.nbarcodes, ploidy=self.ploidy, n_sites_total=int(self.ref.n_sites),
-                                     device=device, stream=stream, segments=segs, halo_bins=self._halo_bins)
+                                     device=device, stream=st, segments=segs, halo_bins=self._halo_bins)
             e.set_shards(n, sid, self.row_start)
             self.engines.append(e)
         self.engine = self.engines[0]
@@ -353,6 +461,15 @@ class ShardedRun(BossRuns):
         view = _Pieces(self)
         for k, c in enumerate(self.contigs_filt.values()):
             c._bind(view, k)
+        if n > 1 and (want_fabric_local or (self._n_virtual is None and self._exchange in ("auto", "fabric"))):
+            self._fabric = bool(self.group.setup_fabric(self._fabric_timeout_s))
+            if self._exchange == "fabric" and not self._fabric:
+                raise RuntimeError("exchange='fabric' was asked for but the shards cannot map each other's memory")
+        logging.info("sharded update over %d shard(s): %s", n, "peer-memory fabric" if self._fabric else "phase protocol")
+
+    @property
+    def exchange_mode(self) -> str:
+        return "fabric" if self._fabric else "phases"
 
     def local_sites(self) -> int:
         return int(sum(s.length for e in self.engines for s in e.segments))
@@ -393,6 +510,20 @@ class ShardedRun(BossRuns):
         w_max = max(int(np.max(np.asarray(approx_ccl) // BIN)), 4)
         if w_max - 1 > self._halo_bins and g.n_shards > 1:
             raise ValueError(f"staircase window of {w_max} bins exceeds the bin halo ({self._halo_bins}) kept on shard edges")
+        if self._fabric:
+            # every kernel of the update, exchanges included, is enqueued on every local shard before anybody
+            # synchronises; the GPUs meet each other at the four exchange steps on their own
+            for e, p in zip(self.engines, ps):
+                e.update_fused_begin(p)
+            outs, err = [], None
+            for e in self.engines:
+                try:
+                    outs.append(e.update_fused_end())
+                except Exception as ex:            # noqa: BLE001 - every shard must be drained before raising
+                    err = err or ex
+            if err is not None:
+                raise err
+            return self._combine(outs)
         for e, p in zip(self.engines, ps):
             e.update_phase(0, p)
             e.halo_pack()
@@ -411,6 +542,10 @@ class ShardedRun(BossRuns):
                 e.update_phase(3, p)
             g.allgather_mask()
         outs = [e.update_phase(4, p) for e, p in zip(self.engines, ps)]
+        return self._combine(outs)
+
+    @staticmethod
+    def _combine(outs) -> UpdateOutcome:
         out = outs[0]
         if len(outs) > 1:
             out.n_accept = (sum(o.n_accept[0] for o in outs), sum(o.n_accept[1] for o in outs))

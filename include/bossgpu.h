@@ -40,6 +40,7 @@ extern "C" {
 #define BOSSGPU_ESTATE       -6   /* call sequence violated (e.g. update phases out of order) */
 #define BOSSGPU_EEMPTY       -7   /* all benefits are zero: upstream `np.max` of an empty array raises
                                      ValueError (sequences.py:588) */
+#define BOSSGPU_EPEER        -8   /* sharded update: a peer shard did not reach an exchange step in time */
 
 /* model constants of the reference (function defaults upstream, fixed here) */
 #define BOSSGPU_BIN          100     /* downsampling window: reference.py:109,215 ; sequences.py:577 */
@@ -225,6 +226,30 @@ int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_update_para
 #define BOSSGPU_BUF_STRAT      6   /* uint8[strat rows * 2 * n_barcodes]: this shard's Contig.strat rows (gather to the
                                       process that writes boss.npz) */
 int bossgpu_exchange_buffer(bossgpu_handle* h, int which, void** dev_ptr, size_t* bytes);
+
+/* Peer-memory fabric: the same four exchanges done by the GPUs themselves, with no host round trip and no
+ * library collective inside an update. Upstream has no counterpart (it is one process: the per-contig loops of
+ * boss/runs/core.py:83-121 and the global threshold of sequences.py:566-649 run back to back); the exchange
+ * points are the ones listed for bossgpu_update_phase.
+ *
+ * Every shard owns one exchange block in its HBM (allocated by bossgpu_set_shards). Peers map it — through the
+ * CUDA IPC handle when shards are processes (one per GPU of the NVSwitch box), or simply by address when they
+ * are handles of one process on one device ("virtual shards", each on its OWN stream) — and store their
+ * contributions and an epoch flag into it over NVLink; a shard spins on its own block only.
+ *   bossgpu_fabric_info    this shard's block: device pointer, size, 64-byte IPC handle (any out may be NULL)
+ *   bossgpu_ipc_open/close map / unmap a peer process' block on `device`
+ *   bossgpu_fabric_attach  peer_ptrs[n_shards]: every shard's block as THIS device addresses it (entry
+ *                          shard_index = own block). timeout_s <= 0 keeps the default (2 s): a peer that does
+ *                          not show up makes bossgpu_update_fused_end return BOSSGPU_EPEER instead of hanging.
+ *   bossgpu_update_fused_begin  enqueue ALL kernels of one update, exchanges included; returns at once. Every
+ *                          shard must call it the same number of times (the epoch is the call count).
+ *   bossgpu_update_fused_end    one stream synchronisation, then the result record (as bossgpu_update). */
+int bossgpu_fabric_info(bossgpu_handle* h, void** dev_ptr, size_t* bytes, unsigned char ipc_handle[64]);
+int bossgpu_ipc_open(int device, const unsigned char ipc_handle[64], void** dev_ptr);
+int bossgpu_ipc_close(int device, void* dev_ptr);
+int bossgpu_fabric_attach(bossgpu_handle* h, int32_t n_shards, const uint64_t* peer_ptrs, double timeout_s);
+int bossgpu_update_fused_begin(bossgpu_handle* h, const bossgpu_update_params* p);
+int bossgpu_update_fused_end(bossgpu_handle* h, bossgpu_update_result* r);
 
 /* ---------------------------------------------------------------------------------------------
  * Results and state access (host buffers, reference layouts).

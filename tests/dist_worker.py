@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--case", default="hap_nb1")
     ap.add_argument("--halo", type=int, default=160)
+    ap.add_argument("--exchange", default="auto")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.backend == "nccl":
@@ -44,7 +45,9 @@ def main():
     g = load_case(a.case)
     run = ShardedRun(contigs=g.records, ploidy=g.ploidy, barcodes=g.barcodes,
                      reject_refs=",".join(g.reject_refs) if g.reject_refs else None, bucket_threshold=g.bucket_threshold,
-                     halo_bins=a.halo, engine_factory=factory, device=local)
+                     halo_bins=a.halo, engine_factory=factory, device=local, exchange=a.exchange, fabric_timeout_s=20.0)
+    if a.exchange != "auto":
+        assert run.exchange_mode == a.exchange, run.exchange_mode
     orc = H.oracle_run(g.records, g.ploidy, g.reject_refs, g.barcodes, g.bucket_threshold) if rank == 0 else None
     n_upd = 0
     for bi, (paf, seqs, bcs) in enumerate(g.batches):
@@ -66,7 +69,7 @@ def main():
                 assert run.contigs[name].strat.shape == (1,) and not run.contigs[name].strat.any()
     if rank == 0:
         assert n_upd >= 2
-        print(f"SHARDED-OK case={a.case} world={dist.get_world_size()} plan={[[(s.contig, s.start, s.length) for s in segs] for segs in run.plan]}")
+        print(f"SHARDED-OK case={a.case} world={dist.get_world_size()} exchange={run.exchange_mode} plan={[[(s.contig, s.start, s.length) for s in segs] for segs in run.plan]}")
     dist.barrier()
     run.close()
     dist.destroy_process_group()
