@@ -293,6 +293,27 @@ def run_b200(args, spec):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # ---- leg 1b: the same, starting one step earlier — from the mapper's raw PAF text ----------
+    # upstream: Paf.parse_PAF(StringIO(paf_raw)) builds {read: [PafLine]} in Python before convert_records
+    # (mapper.py:63-65); process_batch_text tokenises the text in C and never builds those objects
+    txt_times = []
+    for it in range(args.warmup + args.steps):
+        pd, seqs, rb = batches[it % n_batches]
+        barrier()
+        t0 = time.perf_counter()
+        run.process_batch_text(rb.paf_text, seqs)
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            txt_times.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    parse_PAF(io.StringIO(batches[0][2].paf_text), min_len=200)
+    py_parse_ms = (time.perf_counter() - t0) * 1e3
+    txt_t = torch.tensor([float(np.mean(txt_times))], device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(txt_t, op=dist.ReduceOp.MAX)
+    txt_s = float(txt_t.item())
+
     # ---- leg 2: inputs resident in HBM -------------------------------------------------------------------
     dev_batches = []
     for pd, seqs, rb in batches:
@@ -380,6 +401,9 @@ def run_b200(args, spec):
                 "host_ms": dict(zip(("convert_records", "ingest", "update_wrapper"),
                                     (float(x) * 1e3 for x in np.mean(np.array(e2e_parts), axis=0)))),
                 "update_wrapper_ms": getattr(run, "last_host_ms", None)},
+        "e2e_from_paf_text": {"value": total_sites / txt_s / 1e9, "unit": UNIT, "ms_per_step": txt_s * 1e3,
+                              "what": "BossRuns.process_batch_text: raw PAF text + read strings -> masks on the host (C tokeniser, no PafLine objects)",
+                              "python_parse_PAF_ms_avoided": py_parse_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_score_bin", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"

@@ -11,6 +11,7 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <stdint.h>
+#include <string.h>
 
 static PyObject *s_tname, *s_tstart, *s_tend, *s_barcode, *s_rev, *s_cigar, *s_qname, *s_qlen, *s_qstart, *s_qend;
 
@@ -139,8 +140,272 @@ fail:
     return NULL;
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * convert_text — the same batch straight from the mapper's PAF TEXT.
+ *
+ * Upstream goes  paf_raw (str) -> Paf.parse_PAF(StringIO(paf_raw), min_len=mu/2) -> {qname: [PafLine]} -> convert_records
+ * (boss/mapper.py:63-65, boss/paf.py:18-74,653-672, boss/runs/sequences.py:694-738): one Python object with ~25
+ * attributes per alignment. Here the text is tokenised in place and only the winning record of every read is turned
+ * into the ten numbers the device needs; the CIGAR pointers point into the text itself. Semantics followed:
+ *   - lines are split on '\n', stripped (str.strip) and split on tabs; fewer than 12 columns -> IndexError (paf.py:47-52)
+ *   - every core column goes through conv_type(x, int): an all-digit query/target NAME is an int upstream and becomes its
+ *     canonical decimal text again under str() ("007" -> "7", paf.py:54-56)
+ *   - rev = (strand != '+') (paf.py:58); tags are split on ':' into exactly three parts (ValueError otherwise), the type
+ *     letter must be one of i A f Z (KeyError otherwise), a repeated key keeps its last value (paf.py:87-99)
+ *   - AS defaults to 0, primary <=> tp value == "P"; records with alignment_block_length < min_len or not primary are
+ *     dropped AFTER the whole line has been parsed (paf.py:664-669)
+ *   - reads keep their order of first appearance; with several records the winner is the last element of
+ *     np.argsort by (mapq, AS) (paf.py:710-722): for up to 16 candidates NumPy's sort is an insertion sort, i.e. stable,
+ *     so ties go to the LATER record; larger groups are handed to `best_index` (NumPy itself) to stay exact.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { const char* p; Py_ssize_t n; } span_t;
+
+typedef struct {
+    span_t tname, cigar;
+    long long qlen, qstart, qend, tstart, tend, mapq, as;
+    int rev, has_cigar;
+    Py_ssize_t next;          /* next record of the same read, -1 at the end */
+} rec_t;
+
+typedef struct { Py_ssize_t first, last, count; PyObject* qname; } grp_t;
+
+static int is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+
+static span_t strip_span(span_t s) {
+    while (s.n > 0 && is_space((unsigned char)s.p[0])) { ++s.p; --s.n; }
+    while (s.n > 0 && is_space((unsigned char)s.p[s.n - 1])) --s.n;
+    return s;
+}
+
+/* Python's int(str) for the forms a PAF can hold: optional surrounding whitespace, optional sign, decimal digits.
+ * 0 = parsed, -1 = not an integer (upstream would keep the string). */
+static int parse_int(span_t s, long long* out) {
+    s = strip_span(s);
+    if (s.n == 0) return -1;
+    int neg = 0;
+    Py_ssize_t i = 0;
+    if (s.p[0] == '+' || s.p[0] == '-') { neg = s.p[0] == '-'; i = 1; }
+    if (i >= s.n) return -1;
+    unsigned long long v = 0;
+    for (; i < s.n; ++i) {
+        unsigned c = (unsigned char)s.p[i] - '0';
+        if (c > 9) return -1;
+        if (v > (unsigned long long)(INT64_MAX / 10 - 1)) return -1;
+        v = v * 10 + c;
+    }
+    *out = neg ? -(long long)v : (long long)v;
+    return 0;
+}
+
+/* str(conv_type(x, int)) */
+static PyObject* name_object(span_t s) {
+    long long v;
+    if (parse_int(s, &v) == 0) return PyUnicode_FromFormat("%lld", v);
+    return PyUnicode_FromStringAndSize(s.p, s.n);
+}
+
+static PyObject* convert_text(PyObject* self, PyObject* args) {
+    PyObject *text, *seqs, *contig_index, *best_index, *barcodes, *bufs, *keep;
+    long long min_len;
+    if (!PyArg_ParseTuple(args, "UO!O!LOOO!O!", &text, &PyDict_Type, &seqs, &PyDict_Type, &contig_index, &min_len, &barcodes,
+                          &best_index, &PyTuple_Type, &bufs, &PyList_Type, &keep))
+        return NULL;
+    if (barcodes != Py_None && !PyDict_Check(barcodes)) { PyErr_SetString(PyExc_TypeError, "barcodes must be a dict or None"); return NULL; }
+    if (PyTuple_GET_SIZE(bufs) != 10) { PyErr_SetString(PyExc_ValueError, "expected 10 output buffers"); return NULL; }
+    Py_ssize_t tlen = 0;
+    const char* tp = PyUnicode_AsUTF8AndSize(text, &tlen);
+    if (!tp) return NULL;
+    if (tlen != PyUnicode_GET_LENGTH(text)) { PyErr_SetString(PyExc_ValueError, "PAF text must be ASCII"); return NULL; }
+
+    Py_ssize_t n_lines = 0;
+    for (Py_ssize_t i = 0; i < tlen; ++i) n_lines += tp[i] == '\n';
+    if (tlen > 0 && tp[tlen - 1] != '\n') ++n_lines;
+
+    rec_t* recs = (rec_t*)PyMem_Malloc(sizeof(rec_t) * (size_t)(n_lines ? n_lines : 1));
+    grp_t* grps = (grp_t*)PyMem_Malloc(sizeof(grp_t) * (size_t)(n_lines ? n_lines : 1));
+    PyObject* gindex = PyDict_New();
+    Py_ssize_t n_rec = 0, n_grp = 0;
+    Py_buffer vb[10];
+    int got = 0;
+    PyObject* result = NULL;
+    if (!recs || !grps || !gindex) { PyErr_NoMemory(); goto done; }
+
+    /* ---- pass 1: tokenise every line, filter, group by read ---- */
+    for (Py_ssize_t pos = 0; pos < tlen;) {
+        Py_ssize_t e = pos;
+        while (e < tlen && tp[e] != '\n') ++e;
+        span_t line = {tp + pos, e - pos};
+        pos = e + 1;
+        line = strip_span(line);
+        span_t col[12];
+        int nc = 0;
+        Py_ssize_t i = 0, c0 = 0;
+        rec_t r;
+        memset(&r, 0, sizeof r);
+        r.next = -1;
+        long long as = 0, blocklen = 0;
+        int primary = 0;
+        for (;; ++i) {
+            if (i == line.n || line.p[i] == '\t') {
+                span_t f = {line.p + c0, i - c0};
+                if (nc < 12) {
+                    col[nc] = f;
+                } else {
+                    /* key:type:value */
+                    Py_ssize_t a = -1, b = -1, colons = 0;
+                    for (Py_ssize_t k = 0; k < f.n; ++k)
+                        if (f.p[k] == ':') { if (colons == 0) a = k; else if (colons == 1) b = k; ++colons; }
+                    if (colons != 2) {
+                        PyErr_SetString(PyExc_ValueError, colons < 2 ? "not enough values to unpack (expected 3)" : "too many values to unpack (expected 3)");
+                        goto done;
+                    }
+                    span_t key = {f.p, a}, typ = {f.p + a + 1, b - a - 1}, val = {f.p + b + 1, f.n - b - 1};
+                    if (typ.n != 1 || !(typ.p[0] == 'i' || typ.p[0] == 'A' || typ.p[0] == 'f' || typ.p[0] == 'Z')) {
+                        PyObject* ko = PyUnicode_FromStringAndSize(typ.p, typ.n);
+                        if (ko) { PyErr_SetObject(PyExc_KeyError, ko); Py_DECREF(ko); }
+                        goto done;
+                    }
+                    if (key.n == 2 && key.p[0] == 'A' && key.p[1] == 'S') {
+                        if (parse_int(val, &as) != 0) { PyErr_SetString(PyExc_ValueError, "AS tag is not an integer"); goto done; }
+                    } else if (key.n == 2 && key.p[0] == 't' && key.p[1] == 'p') {
+                        primary = val.n == 1 && val.p[0] == 'P';
+                    } else if (key.n == 2 && key.p[0] == 'c' && key.p[1] == 'g') {
+                        r.cigar = val;
+                        r.has_cigar = 1;
+                    }
+                }
+                ++nc;
+                c0 = i + 1;
+                if (i == line.n) break;
+            }
+        }
+        if (nc < 12) { PyErr_SetString(PyExc_IndexError, "list index out of range (PAF line with fewer than 12 columns)"); goto done; }
+        if (parse_int(col[1], &r.qlen) || parse_int(col[2], &r.qstart) || parse_int(col[3], &r.qend) || parse_int(col[7], &r.tstart) ||
+            parse_int(col[8], &r.tend) || parse_int(col[10], &blocklen) || parse_int(col[11], &r.mapq)) {
+            PyErr_SetString(PyExc_ValueError, "PAF line with a non-integer coordinate column");
+            goto done;
+        }
+        r.rev = !(col[4].n == 1 && col[4].p[0] == '+');
+        r.tname = col[5];
+        r.as = as;
+        if (blocklen < min_len || !primary) continue;              /* paf.py:664-669 */
+        PyObject* qn = name_object(col[0]);
+        if (!qn) goto done;
+        PyObject* gi = PyDict_GetItemWithError(gindex, qn);         /* borrowed */
+        if (!gi && PyErr_Occurred()) { Py_DECREF(qn); goto done; }
+        Py_ssize_t g;
+        if (gi) {
+            g = PyLong_AsSsize_t(gi);
+            Py_DECREF(qn);
+            recs[grps[g].last].next = n_rec;
+            grps[g].last = n_rec;
+            grps[g].count++;
+        } else {
+            g = n_grp++;
+            PyObject* go = PyLong_FromSsize_t(g);
+            if (!go || PyDict_SetItem(gindex, qn, go) < 0) { Py_XDECREF(go); Py_DECREF(qn); --n_grp; goto done; }
+            Py_DECREF(go);
+            grps[g].first = grps[g].last = n_rec;
+            grps[g].count = 1;
+            grps[g].qname = qn;                                      /* owned until `done` */
+        }
+        recs[n_rec++] = r;
+    }
+
+    /* ---- pass 2: winner of every read -> the ten arrays ---- */
+    {
+        static const Py_ssize_t item[10] = {4, 8, 8, 4, 1, 8, 8, 8, 8, 8};
+        for (; got < 10; ++got) {
+            if (PyObject_GetBuffer(PyTuple_GET_ITEM(bufs, got), &vb[got], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) goto done;
+            if (vb[got].len < n_grp * item[got]) { ++got; PyErr_SetString(PyExc_ValueError, "output buffer too small"); goto done; }
+        }
+        int32_t* o_contig = (int32_t*)vb[0].buf;   int64_t* o_tstart = (int64_t*)vb[1].buf;  int64_t* o_tend = (int64_t*)vb[2].buf;
+        int32_t* o_bc = (int32_t*)vb[3].buf;       uint8_t* o_rev = (uint8_t*)vb[4].buf;     uint64_t* o_cp = (uint64_t*)vb[5].buf;
+        int64_t* o_cl = (int64_t*)vb[6].buf;       uint64_t* o_sp = (uint64_t*)vb[7].buf;    int64_t* o_sf = (int64_t*)vb[8].buf;
+        int64_t* o_st = (int64_t*)vb[9].buf;
+        Py_ssize_t n = 0, skipped = 0;
+        if (n_grp > 0 && PyList_Append(keep, text) < 0) goto done;  /* the CIGAR pointers live inside the text */
+        for (Py_ssize_t g = 0; g < n_grp; ++g) {
+            Py_ssize_t w = grps[g].first;
+            if (grps[g].count > 16) {
+                PyObject* keys = PyList_New(grps[g].count);
+                if (!keys) goto done;
+                Py_ssize_t k = 0;
+                for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next, ++k)
+                    PyList_SET_ITEM(keys, k, Py_BuildValue("(LL)", recs[x].mapq, recs[x].as));
+                PyObject* bi = PyObject_CallOneArg(best_index, keys);
+                Py_DECREF(keys);
+                if (!bi) goto done;
+                Py_ssize_t want = PyLong_AsSsize_t(bi);
+                Py_DECREF(bi);
+                if (want < 0 || want >= grps[g].count) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "best_index out of range"); goto done; }
+                for (k = 0; k < want; ++k) w = recs[w].next;
+            } else {
+                for (Py_ssize_t x = recs[w].next; x >= 0; x = recs[x].next)
+                    if (recs[x].mapq > recs[w].mapq || (recs[x].mapq == recs[w].mapq && recs[x].as >= recs[w].as)) w = x;
+            }
+            const rec_t* r = &recs[w];
+            PyObject* tn = name_object(r->tname);
+            if (!tn) goto done;
+            PyObject* k = PyDict_GetItemWithError(contig_index, tn);      /* borrowed */
+            Py_DECREF(tn);
+            if (!k) {
+                if (PyErr_Occurred()) goto done;
+                ++skipped;                                                  /* core.py:83-86 */
+                continue;
+            }
+            const long long ki = PyLong_AsLongLong(k);
+            PyObject* s = PyDict_GetItemWithError(seqs, grps[g].qname);    /* borrowed; KeyError like seqs[rec.qname] */
+            if (!s) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, grps[g].qname); goto done; }
+            if (!r->has_cigar) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); goto done; }   /* sequences.py:718 */
+            if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "reads must be str"); goto done; }
+            Py_ssize_t slen = 0;
+            const char* sptr = PyUnicode_AsUTF8AndSize(s, &slen);
+            if (!sptr) goto done;
+            if (slen != PyUnicode_GET_LENGTH(s)) { PyErr_SetString(PyExc_ValueError, "read and CIGAR strings must be ASCII"); goto done; }
+            long long bc = 0;
+            if (barcodes != Py_None) {
+                PyObject* bo = PyDict_GetItemWithError(barcodes, grps[g].qname);
+                if (!bo && PyErr_Occurred()) goto done;
+                if (bo && bo != Py_None) { bc = PyLong_AsLongLong(bo); if (bc == -1 && PyErr_Occurred()) goto done; }
+            }
+            long long lo, hi;
+            const long long len = (long long)slen;
+            if (r->qstart < 0 || r->qend < 0 || r->qlen - r->qend < 0 && r->rev || r->qlen - r->qstart < 0 && r->rev) {
+                PyErr_SetString(PyExc_ValueError, "negative query coordinates");
+                goto done;
+            }
+            if (r->rev) {                                                   /* Q12, as in convert() above */
+                const long long a = r->qlen - r->qend, b = r->qlen - r->qstart;
+                lo = len - (b < len ? b : len); if (lo < 0) lo = 0;
+                hi = len - (a < len ? a : len); if (hi < 0) hi = 0;
+            } else {
+                lo = clampll(r->qstart, 0, len);
+                hi = clampll(r->qend, 0, len);
+            }
+            if (hi < lo) hi = lo;
+            o_contig[n] = (int32_t)ki; o_tstart[n] = r->tstart; o_tend[n] = r->tend; o_bc[n] = (int32_t)bc; o_rev[n] = (uint8_t)r->rev;
+            o_cp[n] = (uint64_t)(uintptr_t)r->cigar.p; o_cl[n] = (int64_t)r->cigar.n;
+            o_sp[n] = (uint64_t)(uintptr_t)sptr; o_sf[n] = lo; o_st[n] = hi;
+            if (PyList_Append(keep, s) < 0) goto done;
+            ++n;
+        }
+        result = Py_BuildValue("nnn", n, skipped, n_grp);
+    }
+done:
+    for (int i = 0; i < got; ++i) PyBuffer_Release(&vb[i]);
+    for (Py_ssize_t g = 0; g < n_grp; ++g) Py_XDECREF(grps[g].qname);
+    Py_XDECREF(gindex);
+    PyMem_Free(recs);
+    PyMem_Free(grps);
+    return result;
+}
+
 static PyMethodDef methods[] = {
     {"convert", convert, METH_VARARGS, "convert(paf_dict, seqs, contig_index, best_record, bufs, keep) -> (n_used, n_skipped)"},
+    {"convert_text", convert_text, METH_VARARGS,
+     "convert_text(paf_text, seqs, contig_index, min_len, barcodes, best_index, bufs, keep) -> (n_used, n_skipped, n_reads)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_fastconv", "host half of the coverage update (C API walk)", -1, methods};

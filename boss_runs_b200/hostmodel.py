@@ -40,6 +40,8 @@ class PafLine:
     def __init__(self, line: str, tags: bool = True):
         self.line = line
         cols = line.strip().split("\t")
+        if len(cols) < 12:
+            raise IndexError("list index out of range")          # upstream indexes all 12 core columns (paf.py:50-52)
         for name, raw in zip(_PAF_FIELDS, cols[:12]):
             setattr(self, name, _conv(raw, int))
         self.qname, self.tname = str(self.qname), str(self.tname)
@@ -193,6 +195,29 @@ class ReadStartDist:
             wins.append(base + w)
             strands.append(1 if rec.rev else 0)
         return np.asarray(wins, dtype=np.int64), np.asarray(strands, dtype=np.uint8)
+
+    def window_events_arrays(self, contig, tstart, tend, rev) -> tuple[np.ndarray, np.ndarray]:
+        """`window_events` for records already reduced to arrays (one winning record per read, `contig` = index in
+        the tracked-contig order): same bins, same drops, vectorised."""
+        if not hasattr(self, "_win_base"):
+            sizes = np.array([int(a.shape[0]) for a in self.read_starts.values()], dtype=np.int64)
+            self._win_nw = sizes
+            self._win_base = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64) if len(sizes) else sizes
+        contig = np.asarray(contig, dtype=np.int64)
+        rev = np.asarray(rev).astype(bool)
+        pos = np.where(rev, np.asarray(tend, dtype=np.int64), np.asarray(tstart, dtype=np.int64))
+        nw = self._win_nw[contig]
+        ok = (pos >= 0) & (pos <= self.window_size * nw) & (nw > 0)
+        w = np.minimum(pos // self.window_size, nw - 1)
+        return (self._win_base[contig] + w)[ok].astype(np.int64), rev[ok].astype(np.uint8)
+
+    def count_read_starts_arrays(self, contig, tstart, tend, rev) -> tuple[np.ndarray, np.ndarray]:
+        """`count_read_starts` from arrays (the text path never builds PafLine objects)."""
+        wins, strands = self.window_events_arrays(contig, tstart, tend, rev)
+        if len(wins):
+            np.add.at(self._merged_rows(), (wins, strands), 1.0)
+            self.csum = getattr(self, "csum", 0.0) + float(len(wins))
+        return wins, strands
 
     def pointmass_scalars(self, csum: float | None = None) -> tuple[float, float, float]:
         """(alpha, denom, zero_value) of `update_f_pointmass` (readstartdist.py:96-111): F-hat is

@@ -25,7 +25,7 @@ import numpy as np
 
 from ._lib import BIN, BUCKET, str_ptr
 from .engine import Engine, UpdateOutcome
-from .hostmodel import ReadlengthDist, ReadStartDist, best_record
+from .hostmodel import ReadlengthDist, ReadStartDist, best_record, parse_PAF
 from .priors import Scoring
 
 _SEQ_LUT = np.zeros(256, dtype=np.uint8)
@@ -59,17 +59,26 @@ class PackedBatch:
     def __len__(self) -> int:
         return int(self.contig.shape[0])
 
+    def cigar_bytes(self, i: int) -> bytes:
+        import ctypes
+        return ctypes.string_at(int(self.cigar_ptr[i]), int(self.cigar_len[i]))
+
+    def slice_bytes(self, i: int) -> bytes:
+        """The aligned slice of read i, original orientation."""
+        import ctypes
+        return ctypes.string_at(int(self.seq_ptr[i]) + int(self.seq_from[i]), int(self.seq_to[i] - self.seq_from[i]))
+
     def texts(self):
         """(cig_off, cigar_text, seq_off, seq_text): the joined-text form `bossgpu_ingest_records` takes."""
-        cigs = self.keep[0::2]
-        seqs = [s[a:b] for s, a, b in zip(self.keep[1::2], self.seq_from, self.seq_to)]
         n = len(self)
+        cigs = [self.cigar_bytes(i) for i in range(n)]
+        seqs = [self.slice_bytes(i) for i in range(n)]
         cig_off = np.zeros(n + 1, dtype=np.int64)
         seq_off = np.zeros(n + 1, dtype=np.int64)
         if n:
             np.cumsum([len(c) for c in cigs], out=cig_off[1:])
             np.cumsum([len(p) for p in seqs], out=seq_off[1:])
-        return cig_off, "".join(cigs).encode("ascii", "replace"), seq_off, "".join(seqs).encode("ascii", "replace")
+        return cig_off, b"".join(cigs), seq_off, b"".join(seqs)
 
 
 class CoverageConverter:
@@ -97,6 +106,32 @@ class CoverageConverter:
         cp, sp = np.empty(n, np.uint64), np.empty(n, np.uint64)
         keep: list = []
         used, skipped = fc.convert(paf_dict, seqs, self.contig_index, best_record, (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st), keep)
+        return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
+                           sf[:used], st[:used], keep, skipped)
+
+    def convert_text(self, paf_raw: str, seqs: dict[str, str], min_len: int = 200,
+                     barcodes: dict[str, int] | None = None) -> PackedBatch:
+        """The batch straight from the mapper's PAF text: `Paf.parse_PAF(StringIO(paf_raw), min_len=mu/2)`
+        (mapper.py:63-65, paf.py:653-672) + `convert_records` in one C pass over the text (csrc/fastconv.c
+        `convert_text`); no PafLine objects are built. `barcodes`: optional {read id: barcode index}.
+        Falls back to `parse_PAF` + `convert_records` when the helper has not been built."""
+        fc = _fastconv()
+        if fc is None or not hasattr(fc, "convert_text"):
+            from io import StringIO
+            pd = parse_PAF(StringIO(paf_raw), min_len=min_len)
+            if barcodes:
+                for rid, recs in pd.items():
+                    for r in recs:
+                        r.barcode = barcodes.get(rid)
+            return self.convert_records(pd, seqs)
+        n = paf_raw.count("\n") + 1
+        contig, bc = np.empty(n, np.int32), np.empty(n, np.int32)
+        tstart, tend, cl, sf, st = (np.empty(n, np.int64) for _ in range(5))
+        rev = np.empty(n, np.uint8)
+        cp, sp = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        keep: list = []
+        used, skipped, _ = fc.convert_text(paf_raw, seqs, self.contig_index, int(min_len), barcodes, _best_index,
+                                           (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st), keep)
         return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
                            sf[:used], st[:used], keep, skipped)
 
@@ -138,6 +173,12 @@ class CoverageConverter:
                            np.asarray(rev, dtype=np.uint8), np.asarray(cp, dtype=np.uint64), np.asarray(cl, dtype=np.int64),
                            np.asarray(sp, dtype=np.uint64), np.asarray(sf, dtype=np.int64), np.asarray(st, dtype=np.int64),
                            keep, skipped)
+
+
+def _best_index(keys: list) -> int:
+    """`Paf.choose_best_mapper` on bare (mapq, AS) pairs (paf.py:710-722): NumPy's own argsort decides."""
+    arr = np.array(keys, dtype=[("q", int), ("dp", int)])
+    return int(np.argsort(arr, order=["q", "dp"])[-1])
 
 
 _FASTCONV = False
@@ -404,7 +445,7 @@ class BossRuns:
     def count_read_starts(self, paf_dict) -> None:
         """`ReadStartDist.count_read_starts` on the host mirror AND on the GPU-side counter."""
         wins, strands = self.read_starts.count_read_starts(paf_dict=paf_dict)
-        self.engine.read_starts_add(wins, strands)
+        self._read_starts_to_device(wins, strands)
 
     # -- one batch (core.py:202-224, minus the mapping call) -------------------------------------------
     def process_batch_runs(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
@@ -417,6 +458,22 @@ class BossRuns:
         self.count_read_starts(paf_dict if paf_dict_starts is None else paf_dict_starts)
         self.update_wrapper()
         self.batch += 1
+
+    def process_batch_text(self, paf_raw: str, seqs: dict[str, str], quals: dict[str, str] | None = None,
+                           barcodes: dict[str, int] | None = None, min_len: int = 200) -> None:
+        """One batch from the mapper's raw PAF text (`Mapper._mappy_batch`'s return value, mapper.py:63): what
+        `process_batch_runs` does after `map_sequences`, without materialising `{read id: [PafLine]}` — the text is
+        tokenised once in C, the winning record of every read goes to the GPU, and the read starts are counted from
+        the same arrays. `min_len` = mu/2 as `Mapper.map_sequences` passes it (mapper.py:64)."""
+        b = self.cc.convert_text(paf_raw, seqs, min_len=min_len, barcodes=barcodes)
+        self._effect_increments(increments=b)
+        wins, strands = self.read_starts.count_read_starts_arrays(b.contig, b.tstart, b.tend, b.rev)
+        self._read_starts_to_device(wins, strands)
+        self.update_wrapper()
+        self.batch += 1
+
+    def _read_starts_to_device(self, wins, strands) -> None:
+        self.engine.read_starts_add(wins, strands)
 
     # -- device-resident variants (bench.py `value` leg, pipelined callers) ----------------------------
     def local_sites(self) -> int:
@@ -438,24 +495,23 @@ class BossRuns:
         keep = [i for i in range(len(batch)) if batch.contig[i] in seg_of
                 and t1s[i] > seg_of[batch.contig[i]][1] and t0s[i] < seg_of[batch.contig[i]][2]]
         n = len(keep)
-        cigs, seqs = batch.keep[0::2], batch.keep[1::2]
         comp = np.arange(256, dtype=np.uint8)
         for a, b in zip(b"ATGC", b"TACG"):
             comp[a] = b
         cig_off = np.zeros(n + 1, dtype=np.int64)
         base_off = np.zeros(n + 1, dtype=np.int64)
-        ops = np.empty(sum(len(cigs[i]) // 2 + 1 for i in keep) + 1, dtype=np.uint32)
+        ops = np.empty(int(sum(int(batch.cigar_len[i]) // 2 + 1 for i in keep)) + 1, dtype=np.uint32)
         bases = np.empty(int(sum(batch.seq_to[i] - batch.seq_from[i] for i in keep)) + 1, dtype=np.uint8)
         r, q = C.c_int64(), C.c_int64()
         w = 0
         for j, i in enumerate(keep):
-            text = cigs[i].encode("ascii", "replace")
+            text = batch.cigar_bytes(i)
             k = lib.bossgpu_tokenize_cigar(text, len(text), ops[w:].ctypes.data, len(ops) - w, C.byref(r), C.byref(q))
             if k < 0:
                 raise ValueError("CIGAR tokenizer failed")
             w += k
             cig_off[j + 1] = w
-            sl = np.frombuffer(seqs[i][int(batch.seq_from[i]): int(batch.seq_to[i])].encode("ascii", "replace"), dtype=np.uint8)
+            sl = np.frombuffer(batch.slice_bytes(i), dtype=np.uint8)
             if q.value != len(sl) or r.value != int(t1s[i] - t0s[i]):
                 raise AssertionError(f"read {i}: CIGAR does not span the aligned slice / target interval")
             base_off[j + 1] = base_off[j] + len(sl)

@@ -497,8 +497,7 @@ class ShardedRun(BossRuns):
         if not self.group.agree(err is None):
             raise err if err is not None else RuntimeError("another shard rejected the batch")
 
-    def count_read_starts(self, paf_dict) -> None:
-        wins, strands = self.read_starts.count_read_starts(paf_dict=paf_dict)
+    def _read_starts_to_device(self, wins, strands) -> None:
         for e in self.engines:                      # the window counts are small and replicated on every shard
             e.read_starts_add(wins, strands)
 
@@ -548,7 +547,9 @@ class ShardedRun(BossRuns):
     def _combine(outs) -> UpdateOutcome:
         out = outs[0]
         if len(outs) > 1:
+            # counters of the LOCAL shards (one process per GPU: this rank's share; virtual shards: the whole genome)
             out.n_accept = (sum(o.n_accept[0] for o in outs), sum(o.n_accept[1] for o in outs))
+            out.n_dropout = sum(o.n_dropout for o in outs)
             out.mirror_bytes = sum(o.mirror_bytes for o in outs)
         return out
 

@@ -147,3 +147,28 @@ def test_mirror_follows_device_state(lib):
         packed = np.unpackbits(run.engine.strat_packed(), bitorder="little")[: dev.size].astype(bool)
         assert np.array_equal(packed, dev.reshape(-1))
     assert moved[0] > 0 and all(m <= dev.size + 1024 for m in moved)
+
+
+def test_text_batches_equal_object_batches(lib):
+    """`process_batch_text` (PAF text tokenised in C, read starts from arrays) leaves exactly the state
+    `process_batch_runs` leaves on the parsed objects of the same text — and that equals the oracle's."""
+    contigs, run_obj = make_run({"a": 180_000, "b": 120_000}, bucket_threshold=0, barcodes=["barcode01", "barcode02", "barcode03"])
+    _, run_txt = make_run({"a": 180_000, "b": 120_000}, bucket_threshold=0, barcodes=["barcode01", "barcode02", "barcode03"])
+    orc = H.oracle_run(list(contigs.items()), 1, [], ["barcode01", "barcode02", "barcode03"], 0)
+    for b in range(3):
+        rb = synth.read_batch(contigs, n_reads=500, seed=700 + b, mean_len=2500.0, min_len=300, max_len=9000, n_barcodes=3)
+        lens = {rid: len(s) for rid, s in rb.seqs.items()}
+        pd = H.parse_batch(rb.paf_text, rb.barcodes, True)
+        pd = {rid: recs for rid, recs in pd.items() if recs[0].alignment_block_length >= 200}     # mapper.py:64
+        for run in (run_obj, run_txt):
+            run.rl_dist.update(lens)
+        orc.rl.update(lens)
+        run_obj.process_batch_runs(pd, rb.seqs)
+        run_txt.process_batch_text(rb.paf_text, rb.seqs, barcodes=rb.barcodes)
+        orc.ingest(pd, rb.seqs); orc.read_starts.count(pd); orc.update()
+        assert run_obj.threshold == run_txt.threshold and run_obj.last.ubar0 == run_txt.last.ubar0
+        assert np.array_equal(run_obj.engine.read_starts(), run_txt.engine.read_starts())
+        for name in contigs:
+            assert np.array_equal(run_obj.contigs[name].coverage, run_txt.contigs[name].coverage)
+            assert np.array_equal(run_obj.contigs[name].strat, run_txt.contigs[name].strat)
+        H.compare_state(run_txt, orc, True, f"text/b{b}")

@@ -92,3 +92,105 @@ def test_paf_parsing_follows_upstream():
         (1000, 10, 990, 1, "ctg", 5000, 5980, 60, 880, "500M2D478M", 1)
     assert r.barcode is None
     assert parse_PAF(12345) == {}
+
+
+# ---- the text path: PAF text -> batch in one C pass (fastconv.c convert_text) -----------------------------------
+def _via_objects(cc, text, seqs, min_len, barcodes=None):
+    pd = parse_PAF(io.StringIO(text), min_len=min_len)
+    if barcodes:
+        for rid, recs in pd.items():
+            for r in recs:
+                r.barcode = barcodes.get(rid)
+    return pd, cc._convert_records_py(pd, seqs)
+
+
+def same_text(a, b):
+    """Same batch; the pointers differ (CIGARs live inside the text on one side, in PafLine attributes on the other)."""
+    for f in ("contig", "tstart", "tend", "barcode", "rev", "cigar_len", "seq_ptr", "seq_from", "seq_to"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.n_skipped == b.n_skipped and len(a) == len(b)
+    for i in range(len(a)):
+        assert a.cigar_bytes(i) == b.cigar_bytes(i) and a.slice_bytes(i) == b.slice_bytes(i)
+
+
+def test_text_path_equals_object_path(fc):
+    contigs = synth.random_contigs({"a": 300_000, "b": 200_000, "7": 120_000, "c": 110_000}, seed=4)
+    rb = synth.read_batch(contigs, n_reads=800, seed=21, mean_len=3000.0, min_len=150, n_barcodes=3)
+    lines = rb.paf_text.splitlines()
+    rng = np.random.default_rng(0)
+    extra = []
+    for i in rng.choice(len(lines), size=200, replace=False):
+        f = lines[i].split("\t")
+        kind = int(rng.integers(0, 5))
+        if kind == 0:                                            # a second record that loses on mapq
+            f[11] = "10"; f[7] = str(int(f[7]) + 3)
+        elif kind == 1:                                          # ties on (mapq, AS): the LATER record wins
+            f[7] = str(int(f[7]) + 5)
+        elif kind == 2:                                          # wins on AS
+            f[12] = "AS:i:999999"; f[5] = "b"; f[6] = "200000"
+        elif kind == 3:                                          # secondary alignment: filtered
+            f[13] = "tp:A:S"; f[11] = "61"
+        else:                                                    # too short: filtered by min_len
+            f[10] = "150"; f[11] = "61"
+        extra.append("\t".join(f))
+    # one read with 20 tied records (> 16: NumPy's sort is no longer an insertion sort; the helper asks NumPy)
+    f = lines[0].split("\t")
+    big = []
+    for k in range(20):
+        g = list(f); g[0] = "whale"; g[7] = str(int(f[7]) + k); g[11] = str(30 + (k * 7) % 3); g[12] = f"AS:i:{100 + (k * 5) % 4}"
+        big.append("\t".join(g))
+    text = "\n".join(lines[:400] + extra[:100] + big + lines[400:] + extra[100:])      # no trailing newline, like mapper.py:87
+    seqs = dict(rb.seqs)
+    seqs["whale"] = seqs[f[0]]
+    cc = CoverageConverter({"a": 0, "b": 1, "7": 2})            # "c" is not tracked; "7" is an all-digit name
+    bcs = dict(rb.barcodes); bcs["whale"] = 2
+    for min_len in (1, 200):
+        for barcodes in (None, bcs):
+            pd, want = _via_objects(cc, text, seqs, min_len, barcodes)
+            got = cc.convert_text(text, seqs, min_len=min_len, barcodes=barcodes)
+            same_text(got, want)
+            assert got.n_skipped > 0 and len(got) > 600
+    # read starts from the arrays == read starts from the objects
+    from boss_runs_b200.hostmodel import ReadStartDist
+
+    class C:
+        def __init__(self, n): self.length = n
+    tracked = {n: C(len(contigs[n])) for n in ("a", "b", "7")}
+    r1, r2 = ReadStartDist(tracked), ReadStartDist(tracked)
+    pd, want = _via_objects(cc, text, seqs, 200)
+    w1, s1 = r1.count_read_starts(pd)
+    w2, s2 = r2.count_read_starts_arrays(want.contig, want.tstart, want.tend, want.rev)
+    assert np.array_equal(w1, w2) and np.array_equal(s1, s2) and np.array_equal(r1.merge(), r2.merge()) and len(w1) > 600
+
+
+def test_text_path_names_and_errors(fc):
+    contigs = synth.random_contigs({"a": 150_000}, seed=3)
+    read = contigs["a"][1000:1400]
+    base = "\t".join(["007", "400", "0", "400", "+", "a", "150000", "1000", "1400", "400", "400", "60", "AS:i:400", "tp:A:P", "cg:Z:400M"])
+    cc = CoverageConverter({"a": 0})
+    # an all-digit read id is an int upstream and comes back as "7" (paf.py:54-56): the lookup uses the canonical text
+    got = cc.convert_text(base + "\n", {"7": read})
+    assert len(got) == 1 and got.cigar_bytes(0) == b"400M" and got.slice_bytes(0) == read.encode()
+    with pytest.raises(KeyError):
+        cc.convert_text(base, {"007": read})
+    pd, want = _via_objects(cc, base, {"7": read}, 1)
+    same_text(got, want)
+    assert len(cc.convert_text("", {})) == 0
+    for bad, exc in ((base.replace("\tcg:Z:400M", ""), AssertionError),           # no CIGAR (sequences.py:718)
+                     ("r\t400\t0\t400\t+\ta", IndexError),                         # fewer than 12 columns
+                     (base + "\n\n" + base, IndexError),                           # an empty line inside the text
+                     (base + "\tzz:Z:a:b", ValueError),                            # tag with an extra ':'
+                     (base + "\tzz:Q:1", KeyError),                                # unknown tag type
+                     (base.replace("AS:i:400", "AS:i:x"), ValueError),
+                     (base.replace("\t1000\t", "\tx\t"), ValueError)):
+        with pytest.raises(exc):
+            cc.convert_text(bad, {"7": read})
+        if exc is not AssertionError and exc is not ValueError:
+            with pytest.raises(exc):
+                parse_PAF(io.StringIO(bad))
+    # later duplicates of a tag win; '\r\n' line ends are stripped; the strand test is `!= '+'`
+    odd = base.replace("tp:A:P", "tp:A:S") + "\ttp:A:P\r\n" + base.replace("\t+\t", "\t-\t").replace("007", "r2") + "\n"
+    got = cc.convert_text(odd, {"7": read, "r2": read})
+    pd, want = _via_objects(cc, odd, {"7": read, "r2": read}, 1)
+    same_text(got, want)
+    assert list(got.rev) == [0, 1]
