@@ -219,7 +219,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
     if (tlen != PyUnicode_GET_LENGTH(text)) { PyErr_SetString(PyExc_ValueError, "PAF text must be ASCII"); return NULL; }
 
     Py_ssize_t n_lines = 0;
-    for (Py_ssize_t i = 0; i < tlen; ++i) n_lines += tp[i] == '\n';
+    for (const char* q = tp; (q = (const char*)memchr(q, '\n', (size_t)(tp + tlen - q))) != NULL; ++q) ++n_lines;
     if (tlen > 0 && tp[tlen - 1] != '\n') ++n_lines;
 
     rec_t* recs = (rec_t*)PyMem_Malloc(sizeof(rec_t) * (size_t)(n_lines ? n_lines : 1));
@@ -233,8 +233,8 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
 
     /* ---- pass 1: tokenise every line, filter, group by read ---- */
     for (Py_ssize_t pos = 0; pos < tlen;) {
-        Py_ssize_t e = pos;
-        while (e < tlen && tp[e] != '\n') ++e;
+        const char* nl = (const char*)memchr(tp + pos, '\n', (size_t)(tlen - pos));
+        const Py_ssize_t e = nl ? (Py_ssize_t)(nl - tp) : tlen;
         span_t line = {tp + pos, e - pos};
         pos = e + 1;
         line = strip_span(line);
@@ -246,16 +246,25 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
         r.next = -1;
         long long as = 0, blocklen = 0;
         int primary = 0;
-        for (;; ++i) {
-            if (i == line.n || line.p[i] == '\t') {
+        for (;;) {
+            {
+                const char* tb = (const char*)memchr(line.p + c0, '\t', (size_t)(line.n - c0));
+                i = tb ? (Py_ssize_t)(tb - line.p) : line.n;
                 span_t f = {line.p + c0, i - c0};
                 if (nc < 12) {
                     col[nc] = f;
                 } else {
                     /* key:type:value */
                     Py_ssize_t a = -1, b = -1, colons = 0;
-                    for (Py_ssize_t k = 0; k < f.n; ++k)
-                        if (f.p[k] == ':') { if (colons == 0) a = k; else if (colons == 1) b = k; ++colons; }
+                    const char* c1 = (const char*)memchr(f.p, ':', (size_t)f.n);
+                    if (c1) {
+                        a = c1 - f.p; colons = 1;
+                        const char* c2 = (const char*)memchr(c1 + 1, ':', (size_t)(f.n - a - 1));
+                        if (c2) {
+                            b = c2 - f.p; colons = 2;
+                            if (memchr(c2 + 1, ':', (size_t)(f.n - b - 1))) colons = 3;
+                        }
+                    }
                     if (colons != 2) {
                         PyErr_SetString(PyExc_ValueError, colons < 2 ? "not enough values to unpack (expected 3)" : "too many values to unpack (expected 3)");
                         goto done;
@@ -316,9 +325,11 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
     /* ---- pass 2: winner of every read -> the ten arrays ---- */
     {
         static const Py_ssize_t item[10] = {4, 8, 8, 4, 1, 8, 8, 8, 8, 8};
+        Py_ssize_t cap = 0;          /* entries the caller's buffers hold: len(seqs) always suffices (every used read is a key of seqs) */
         for (; got < 10; ++got) {
             if (PyObject_GetBuffer(PyTuple_GET_ITEM(bufs, got), &vb[got], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) goto done;
-            if (vb[got].len < n_grp * item[got]) { ++got; PyErr_SetString(PyExc_ValueError, "output buffer too small"); goto done; }
+            const Py_ssize_t c = vb[got].len / item[got];
+            if (got == 0 || c < cap) cap = c;
         }
         int32_t* o_contig = (int32_t*)vb[0].buf;   int64_t* o_tstart = (int64_t*)vb[1].buf;  int64_t* o_tend = (int64_t*)vb[2].buf;
         int32_t* o_bc = (int32_t*)vb[3].buf;       uint8_t* o_rev = (uint8_t*)vb[4].buf;     uint64_t* o_cp = (uint64_t*)vb[5].buf;
@@ -385,6 +396,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                 hi = clampll(r->qend, 0, len);
             }
             if (hi < lo) hi = lo;
+            if (n >= cap) { PyErr_SetString(PyExc_ValueError, "output buffer too small"); goto done; }
             o_contig[n] = (int32_t)ki; o_tstart[n] = r->tstart; o_tend[n] = r->tend; o_bc[n] = (int32_t)bc; o_rev[n] = (uint8_t)r->rev;
             o_cp[n] = (uint64_t)(uintptr_t)r->cigar.p; o_cl[n] = (int64_t)r->cigar.n;
             o_sp[n] = (uint64_t)(uintptr_t)sptr; o_sf[n] = lo; o_st[n] = hi;

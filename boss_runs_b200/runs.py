@@ -124,7 +124,7 @@ class CoverageConverter:
                     for r in recs:
                         r.barcode = barcodes.get(rid)
             return self.convert_records(pd, seqs)
-        n = paf_raw.count("\n") + 1
+        n = len(seqs) + 1                          # every read that is used is a key of `seqs`
         contig, bc = np.empty(n, np.int32), np.empty(n, np.int32)
         tstart, tend, cl, sf, st = (np.empty(n, np.int64) for _ in range(5))
         rev = np.empty(n, np.uint8)
