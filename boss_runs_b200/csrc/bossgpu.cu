@@ -1176,6 +1176,30 @@ extern "C" int bossgpu_ipc_close(int device, void* dev_ptr) {
     return 0;
 }
 
+// CUDA loads a kernel's code on its first launch (lazy module loading, the default since 12.2), and loading
+// synchronises the context. Inside a fused update that is fatal for shards sharing one context: the host would
+// block loading the next kernel while an exchange kernel of this shard spins for a peer whose work the host has not
+// enqueued yet. So every kernel an update can launch is loaded before the first exchange is ever enqueued.
+template <typename K>
+static int preload_kernel(K kernel, const char* name) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BOSSGPU_ECUDA, "loading %s failed: %s", name, cudaGetErrorString(e)); }
+    return 0;
+}
+#define PRELOAD(...) TRY(preload_kernel(__VA_ARGS__, #__VA_ARGS__))
+
+static int preload_update_kernels() {
+    PRELOAD(k_drop_thresholds); PRELOAD(k_rowflags); PRELOAD(k_buckets);
+    PRELOAD(k_score_bin<false>); PRELOAD(k_score_bin<true>);
+    PRELOAD(k_score_bin_tma<false, 2>); PRELOAD(k_score_bin_tma<false, 4>); PRELOAD(k_score_bin_tma<true, 2>);
+    PRELOAD(k_fhat_from_counts); PRELOAD(k_fhat_sum); PRELOAD(k_fhat_finish);
+    PRELOAD(k_smooth); PRELOAD(k_smooth_direct); PRELOAD(k_hist); PRELOAD(k_threshold); PRELOAD(k_pack_mask);
+    PRELOAD(k_distribute<true>); PRELOAD(k_distribute<false>);
+    PRELOAD(k_fabric_switch_halo); PRELOAD(k_fabric_norm); PRELOAD(k_fabric_hist); PRELOAD(k_fabric_mask_ready);
+    return 0;
+}
+
 extern "C" int bossgpu_fabric_attach(bossgpu_handle* h, int32_t n_shards, const uint64_t* peer_ptrs, double timeout_s) {
     H_CHECK(h);
     if (!h->d_fabric) return fail(BOSSGPU_ESTATE, "no exchange block: call bossgpu_set_shards first");
@@ -1194,6 +1218,7 @@ extern "C" int bossgpu_fabric_attach(bossgpu_handle* h, int32_t n_shards, const 
     BOSS_CUDA(cudaMemcpy(h->d_fab_mask_ptrs, mp.data(), sizeof(uint8_t*) * n_shards, cudaMemcpyHostToDevice));
     BOSS_CUDA(cudaMemset(h->d_fabric, 0, FL.o_sw));           // flags: no epoch seen yet
     if (timeout_s > 0) h->fabric_timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    TRY(preload_update_kernels());
     h->fabric_epoch = 0;
     h->fabric_attached = true;
     return 0;
@@ -1512,6 +1537,13 @@ extern "C" int bossgpu_host_register(void* host_ptr, int64_t bytes) {
     uintptr_t lo, hi;
     page_range(host_ptr, (size_t)bytes, &lo, &hi);       // shared-memory and malloc mappings cover whole pages
     cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        // a previous owner of these pages went away without unregistering them (the allocator reused the address)
+        cudaGetLastError();
+        cudaHostUnregister((void*)lo);
+        cudaGetLastError();
+        e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(BOSSGPU_ECUDA, "cudaHostRegister(%zu bytes) failed: %s", (size_t)(hi - lo), cudaGetErrorString(e));

@@ -599,6 +599,12 @@ class ShardedRun(BossRuns):
         for c, v in zip(self.contigs_filt.values(), self._global_views):
             c.strat = v
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self) -> None:
         for e in getattr(self, "engines", []):
             e.close()
