@@ -73,6 +73,10 @@ static int ensure_stage(bossgpu_handle* h, size_t bytes) {
     }
     if (bytes > h->stage_h_bytes) {
         if (h->stage_h) cudaFreeHost(h->stage_h);
+    if (h->pre_stage_h) cudaFreeHost(h->pre_stage_h);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_pre_thr) cudaEventDestroy(h->ev_pre_thr);
+    if (h->ev_pre_done) cudaEventDestroy(h->ev_pre_done);
         h->stage_h = nullptr; h->stage_h_bytes = 0;
         size_t want = bytes + bytes / 4;
         cudaError_t e = cudaMallocHost(&h->stage_h, want);
@@ -306,6 +310,26 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         }
         BOSS_CUDA(cudaMemcpy(h->d_tiles, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice));
     }
+    {   // split score/bin pass
+        std::vector<int32_t> soc((size_t)h->n_contigs_total, -1);
+        bool one_each = true;
+        for (int s = 0; s < h->n_seg; ++s) {
+            if (soc[h->segs[s].contig] >= 0) one_each = false;
+            soc[h->segs[s].contig] = s;
+        }
+        A(dev_alloc(&h->d_seg_of_contig, (size_t)h->n_contigs_total));
+        BOSS_CUDA(cudaMemcpy(h->d_seg_of_contig, soc.data(), sizeof(int32_t) * soc.size(), cudaMemcpyHostToDevice));
+        A(dev_alloc(&h->d_touched, (size_t)(tiles / 32 + 2)));
+        A(dev_alloc(&h->d_touched_list, (size_t)tiles + 1));
+        A(dev_alloc(&h->d_pre_misc, 2));
+        A(dev_alloc(&h->d_pre_cov_add, (size_t)h->n_contigs_total));
+        BOSS_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_thr, cudaEventDisableTiming));
+        BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_done, cudaEventDisableTiming));
+        h->prescore_ok = one_each && h->nb == 1 && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
+        BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
+        BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
+    }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
     BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 4)));
@@ -338,7 +362,8 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
                     h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
                     h->d_hist, h->d_strat_alloc, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
                     h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts,
-                    h->d_mask_ptrs, h->d_fabric, h->d_peer_ptrs, h->d_fab_mask_ptrs};
+                    h->d_mask_ptrs, h->d_fabric, h->d_peer_ptrs, h->d_fab_mask_ptrs, h->d_seg_of_contig, h->d_touched,
+                    h->d_touched_list, h->d_pre_misc, h->d_pre_cov_add, h->pre_stage_d};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
@@ -347,6 +372,10 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
     if (h->h_seg_accept) cudaFreeHost(h->h_seg_accept);
     if (h->h_bucket_sw) cudaFreeHost(h->h_bucket_sw);
     if (h->stage_h) cudaFreeHost(h->stage_h);
+    if (h->pre_stage_h) cudaFreeHost(h->pre_stage_h);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_pre_thr) cudaEventDestroy(h->ev_pre_thr);
+    if (h->ev_pre_done) cudaEventDestroy(h->ev_pre_done);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     delete h;
     return 0;
@@ -397,6 +426,25 @@ static int add_contig_totals(bossgpu_handle* h, const int64_t* contig_cov_add) {
     return 0;
 }
 
+static uint64_t batch_hash(int64_t n, const int32_t* contig, const int64_t* tstart, const int64_t* tend) {
+    uint64_t hsh = 0x9E3779B97F4A7C15ull;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t t0 = (uint64_t)std::min(tstart[i], tend[i]), t1 = (uint64_t)std::max(tstart[i], tend[i]);
+        hsh = (hsh ^ ((uint64_t)(uint32_t)contig[i] + (t0 << 20) + (t1 << 42) + (t1 >> 22))) * 0x100000001B3ull;
+        hsh ^= hsh >> 29;
+    }
+    return hsh;
+}
+
+// any ingest other than the announced text batch invalidates an early score pass (the update redoes every tile)
+static int prescore_invalidate(bossgpu_handle* h) {
+    if (h->prescore_state == 1 || h->prescore_state == 2) {
+        BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_thr, 0));
+        h->prescore_state = -1;
+    }
+    return 0;
+}
+
 static int check_ingest_error(bossgpu_handle* h) {
     BOSS_CUDA(cudaMemcpyAsync(h->h_ingest_err, h->d_ingest_err, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
@@ -418,6 +466,7 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
                                      const int64_t* contig_cov_add) {
     H_CHECK(h);
     if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
+    TRY(prescore_invalidate(h));
     if (contig_cov_add) {
         if (on_device) {
             k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
@@ -511,6 +560,13 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         const SegDev& S = h->segs[sg];
         if (t1 <= S.start || t0 >= S.start + S.len) continue;
         sel.push_back(i);
+    }
+    if (h->prescore_state == 1) {
+        // the early score pass was announced this batch? Same reads, same intervals -> its thresholds and its set of
+        // touched tiles hold. The totals it read must not move before it has read them.
+        h->prescore_state = (n_all == h->pre_n_reads && cov_add == h->pre_cov_add &&
+                             batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
+        BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_thr, 0));
     }
     const int64_t n_reads = (int64_t)sel.size();
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -690,6 +746,7 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
                            (const int64_t*)(ds + o_bo), nullptr, (const uint8_t*)(ds + o_rv), /*ascii=*/1,
                            /*count_totals=*/false, /*check_spans=*/false, pk, /*record_begin=*/false));
     int rc = check_ingest_error(h);       // synchronises: exc_blob, the staging buffer and the scratch are free again
+    if (rc != 0 && h->prescore_state == 2) h->prescore_state = -1;    // a rejected batch adds nothing to the totals
     h->last_ingest_h2d = (int64_t)(small_bytes + (size_t)total_text + (size_t)total_packed + exc_blob.size());
     if (trace)
         fprintf(stderr, "[bossgpu] ingest %lld of %lld reads, %d threads x %d groups (hw %u): layout %.2f ms, copy+pack (h2d overlapped) %.2f, tokenise + scatter on the GPU %.2f; %zu B staged\n",
@@ -750,19 +807,58 @@ static int validate_params(const bossgpu_update_params* p) {
 #define EV_BEGIN(i) BOSS_CUDA(cudaEventRecord(h->ev[2 * (i)], h->stream))
 #define EV_END(i)   do { BOSS_CUDA(cudaEventRecord(h->ev[2 * (i) + 1], h->stream)); h->ev_valid[i] = true; } while (0)
 
-static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
-    // reset per-update device scalars (keeps `error`)
-    BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
-    BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
-    k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
-        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr);
-    BOSS_KERNEL_CHECK();
-    h->launches++;
+static int ensure_pre_stage(bossgpu_handle* h, size_t want) {
+    if (h->pre_stage_bytes >= want) return 0;
+    want = want * 2 + 4096;
+    if (h->pre_stage_h) cudaFreeHost(h->pre_stage_h);
+    if (h->pre_stage_d) cudaFree(h->pre_stage_d);
+    h->pre_stage_h = nullptr; h->pre_stage_d = nullptr; h->pre_stage_bytes = 0;
+    if (cudaMallocHost(&h->pre_stage_h, want) != cudaSuccess || cudaMalloc(&h->pre_stage_d, want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BOSSGPU_ENOMEM, "staging for the early score pass (%zu bytes)", want);
+    }
+    h->pre_stage_bytes = want;
+    return 0;
+}
+
+static ScoreArgs score_args(bossgpu_handle* h) {
     ScoreArgs a;
     a.tiles = (const TileDesc*)h->d_tiles; a.nb = h->nb; a.P = h->P;
     a.ref = h->d_ref; a.cov = h->d_cov; a.rowflag = h->d_rowflag; a.table = h->d_table; a.drop_thr = h->d_drop_thr;
     a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
     a.n_dropout = &h->d_upd->n_dropout;
+    return a;
+}
+
+static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
+    // an early pass over the untouched tiles may be in flight on stream2 (bossgpu_prescore)
+    const int pre = h->prescore_state;
+    const bool split = pre == 2 || (pre == 1 && h->pre_n_reads == 0);
+    h->prescore_state = 0;
+    if (pre != 0) BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_done, 0));
+    // reset per-update device scalars (keeps `error`)
+    BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
+    ScoreArgs a = score_args(h);
+    if (split) {
+        // bucket sums, bins and the dropout count of every untouched tile are in place; thresholds were formed from
+        // the same totals (the ingest confirmed the batch's spans): add the early pass' dropout count and score the
+        // tiles the batch wrote to
+        k_add_u64<<<1, 32, 0, h->stream>>>(&h->d_upd->n_dropout, h->d_pre_misc + 1, 1);
+        BOSS_KERNEL_CHECK();
+        a.tile_list = h->d_touched_list;
+        a.list_n = reinterpret_cast<const unsigned*>(h->d_pre_misc);
+        EV_BEGIN(1);
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+        k_score_bin_tma<false, 2, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+        BOSS_KERNEL_CHECK();
+        EV_END(1);
+        h->launches += 2;
+    } else {
+    BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
+    k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
+        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
     EV_BEGIN(1);
     if (h->nb > 1) {
         k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
@@ -782,6 +878,7 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     h->launches++;
     BOSS_KERNEL_CHECK();
     EV_END(1);
+    }
     EV_BEGIN(2);
     int64_t max_sw = 0;
     for (auto& S : h->segs) max_sw = std::max(max_sw, S.n_sw);
@@ -791,6 +888,65 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     BOSS_KERNEL_CHECK();
     h->launches++;
     EV_END(2);
+    return 0;
+}
+
+// The early half of a split score/bin pass. Called with the batch's alignment intervals as soon as they are known
+// (before the reads are packed and copied): every tile the batch will NOT write to is scored right away on a second
+// stream, with the dropout thresholds the update will see (depth totals + the batch's reference span, the same
+// numbers the ingest adds), while the host is still busy with the batch. The update then scores only the touched
+// tiles. Every tile is still scored once per update from the counters — nothing is carried over between updates.
+// If the batch that is then ingested differs from the announced one, the update falls back to the whole pass.
+extern "C" int bossgpu_prescore(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+                                const int64_t* tend) {
+    H_CHECK(h);
+    if (n_reads < 0 || (n_reads > 0 && (!contig || !tstart || !tend))) return fail(BOSSGPU_EINVAL, "bad batch arrays");
+    if (h->prescore_state != 0) {            // an earlier announcement was never consumed: let it drain, start over
+        BOSS_CUDA(cudaStreamSynchronize(h->stream2));
+        h->prescore_state = 0;
+    }
+    if (!h->prescore_ok || h->score_kernel_ldg || h->score_stages != 2 || h->fused_open) return 0;
+    h->pre_cov_add.assign((size_t)h->n_contigs_total, 0ull);
+    const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
+    const size_t o_t0 = round_up(sizeof(int32_t) * nr, 16), o_t1 = o_t0 + sizeof(int64_t) * nr, total = o_t1 + sizeof(int64_t) * nr;
+    TRY(ensure_pre_stage(h, total));
+    char* hs = (char*)h->pre_stage_h;
+    int32_t* s_c = (int32_t*)hs; int64_t* s_t0 = (int64_t*)(hs + o_t0); int64_t* s_t1 = (int64_t*)(hs + o_t1);
+    for (int64_t i = 0; i < n_reads; ++i) {
+        if (contig[i] < 0 || contig[i] >= h->n_contigs_total) return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
+        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
+        h->pre_cov_add[contig[i]] += (unsigned long long)(t1 - t0);
+        s_c[i] = contig[i]; s_t0[i] = t0; s_t1[i] = t1;
+    }
+    cudaStream_t st = h->stream2;
+    BOSS_CUDA(cudaMemsetAsync(h->d_touched, 0, sizeof(uint32_t) * (size_t)(h->n_tiles / 32 + 2), st));
+    BOSS_CUDA(cudaMemsetAsync(h->d_pre_misc, 0, sizeof(unsigned long long) * 2, st));
+    BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, st));
+    BOSS_CUDA(cudaMemcpyAsync(h->d_pre_cov_add, h->pre_cov_add.data(), sizeof(unsigned long long) * h->n_contigs_total,
+                              cudaMemcpyHostToDevice, st));
+    k_drop_thresholds_pred<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, st>>>(
+        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_pre_cov_add, h->d_drop_thr);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaEventRecord(h->ev_pre_thr, st));       // the ingest may add to the totals after this point
+    if (n_reads > 0) {
+        BOSS_CUDA(cudaMemcpyAsync(h->pre_stage_d, hs, total, cudaMemcpyHostToDevice, st));
+        const char* ds = (const char*)h->pre_stage_d;
+        k_mark_tiles<<<(unsigned)ceil_div(n_reads, 128), 128, 0, st>>>(
+            n_reads, (const int32_t*)ds, (const int64_t*)(ds + o_t0), (const int64_t*)(ds + o_t1), h->d_seg_of_contig, h->d_segs,
+            h->d_touched, h->d_touched_list, reinterpret_cast<unsigned*>(h->d_pre_misc));
+        BOSS_KERNEL_CHECK();
+    }
+    ScoreArgs a = score_args(h);
+    a.touched = h->d_touched;
+    a.n_dropout = h->d_pre_misc + 1;
+    dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+    k_score_bin_tma<false, 2, 1><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), st>>>(a, h->n_tiles);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaEventRecord(h->ev_pre_done, st));
+    h->launches += 3;
+    h->pre_n_reads = n_reads;
+    h->pre_hash = batch_hash(n_reads, contig, tstart, tend);
+    h->prescore_state = 1;
     return 0;
 }
 
@@ -1193,6 +1349,8 @@ static int preload_update_kernels() {
     PRELOAD(k_drop_thresholds); PRELOAD(k_rowflags); PRELOAD(k_buckets);
     PRELOAD(k_score_bin<false>); PRELOAD(k_score_bin<true>);
     PRELOAD(k_score_bin_tma<false, 2>); PRELOAD(k_score_bin_tma<false, 4>); PRELOAD(k_score_bin_tma<true, 2>);
+    PRELOAD(k_score_bin_tma<false, 2, 1>); PRELOAD(k_score_bin_tma<false, 2, 2>); PRELOAD(k_mark_tiles);
+    PRELOAD(k_drop_thresholds_pred); PRELOAD(k_add_u64);
     PRELOAD(k_fhat_from_counts); PRELOAD(k_fhat_sum); PRELOAD(k_fhat_finish);
     PRELOAD(k_smooth); PRELOAD(k_smooth_direct); PRELOAD(k_hist); PRELOAD(k_threshold); PRELOAD(k_pack_mask);
     PRELOAD(k_distribute<true>); PRELOAD(k_distribute<false>);
@@ -1351,6 +1509,7 @@ extern "C" int bossgpu_get_coverage(bossgpu_handle* h, int32_t seg, uint16_t* ou
 
 extern "C" int bossgpu_set_coverage(bossgpu_handle* h, int32_t seg, const uint16_t* in, int64_t in_elems) {
     H_CHECK(h);
+    TRY(prescore_invalidate(h));
     SEG_CHECK(h, seg);
     const SegDev& S = h->segs[seg];
     int64_t n = S.len * 5 * h->nb;

@@ -201,5 +201,20 @@ struct bossgpu_handle {
     double*  d_halo = nullptr;               // [send L | send R | recv L | recv R] x halo_bins x nb
     bool have_fhat = false;
     bool debug_bufs = false;
+    // split score/bin pass (bossgpu_prescore): tiles the coming batch does not touch are scored on `stream2` while the
+    // host is still packing the batch; the update then only scores the touched tiles
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_pre_thr = nullptr, ev_pre_done = nullptr;
+    int  prescore_state = 0;                 // 0 none, 1 enqueued, 2 confirmed by the ingest, -1 batch differs: redo everything
+    bool prescore_ok = false;                // geometry allows it (one segment per contig, no barcodes, staged kernel)
+    int64_t pre_n_reads = 0;
+    uint64_t pre_hash = 0;
+    std::vector<unsigned long long> pre_cov_add;
+    int32_t*  d_seg_of_contig = nullptr;     // [n_contigs_total] local segment of a contig, -1 if none
+    uint32_t* d_touched = nullptr;           // bitmap over tile ids
+    int32_t*  d_touched_list = nullptr;      // [n_tiles]
+    unsigned long long* d_pre_misc = nullptr; // [0] list length (low 32 bits used), [1] dropout rows seen by the early pass
+    unsigned long long* d_pre_cov_add = nullptr; // [n_contigs_total]
+    void* pre_stage_h = nullptr; void* pre_stage_d = nullptr; size_t pre_stage_bytes = 0;
     boss::UpdateDev last;
 };

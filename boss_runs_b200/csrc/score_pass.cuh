@@ -46,6 +46,10 @@ struct ScoreArgs {
     int64_t ds_len;
     unsigned long long* bucket_sum;  // [n_sw][nb]
     unsigned long long* n_dropout;
+    // split pass (k_score_bin_tma MODE 1 / 2, see bossgpu_prescore): tiles the coming batch touches
+    const uint32_t* touched = nullptr;   // bitmap over tile ids
+    const int32_t* tile_list = nullptr;  // the same tiles as a list, in no particular order
+    const unsigned* list_n = nullptr;
 };
 
 constexpr int ROW_TINY = NPAT;       // depth >= 30: frozen site            (sequences.py:419-420,430)
@@ -261,7 +265,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SBT_CONSUMERS) : "memory"); }
 
-template <bool MULTI, int SBT_STAGES>
+// MODE 0: every tile. MODE 1: every tile whose bit in a.touched is clear. MODE 2: the tiles of a.tile_list.
+// Producer and consumers walk the same sequence and skip the same entries, so the stage counters stay in step.
+template <bool MULTI, int SBT_STAGES, int MODE = 0>
 __global__ void __launch_bounds__(SBT_THREADS, 3)
 k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -297,7 +303,10 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
         if (t == SBT_CONSUMERS) {
             const uint16_t* plane0 = a.cov + (size_t)b * 5 * a.P;
             int it = 0;
-            for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+            const int64_t n_iter = MODE == 2 ? (int64_t)*a.list_n : n_tiles;
+            for (int64_t idx = first; idx < n_iter; idx += stride) {
+                const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
+                if (MODE == 1 && ((a.touched[tile >> 5] >> (tile & 31)) & 1u)) continue;
                 const int stage = it % SBT_STAGES;
                 const uint32_t full = smem_u32(&s_bar[stage]), empty = smem_u32(&s_bar[SBT_STAGES + stage]);
                 if (it >= SBT_STAGES) mbar_wait(empty, ((it / SBT_STAGES) - 1) & 1);
@@ -310,6 +319,7 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
                     bulk_g2s(dst + k * SBT_PLANE_BYTES, plane0 + (size_t)k * a.P + td.site_off, SBT_PLANE_BYTES, full);
                 bulk_g2s(dst + SBT_REF_OFF, a.ref + td.site_off, TILE, full);
                 if (MULTI) bulk_g2s(dst + SBT_FLAG_OFF, a.rowflag + td.site_off, TILE * 4, full);
+                ++it;
             }
         }
         return;
@@ -317,7 +327,9 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
 
     // ----------------------------------- consumers -----------------------------------
     int it = 0, buf = 0;
-    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it, buf ^= 1) {
+    const int64_t n_iter = MODE == 2 ? (int64_t)*a.list_n : n_tiles;
+    for (int64_t idx = first; idx < n_iter; idx += stride) {
+        if (MODE == 1 && ((a.touched[idx >> 5] >> (idx & 31)) & 1u)) continue;
         const int stage = it % SBT_STAGES;
         mbar_wait(smem_u32(&s_bar[stage]), (it / SBT_STAGES) & 1);
         const TileDesc td = s_td[stage];
@@ -432,7 +444,39 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
             if (td.bucket >= 0 && cov) atomicAdd(&a.bucket_sum[(size_t)td.bucket * a.nb + b], (unsigned long long)cov);
             if (dr && b == 0) atomicAdd(a.n_dropout, (unsigned long long)dr);
         }
+        ++it;
+        buf ^= 1;
     }
+}
+
+// Tiles the coming batch will write to: one thread per read marks the tiles its reference interval overlaps in its
+// contig's segment of this shard (the same clipping the scatter applies) and appends newly marked tiles to a list.
+__global__ void k_mark_tiles(int64_t n_reads, const int32_t* __restrict__ contig, const int64_t* __restrict__ t0s,
+                             const int64_t* __restrict__ t1s, const int32_t* __restrict__ seg_of_contig,
+                             const SegDev* __restrict__ segs, uint32_t* __restrict__ touched, int32_t* __restrict__ list,
+                             unsigned* __restrict__ list_n) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int32_t sg = seg_of_contig[contig[r]];
+    if (sg < 0) return;
+    const SegDev S = segs[sg];
+    const int64_t lo = max(t0s[r], S.start) - S.start, hi = min(t1s[r], S.start + S.len) - S.start;   // [lo, hi)
+    if (hi <= lo) return;
+    for (int64_t tile = S.tile_off + lo / TILE; tile <= S.tile_off + (hi - 1) / TILE; ++tile) {
+        const uint32_t bit = 1u << (tile & 31);
+        const uint32_t old = atomicOr(&touched[tile >> 5], bit);
+        if (!(old & bit)) list[atomicAdd(list_n, 1u)] = (int32_t)tile;
+    }
+}
+
+// dropout thresholds the update WILL see: depth totals + the reference span of the batch about to be ingested
+__global__ void k_drop_thresholds_pred(int n_contigs, const int64_t* __restrict__ contig_len, int nb,
+                                       const unsigned long long* __restrict__ cov_total,
+                                       const unsigned long long* __restrict__ cov_add, int32_t* __restrict__ thr) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_contigs) return;
+    double mean = (double)(cov_total[k] + cov_add[k]) / (double)(contig_len[k] * (int64_t)nb);
+    thr[k] = mean > 5.0 ? (int32_t)(mean / 8.0) : -1;
 }
 
 constexpr size_t sbt_smem_bytes(bool multi, int SBT_STAGES) {

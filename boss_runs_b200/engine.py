@@ -173,6 +173,12 @@ class Engine:
                                                   ptr(rev), ptr(cigar_ptr), ptr(cigar_len), ptr(seq_ptr), ptr(seq_from),
                                                   ptr(seq_to), int(n_threads)))
 
+    def prescore(self, contig, tstart, tend) -> None:
+        """Announce the coming batch's alignment intervals: tiles it does not touch are scored right away on a
+        second stream while the host packs the batch (`bossgpu_prescore`); results do not depend on it."""
+        contig = as_c(contig, np.int32); tstart = as_c(tstart, np.int64); tend = as_c(tend, np.int64)
+        check(self.lib.bossgpu_prescore(self.h, len(contig), ptr(contig), ptr(tstart), ptr(tend)))
+
     def read_starts_add(self, window, strand) -> None:
         window = as_c(window, np.int64); strand = as_c(strand, np.uint8)
         assert len(window) == len(strand)

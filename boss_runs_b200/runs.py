@@ -454,6 +454,7 @@ class BossRuns:
         is the subset that feeds the read-start distribution — the simulator passes accepted reads only
         (simulation.py:171)."""
         increments = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
+        self._prescore(increments)
         self._effect_increments(increments=increments)
         self.count_read_starts(paf_dict if paf_dict_starts is None else paf_dict_starts)
         self.update_wrapper()
@@ -466,6 +467,7 @@ class BossRuns:
         tokenised once in C, the winning record of every read goes to the GPU, and the read starts are counted from
         the same arrays. `min_len` = mu/2 as `Mapper.map_sequences` passes it (mapper.py:64)."""
         b = self.cc.convert_text(paf_raw, seqs, min_len=min_len, barcodes=barcodes)
+        self._prescore(b)
         self._effect_increments(increments=b)
         wins, strands = self.read_starts.count_read_starts_arrays(b.contig, b.tstart, b.tend, b.rev)
         self._read_starts_to_device(wins, strands)
@@ -474,6 +476,19 @@ class BossRuns:
 
     def _read_starts_to_device(self, wins, strands) -> None:
         self.engine.read_starts_add(wins, strands)
+
+    use_prescore = True
+
+    def _engines(self):
+        return getattr(self, "engines", None) or [self.engine]
+
+    def _prescore(self, b: PackedBatch) -> None:
+        """The GPU starts scoring every tile the batch will not touch while the host packs the batch (split score/bin
+        pass, `bossgpu_prescore`); only done when an update is certain to follow, i.e. from `process_batch_*`."""
+        if self.use_prescore:
+            for e in self._engines():
+                if hasattr(e, "prescore"):
+                    e.prescore(b.contig, b.tstart, b.tend)
 
     # -- device-resident variants (bench.py `value` leg, pipelined callers) ----------------------------
     def local_sites(self) -> int:

@@ -172,3 +172,44 @@ def test_text_batches_equal_object_batches(lib):
             assert np.array_equal(run_obj.contigs[name].coverage, run_txt.contigs[name].coverage)
             assert np.array_equal(run_obj.contigs[name].strat, run_txt.contigs[name].strat)
         H.compare_state(run_txt, orc, True, f"text/b{b}")
+
+
+def test_split_score_pass_is_invisible(lib):
+    """`process_batch_*` announce the batch before ingesting it, so the tiles it will not touch are scored while the
+    host packs the reads (bossgpu_prescore). Every number must equal the run that scores all tiles after the scatter:
+    bins, dropout counts, switches, thresholds, masks — also after a batch was rejected half-way and after updates
+    that came without an announcement."""
+    lens = {"a": 260_000, "b": 141_000, "c": 100_000}
+    contigs, split = make_run(lens, bucket_threshold=4)
+    _, whole = make_run(lens, bucket_threshold=4)
+    whole.use_prescore = False
+    ref = contigs["a"]
+    bad_read = ref[7000:7050] + "N" + ref[7051:7100]
+    bad = parse_PAF(io.StringIO(paf_line("bad", bad_read, 0, 100, "+", "a", 260_000, 7000, 7100, "100M")))
+    for b in range(5):
+        rb = synth.read_batch(contigs, n_reads=500, seed=900 + b, mean_len=2500.0, min_len=300, max_len=9000,
+                              focus=("a", 30_000, 33_000, 0.15))
+        pd = parse_PAF(io.StringIO(rb.paf_text))
+        lens_b = {rid: recs[0].qlen for rid, recs in pd.items()}
+        if b == 2:                                                   # announced, then rejected by the scatter (IndexError upstream)
+            for run in (split, whole):
+                with pytest.raises(IndexError):
+                    run.process_batch_runs(bad, {"bad": bad_read})
+        for run in (split, whole):
+            run.rl_dist.update(lens_b)
+            if b == 3:                                               # the text entry point announces too
+                run.process_batch_text(rb.paf_text, rb.seqs, min_len=1)
+            else:
+                run.process_batch_runs(pd, rb.seqs)
+        if b == 1:                                                   # an update nobody announced
+            for run in (split, whole):
+                run.update_wrapper()
+        assert split.last.switched_on == whole.last.switched_on
+        assert (split.threshold, split.last.ubar0, split.last.n_nonzero, split.last.n_dropout, split.last.n_accept) == \
+               (whole.threshold, whole.last.ubar0, whole.last.n_nonzero, whole.last.n_dropout, whole.last.n_accept), f"batch {b}"
+        for name in lens:
+            s, w = split.contigs[name], whole.contigs[name]
+            assert np.array_equal(s.coverage, w.coverage) and np.array_equal(s.bucket_switches, w.bucket_switches)
+            assert np.array_equal(s.scores_ds, w.scores_ds), f"batch {b}/{name}: bins differ"
+            assert np.array_equal(s.strat, w.strat), f"batch {b}/{name}: masks differ"
+    assert split.last.n_dropout > 0 and (split.contigs["a"].coverage.sum(axis=1) >= 30).any()
