@@ -73,10 +73,6 @@ static int ensure_stage(bossgpu_handle* h, size_t bytes) {
     }
     if (bytes > h->stage_h_bytes) {
         if (h->stage_h) cudaFreeHost(h->stage_h);
-    if (h->pre_stage_h) cudaFreeHost(h->pre_stage_h);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
-    if (h->ev_pre_thr) cudaEventDestroy(h->ev_pre_thr);
-    if (h->ev_pre_done) cudaEventDestroy(h->ev_pre_done);
         h->stage_h = nullptr; h->stage_h_bytes = 0;
         size_t want = bytes + bytes / 4;
         cudaError_t e = cudaMallocHost(&h->stage_h, want);

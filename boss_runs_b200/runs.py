@@ -327,7 +327,10 @@ class BossRuns:
     def __init__(self, ref: str | None = None, contigs=None, ploidy: int = 1, barcodes: list[str] | None = None,
                  reject_refs: str | None = None, bucket_threshold: float = 5, out_dir: str | None = None,
                  device: int = 0, stream: int | None = None, strict_upstream_asserts: bool = True,
-                 write_debug: bool = False):
+                 write_debug: bool = False, strategy_format: str = "npz"):
+        if strategy_format not in ("npz", "bits", "both"):
+            raise ValueError("strategy_format must be 'npz' (upstream's file, default), 'bits' or 'both'")
+        self.strategy_format = strategy_format
         if not barcodes:
             self.barcodes_index = {"": 0}
         else:
@@ -374,9 +377,24 @@ class BossRuns:
     def _write_contig_strategies(self, contig_strats: dict[str, np.ndarray]) -> None:
         if self.out_dir is None:
             return
-        tmp = f"{self.out_dir}/masks/boss_tmp.npz"
-        np.savez(tmp, **contig_strats)
-        Path(tmp).rename(f"{self.out_dir}/masks/boss.npz")
+        if self.strategy_format in ("npz", "both"):
+            tmp = f"{self.out_dir}/masks/boss_tmp.npz"
+            np.savez(tmp, **contig_strats)
+            Path(tmp).rename(f"{self.out_dir}/masks/boss.npz")
+        if self.strategy_format in ("bits", "both"):
+            self._write_packed_strategies()
+
+    def _write_packed_strategies(self) -> None:
+        """The same masks as `boss.bits` (stratfile.py): 1 bit per entry, packed on the GPU when one engine holds the
+        genome, from the host mirror otherwise."""
+        from . import stratfile
+        tracked = [(n, c.length // BIN) for n, c in self.contigs_filt.items()]
+        if getattr(self, "engines", None) is None and self._strat_views is not None:
+            packed = self.engine.strat_packed()
+        else:
+            packed = stratfile.pack_strategies([c.strat for c in self.contigs_filt.values()])
+        stratfile.write_bits(f"{self.out_dir}/masks/boss.bits", tracked, self.nbarcodes, packed,
+                             rejected=[n for n, c in self.contigs.items() if c.rej])
 
     # -- coverage (core.py:77-86) ----------------------------------------------------------------------
     def _effect_increments(self, increments: PackedBatch) -> None:

@@ -213,3 +213,37 @@ def test_split_score_pass_is_invisible(lib):
             assert np.array_equal(s.scores_ds, w.scores_ds), f"batch {b}/{name}: bins differ"
             assert np.array_equal(s.strat, w.strat), f"batch {b}/{name}: masks differ"
     assert split.last.n_dropout > 0 and (split.contigs["a"].coverage.sum(axis=1) >= 30).any()
+
+
+def test_packed_strategy_file_matches_npz(lib, tmp_path):
+    """`strategy_format="both"`: boss.bits (packed on the GPU) and upstream's boss.npz describe the same masks, for a
+    reference with a reject ref and barcodes, before the first update and after every update."""
+    from boss_runs_b200 import stratfile
+    from boss_runs_b200.runs import BossRuns
+    contigs = synth.random_contigs({"a": 180_000, "rej": 120_000, "b": 130_000}, seed=8)
+    barcodes = ["barcode01", "barcode02"]
+    run = BossRuns(contigs=contigs, bucket_threshold=0, barcodes=barcodes, reject_refs="rej", out_dir=str(tmp_path),
+                   strategy_format="both")
+    sb = stratfile.StrategyBits(tmp_path / "masks", barcodes=barcodes)
+
+    def same():
+        assert sb.reload() in (0, 1)
+        npz = np.load(tmp_path / "masks" / "boss.npz")
+        bits = sb.as_dict()
+        assert set(npz.files) == set(bits) == {"a", "rej", "b"}
+        for name in npz.files:
+            assert np.array_equal(npz[name], bits[name]), name
+        assert sb.check_coord("rej", 500, False, "barcode01") == 0
+    same()
+    tracked = {n: s for n, s in contigs.items() if n != "rej"}
+    for b in range(3):
+        rb = synth.read_batch(tracked, n_reads=400, seed=40 + b, mean_len=2500.0, min_len=300, max_len=9000, n_barcodes=2)
+        pd = H.parse_batch(rb.paf_text, rb.barcodes, True)
+        run.rl_dist.update({rid: recs[0].qlen for rid, recs in pd.items()})
+        run.process_batch_runs(pd, rb.seqs)
+        os_mtime = (tmp_path / "masks" / "boss.bits").stat().st_mtime
+        sb.last_mask_mtime = 0.0                                    # force the reload whatever the clock's granularity
+        same()
+        assert not run.contigs["a"].strat.all(), "the update should have rejected something"
+        for pos, rev, bc in ((0, False, "barcode01"), (90_050, True, "barcode02"), (179_999, False, "barcode02")):
+            assert sb.check_coord("a", pos, rev, bc) == int(run.contigs["a"].strat[pos // 100, int(rev), int(bc[-1]) - 1])
