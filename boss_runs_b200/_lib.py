@@ -71,6 +71,7 @@ SYMBOLS = {
     "bossgpu_synchronize": (C.c_int, [_P]),
     "bossgpu_ingest_packed": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bossgpu_ingest_records": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
+    "bossgpu_prescore_begin": (C.c_int, [_P]),
     "bossgpu_prescore": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     "bossgpu_ingest_records_ptr": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
     "bossgpu_strat_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -318,12 +318,13 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         A(dev_alloc(&h->d_touched, (size_t)(tiles / 32 + 2)));
         A(dev_alloc(&h->d_touched_list, (size_t)tiles + 1));
         A(dev_alloc(&h->d_pre_misc, 2));
-        A(dev_alloc(&h->d_pre_cov_add, (size_t)h->n_contigs_total));
+        A(dev_alloc(&h->d_drop_thr_spec, (size_t)h->n_contigs_total));
+        A(dev_alloc(&h->d_tile_cov, (size_t)(tiles + 1) * h->nb));
+        A(dev_alloc(&h->d_tile_drop, (size_t)tiles + 1));
         BOSS_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_thr, cudaEventDisableTiming));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_done, cudaEventDisableTiming));
         h->prescore_ok = one_each && h->nb == 1 && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
-        BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
         BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
     }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -359,7 +360,7 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
                     h->d_hist, h->d_strat_alloc, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
                     h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts,
                     h->d_mask_ptrs, h->d_fabric, h->d_peer_ptrs, h->d_fab_mask_ptrs, h->d_seg_of_contig, h->d_touched,
-                    h->d_touched_list, h->d_pre_misc, h->d_pre_cov_add, h->pre_stage_d};
+                    h->d_touched_list, h->d_pre_misc, h->d_drop_thr_spec, h->d_tile_cov, h->d_tile_drop, h->pre_stage_d};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
@@ -432,12 +433,16 @@ static uint64_t batch_hash(int64_t n, const int32_t* contig, const int64_t* tsta
     return hsh;
 }
 
-// any ingest other than the announced text batch invalidates an early score pass (the update redoes every tile)
+// The totals the early pass formed its thresholds from must not move before it has read them.
+static int spec_order_totals(bossgpu_handle* h) {
+    if (h->spec_state == 1) BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_thr, 0));
+    return 0;
+}
+
+// any ingest other than the announced text batch voids the announcement (the update then scores every tile again)
 static int prescore_invalidate(bossgpu_handle* h) {
-    if (h->prescore_state == 1 || h->prescore_state == 2) {
-        BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_thr, 0));
-        h->prescore_state = -1;
-    }
+    TRY(spec_order_totals(h));
+    if (h->prescore_state == 1 || h->prescore_state == 2) h->prescore_state = -1;
     return 0;
 }
 
@@ -557,13 +562,9 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         if (t1 <= S.start || t0 >= S.start + S.len) continue;
         sel.push_back(i);
     }
-    if (h->prescore_state == 1) {
-        // the early score pass was announced this batch? Same reads, same intervals -> its thresholds and its set of
-        // touched tiles hold. The totals it read must not move before it has read them.
-        h->prescore_state = (n_all == h->pre_n_reads && cov_add == h->pre_cov_add &&
-                             batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
-        BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_thr, 0));
-    }
+    TRY(spec_order_totals(h));
+    if (h->prescore_state == 1)       // is this the batch that was announced? Same reads, same intervals -> its tile marks hold
+        h->prescore_state = (n_all == h->pre_n_reads && batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
     const int64_t n_reads = (int64_t)sel.size();
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(hw > 2 ? hw - 1 : hw, 32u);   // one thread keeps issuing copies
@@ -821,60 +822,64 @@ static ScoreArgs score_args(bossgpu_handle* h) {
     ScoreArgs a;
     a.tiles = (const TileDesc*)h->d_tiles; a.nb = h->nb; a.P = h->P;
     a.ref = h->d_ref; a.cov = h->d_cov; a.rowflag = h->d_rowflag; a.table = h->d_table; a.drop_thr = h->d_drop_thr;
-    a.ds = h->d_ds; a.ds_len = h->ds_len; a.bucket_sum = h->d_bucket_sum;
-    a.n_dropout = &h->d_upd->n_dropout;
+    a.ds = h->d_ds; a.ds_len = h->ds_len; a.tile_cov = h->d_tile_cov; a.tile_drop = h->d_tile_drop;
     return a;
 }
 
 static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
-    // an early pass over the untouched tiles may be in flight on stream2 (bossgpu_prescore)
-    const int pre = h->prescore_state;
-    const bool split = pre == 2 || (pre == 1 && h->pre_n_reads == 0);
+    // An early pass over every tile may be in flight on stream2 (bossgpu_prescore_begin). If the batch that was ingested
+    // since is the one that was announced (bossgpu_prescore), only the tiles it wrote to — and the tiles of contigs
+    // whose dropout threshold moved with the new depth total — are scored again; otherwise every tile is.
+    const bool begun = h->spec_state == 1;
+    const int ann = h->prescore_state;
+    const bool split = begun && (ann == 2 || (ann == 1 && h->pre_n_reads == 0));
+    h->spec_state = 0;
     h->prescore_state = 0;
-    if (pre != 0) BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_done, 0));
+    if (begun) BOSS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pre_done, 0));
     // reset per-update device scalars (keeps `error`)
     BOSS_CUDA(cudaMemsetAsync(h->d_upd, 0, offsetof(UpdateDev, error), h->stream));
-    ScoreArgs a = score_args(h);
-    if (split) {
-        // bucket sums, bins and the dropout count of every untouched tile are in place; thresholds were formed from
-        // the same totals (the ingest confirmed the batch's spans): add the early pass' dropout count and score the
-        // tiles the batch wrote to
-        k_add_u64<<<1, 32, 0, h->stream>>>(&h->d_upd->n_dropout, h->d_pre_misc + 1, 1);
-        BOSS_KERNEL_CHECK();
-        a.tile_list = h->d_touched_list;
-        a.list_n = reinterpret_cast<const unsigned*>(h->d_pre_misc);
-        EV_BEGIN(1);
-        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
-        k_score_bin_tma<false, 2, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
-        BOSS_KERNEL_CHECK();
-        EV_END(1);
-        h->launches += 2;
-    } else {
     BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, h->stream));
     k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, h->stream>>>(
         h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr);
     BOSS_KERNEL_CHECK();
     h->launches++;
+    ScoreArgs a = score_args(h);
     EV_BEGIN(1);
-    if (h->nb > 1) {
-        k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
+    if (split) {
+        k_mark_changed<<<(unsigned)h->n_seg, 256, 0, h->stream>>>(h->d_segs, h->d_drop_thr_spec, h->d_drop_thr, h->d_touched,
+                                                                 h->d_touched_list, reinterpret_cast<unsigned*>(h->d_pre_misc));
+        BOSS_KERNEL_CHECK();
+        a.tile_list = h->d_touched_list;
+        a.list_n = reinterpret_cast<const unsigned*>(h->d_pre_misc);
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+        k_score_bin_tma<false, 2, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+        BOSS_KERNEL_CHECK();
+        h->launches += 2;
+    } else {
+        if (h->nb > 1) {
+            k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
+            BOSS_KERNEL_CHECK();
+            h->launches++;
+        }
+        if (h->score_kernel_ldg) {
+            dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
+            if (h->nb > 1) k_score_bin<true><<<grid, SB_THREADS, 0, h->stream>>>(a);
+            else k_score_bin<false><<<grid, SB_THREADS, 0, h->stream>>>(a);
+        } else {
+            dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), (unsigned)h->nb);
+            if (h->nb > 1) k_score_bin_tma<true, 2><<<grid, SBT_THREADS, sbt_smem_bytes(true, 2), h->stream>>>(a, h->n_tiles);
+            else if (h->score_stages == 4) k_score_bin_tma<false, 4><<<grid, SBT_THREADS, sbt_smem_bytes(false, 4), h->stream>>>(a, h->n_tiles);
+            else k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+        }
         BOSS_KERNEL_CHECK();
         h->launches++;
     }
-    if (h->score_kernel_ldg) {
-        dim3 grid((unsigned)h->n_tiles, (unsigned)h->nb);
-        if (h->nb > 1) k_score_bin<true><<<grid, SB_THREADS, 0, h->stream>>>(a);
-        else k_score_bin<false><<<grid, SB_THREADS, 0, h->stream>>>(a);
-    } else {
-        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), (unsigned)h->nb);
-        if (h->nb > 1) k_score_bin_tma<true, 2><<<grid, SBT_THREADS, sbt_smem_bytes(true, 2), h->stream>>>(a, h->n_tiles);
-        else if (h->score_stages == 4) k_score_bin_tma<false, 4><<<grid, SBT_THREADS, sbt_smem_bytes(false, 4), h->stream>>>(a, h->n_tiles);
-        else k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
-    }
-    h->launches++;
-    BOSS_KERNEL_CHECK();
     EV_END(1);
-    }
+    // per-tile depth totals and dropout counts -> bucket sums, n_dropout
+    k_tile_reduce<<<(unsigned)ceil_div(h->n_tiles, 256), 256, 0, h->stream>>>(h->n_tiles, h->nb, (const TileDesc*)h->d_tiles, h->d_tile_cov,
+                                                                             h->d_tile_drop, h->d_bucket_sum, &h->d_upd->n_dropout);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
     EV_BEGIN(2);
     int64_t max_sw = 0;
     for (auto& S : h->segs) max_sw = std::max(max_sw, S.n_sw);
@@ -887,43 +892,57 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
     return 0;
 }
 
-// The early half of a split score/bin pass. Called with the batch's alignment intervals as soon as they are known
-// (before the reads are packed and copied): every tile the batch will NOT write to is scored right away on a second
-// stream, with the dropout thresholds the update will see (depth totals + the batch's reference span, the same
-// numbers the ingest adds), while the host is still busy with the batch. The update then scores only the touched
-// tiles. Every tile is still scored once per update from the counters — nothing is carried over between updates.
-// If the batch that is then ingested differs from the announced one, the update falls back to the whole pass.
+// The early half of a split score/bin pass (see include/bossgpu.h). _begin: called when a batch arrives, before anything
+// is known about it — every tile is scored at once on a second stream from the counters as they are, with the dropout
+// thresholds of the current depth totals, while the host picks records, packs bases and copies. bossgpu_prescore:
+// called once the alignment intervals are known — marks the tiles the batch will write to. The update then scores
+// only the marked tiles (after the scatter) plus the tiles of any contig whose threshold moved; every other tile's
+// bins, depth total and dropout count from the early pass are exactly what the late pass would compute (same counters,
+// same threshold). Tiles the scatter modifies while the early pass reads them yield garbage that the late pass
+// overwrites (per-tile outputs are plain stores; any counter values index inside the table).
+extern "C" int bossgpu_prescore_begin(bossgpu_handle* h) {
+    H_CHECK(h);
+    if (h->spec_state != 0) BOSS_CUDA(cudaStreamSynchronize(h->stream2));     // an earlier early pass was never consumed
+    h->spec_state = 0;
+    h->prescore_state = 0;
+    if (!h->prescore_ok || h->score_kernel_ldg || h->score_stages != 2 || h->fused_open) return 0;
+    cudaStream_t st = h->stream2;
+    k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, st>>>(
+        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr_spec);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaEventRecord(h->ev_pre_thr, st));       // the ingest may add to the totals after this point
+    ScoreArgs a = score_args(h);
+    a.drop_thr = h->d_drop_thr_spec;
+    dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+    k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), st>>>(a, h->n_tiles);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaEventRecord(h->ev_pre_done, st));
+    h->launches += 2;
+    h->spec_state = 1;
+    return 0;
+}
+
 extern "C" int bossgpu_prescore(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
                                 const int64_t* tend) {
     H_CHECK(h);
     if (n_reads < 0 || (n_reads > 0 && (!contig || !tstart || !tend))) return fail(BOSSGPU_EINVAL, "bad batch arrays");
-    if (h->prescore_state != 0) {            // an earlier announcement was never consumed: let it drain, start over
-        BOSS_CUDA(cudaStreamSynchronize(h->stream2));
-        h->prescore_state = 0;
-    }
-    if (!h->prescore_ok || h->score_kernel_ldg || h->score_stages != 2 || h->fused_open) return 0;
-    h->pre_cov_add.assign((size_t)h->n_contigs_total, 0ull);
+    h->prescore_state = 0;
+    if (h->spec_state != 1) return 0;                    // nothing in flight that the marks could save work for
     const size_t nr = (size_t)std::max<int64_t>(n_reads, 1);
     const size_t o_t0 = round_up(sizeof(int32_t) * nr, 16), o_t1 = o_t0 + sizeof(int64_t) * nr, total = o_t1 + sizeof(int64_t) * nr;
-    TRY(ensure_pre_stage(h, total));
+    if (total > h->pre_stage_bytes) {
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));     // an earlier announcement may still be copying out of the buffer
+        TRY(ensure_pre_stage(h, total));
+    }
     char* hs = (char*)h->pre_stage_h;
     int32_t* s_c = (int32_t*)hs; int64_t* s_t0 = (int64_t*)(hs + o_t0); int64_t* s_t1 = (int64_t*)(hs + o_t1);
     for (int64_t i = 0; i < n_reads; ++i) {
         if (contig[i] < 0 || contig[i] >= h->n_contigs_total) return fail(BOSSGPU_EINVAL, "read %lld: contig index out of range", (long long)i);
-        const int64_t t0 = std::min(tstart[i], tend[i]), t1 = std::max(tstart[i], tend[i]);
-        h->pre_cov_add[contig[i]] += (unsigned long long)(t1 - t0);
-        s_c[i] = contig[i]; s_t0[i] = t0; s_t1[i] = t1;
+        s_c[i] = contig[i]; s_t0[i] = std::min(tstart[i], tend[i]); s_t1[i] = std::max(tstart[i], tend[i]);
     }
-    cudaStream_t st = h->stream2;
+    cudaStream_t st = h->stream;                         // ahead of the scatter, in stream order
     BOSS_CUDA(cudaMemsetAsync(h->d_touched, 0, sizeof(uint32_t) * (size_t)(h->n_tiles / 32 + 2), st));
     BOSS_CUDA(cudaMemsetAsync(h->d_pre_misc, 0, sizeof(unsigned long long) * 2, st));
-    BOSS_CUDA(cudaMemsetAsync(h->d_bucket_sum, 0, sizeof(unsigned long long) * h->n_sw * h->nb, st));
-    BOSS_CUDA(cudaMemcpyAsync(h->d_pre_cov_add, h->pre_cov_add.data(), sizeof(unsigned long long) * h->n_contigs_total,
-                              cudaMemcpyHostToDevice, st));
-    k_drop_thresholds_pred<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, st>>>(
-        h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_pre_cov_add, h->d_drop_thr);
-    BOSS_KERNEL_CHECK();
-    BOSS_CUDA(cudaEventRecord(h->ev_pre_thr, st));       // the ingest may add to the totals after this point
     if (n_reads > 0) {
         BOSS_CUDA(cudaMemcpyAsync(h->pre_stage_d, hs, total, cudaMemcpyHostToDevice, st));
         const char* ds = (const char*)h->pre_stage_d;
@@ -931,15 +950,8 @@ extern "C" int bossgpu_prescore(bossgpu_handle* h, int64_t n_reads, const int32_
             n_reads, (const int32_t*)ds, (const int64_t*)(ds + o_t0), (const int64_t*)(ds + o_t1), h->d_seg_of_contig, h->d_segs,
             h->d_touched, h->d_touched_list, reinterpret_cast<unsigned*>(h->d_pre_misc));
         BOSS_KERNEL_CHECK();
+        h->launches++;
     }
-    ScoreArgs a = score_args(h);
-    a.touched = h->d_touched;
-    a.n_dropout = h->d_pre_misc + 1;
-    dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
-    k_score_bin_tma<false, 2, 1><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), st>>>(a, h->n_tiles);
-    BOSS_KERNEL_CHECK();
-    BOSS_CUDA(cudaEventRecord(h->ev_pre_done, st));
-    h->launches += 3;
     h->pre_n_reads = n_reads;
     h->pre_hash = batch_hash(n_reads, contig, tstart, tend);
     h->prescore_state = 1;
@@ -1345,8 +1357,7 @@ static int preload_update_kernels() {
     PRELOAD(k_drop_thresholds); PRELOAD(k_rowflags); PRELOAD(k_buckets);
     PRELOAD(k_score_bin<false>); PRELOAD(k_score_bin<true>);
     PRELOAD(k_score_bin_tma<false, 2>); PRELOAD(k_score_bin_tma<false, 4>); PRELOAD(k_score_bin_tma<true, 2>);
-    PRELOAD(k_score_bin_tma<false, 2, 1>); PRELOAD(k_score_bin_tma<false, 2, 2>); PRELOAD(k_mark_tiles);
-    PRELOAD(k_drop_thresholds_pred); PRELOAD(k_add_u64);
+    PRELOAD(k_score_bin_tma<false, 2, 2>); PRELOAD(k_mark_tiles); PRELOAD(k_mark_changed); PRELOAD(k_tile_reduce);
     PRELOAD(k_fhat_from_counts); PRELOAD(k_fhat_sum); PRELOAD(k_fhat_finish);
     PRELOAD(k_smooth); PRELOAD(k_smooth_direct); PRELOAD(k_hist); PRELOAD(k_threshold); PRELOAD(k_pack_mask);
     PRELOAD(k_distribute<true>); PRELOAD(k_distribute<false>);

@@ -205,7 +205,11 @@ struct bossgpu_handle {
     // host is still packing the batch; the update then only scores the touched tiles
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_pre_thr = nullptr, ev_pre_done = nullptr;
-    int  prescore_state = 0;                 // 0 none, 1 enqueued, 2 confirmed by the ingest, -1 batch differs: redo everything
+    int  spec_state = 0;                     // 1: an early pass over every tile is in flight / done on stream2
+    int  prescore_state = 0;                 // batch announcement: 0 none, 1 announced, 2 confirmed by the ingest, -1 differs
+    int32_t*  d_drop_thr_spec = nullptr;     // [n_contigs_total] thresholds the early pass used
+    uint32_t* d_tile_cov = nullptr;          // [n_tiles][nb] per-tile depth totals (score_pass.cuh)
+    uint32_t* d_tile_drop = nullptr;         // [n_tiles]
     bool prescore_ok = false;                // geometry allows it (one segment per contig, no barcodes, staged kernel)
     int64_t pre_n_reads = 0;
     uint64_t pre_hash = 0;
@@ -213,8 +217,7 @@ struct bossgpu_handle {
     int32_t*  d_seg_of_contig = nullptr;     // [n_contigs_total] local segment of a contig, -1 if none
     uint32_t* d_touched = nullptr;           // bitmap over tile ids
     int32_t*  d_touched_list = nullptr;      // [n_tiles]
-    unsigned long long* d_pre_misc = nullptr; // [0] list length (low 32 bits used), [1] dropout rows seen by the early pass
-    unsigned long long* d_pre_cov_add = nullptr; // [n_contigs_total]
+    unsigned long long* d_pre_misc = nullptr; // [0] list length (low 32 bits used)
     void* pre_stage_h = nullptr; void* pre_stage_d = nullptr; size_t pre_stage_bytes = 0;
     boss::UpdateDev last;
 };

@@ -44,11 +44,10 @@ struct ScoreArgs {
     const int32_t* drop_thr;         // per global contig; -1 = rule inactive
     double* ds;                      // [nb][ds_len]
     int64_t ds_len;
-    unsigned long long* bucket_sum;  // [n_sw][nb]
-    unsigned long long* n_dropout;
-    // split pass (k_score_bin_tma MODE 1 / 2, see bossgpu_prescore): tiles the coming batch touches
-    const uint32_t* touched = nullptr;   // bitmap over tile ids
-    const int32_t* tile_list = nullptr;  // the same tiles as a list, in no particular order
+    uint32_t* tile_cov;              // [n_tiles][nb] depth total of the tile  (plain stores: a tile scored twice in
+    uint32_t* tile_drop;             // [n_tiles]     rows zeroed by the depth rule    one update simply overwrites itself)
+    // late half of a split pass (k_score_bin_tma MODE 2, see bossgpu_prescore): the tiles to score, in no particular order
+    const int32_t* tile_list = nullptr;
     const unsigned* list_n = nullptr;
 };
 
@@ -212,8 +211,8 @@ k_score_bin(ScoreArgs a) {
             a.ds[(size_t)b * a.ds_len + td.ds_index + t] = acc;
         }
     } else if (t == 32) {
-        if (td.bucket >= 0 && s_cov) atomicAdd(&a.bucket_sum[(size_t)td.bucket * a.nb + b], (unsigned long long)s_cov);
-        if (s_drop && b == 0) atomicAdd(a.n_dropout, (unsigned long long)s_drop);
+        a.tile_cov[(size_t)blockIdx.x * a.nb + b] = s_cov;
+        if (b == 0) a.tile_drop[blockIdx.x] = s_drop;
     }
 }
 
@@ -265,8 +264,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SBT_CONSUMERS) : "memory"); }
 
-// MODE 0: every tile. MODE 1: every tile whose bit in a.touched is clear. MODE 2: the tiles of a.tile_list.
-// Producer and consumers walk the same sequence and skip the same entries, so the stage counters stay in step.
+// MODE 0: every tile. MODE 2: the tiles of a.tile_list (late half of a split pass, bossgpu_prescore*).
 template <bool MULTI, int SBT_STAGES, int MODE = 0>
 __global__ void __launch_bounds__(SBT_THREADS, 3)
 k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
@@ -306,7 +304,6 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
             const int64_t n_iter = MODE == 2 ? (int64_t)*a.list_n : n_tiles;
             for (int64_t idx = first; idx < n_iter; idx += stride) {
                 const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
-                if (MODE == 1 && ((a.touched[tile >> 5] >> (tile & 31)) & 1u)) continue;
                 const int stage = it % SBT_STAGES;
                 const uint32_t full = smem_u32(&s_bar[stage]), empty = smem_u32(&s_bar[SBT_STAGES + stage]);
                 if (it >= SBT_STAGES) mbar_wait(empty, ((it / SBT_STAGES) - 1) & 1);
@@ -329,7 +326,6 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
     int it = 0, buf = 0;
     const int64_t n_iter = MODE == 2 ? (int64_t)*a.list_n : n_tiles;
     for (int64_t idx = first; idx < n_iter; idx += stride) {
-        if (MODE == 1 && ((a.touched[idx >> 5] >> (idx & 31)) & 1u)) continue;
         const int stage = it % SBT_STAGES;
         mbar_wait(smem_u32(&s_bar[stage]), (it / SBT_STAGES) & 1);
         const TileDesc td = s_td[stage];
@@ -441,12 +437,33 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
             unsigned cov = 0, dr = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { cov += s_covw[buf * 8 + w]; dr += s_dropw[buf * 8 + w]; }
-            if (td.bucket >= 0 && cov) atomicAdd(&a.bucket_sum[(size_t)td.bucket * a.nb + b], (unsigned long long)cov);
-            if (dr && b == 0) atomicAdd(a.n_dropout, (unsigned long long)dr);
+            const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
+            a.tile_cov[(size_t)tile * a.nb + b] = cov;
+            if (b == 0) a.tile_drop[tile] = dr;
         }
         ++it;
         buf ^= 1;
     }
+}
+
+// per-tile depth totals -> bucket sums (reference.py:196-198 sums whole 20 kb buckets; a tile is a tenth of one), and
+// the number of dropped rows for the log line. Integer sums: order-free.
+__global__ void k_tile_reduce(int64_t n_tiles, int nb, const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ tile_cov,
+                              const uint32_t* __restrict__ tile_drop, unsigned long long* __restrict__ bucket_sum,
+                              unsigned long long* __restrict__ n_dropout) {
+    const int64_t tile = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long dr = 0;
+    if (tile < n_tiles) {
+        const int32_t bucket = tiles[tile].bucket;
+        if (bucket >= 0)
+            for (int b = 0; b < nb; ++b) {
+                const uint32_t c = tile_cov[(size_t)tile * nb + b];
+                if (c) atomicAdd(&bucket_sum[(size_t)bucket * nb + b], (unsigned long long)c);
+            }
+        dr = tile_drop[tile];
+    }
+    for (int o = 16; o > 0; o >>= 1) dr += __shfl_down_sync(0xFFFFFFFFu, dr, o);
+    if ((threadIdx.x & 31) == 0 && dr) atomicAdd(n_dropout, dr);
 }
 
 // Tiles the coming batch will write to: one thread per read marks the tiles its reference interval overlaps in its
@@ -469,14 +486,18 @@ __global__ void k_mark_tiles(int64_t n_reads, const int32_t* __restrict__ contig
     }
 }
 
-// dropout thresholds the update WILL see: depth totals + the reference span of the batch about to be ingested
-__global__ void k_drop_thresholds_pred(int n_contigs, const int64_t* __restrict__ contig_len, int nb,
-                                       const unsigned long long* __restrict__ cov_total,
-                                       const unsigned long long* __restrict__ cov_add, int32_t* __restrict__ thr) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_contigs) return;
-    double mean = (double)(cov_total[k] + cov_add[k]) / (double)(contig_len[k] * (int64_t)nb);
-    thr[k] = mean > 5.0 ? (int32_t)(mean / 8.0) : -1;
+// Contigs whose dropout threshold differs between the early pass and the update (the batch moved the mean depth across
+// a multiple of 8): every tile of their segment goes onto the list. One CTA per local segment.
+__global__ void k_mark_changed(const SegDev* __restrict__ segs, const int32_t* __restrict__ thr_early,
+                               const int32_t* __restrict__ thr_now, uint32_t* __restrict__ touched, int32_t* __restrict__ list,
+                               unsigned* __restrict__ list_n) {
+    const SegDev S = segs[blockIdx.x];
+    if (thr_early[S.contig] == thr_now[S.contig]) return;
+    for (int64_t tile = S.tile_off + threadIdx.x; tile < S.tile_off + S.n_tiles; tile += blockDim.x) {
+        const uint32_t bit = 1u << (tile & 31);
+        const uint32_t old = atomicOr(&touched[tile >> 5], bit);
+        if (!(old & bit)) list[atomicAdd(list_n, 1u)] = (int32_t)tile;
+    }
 }
 
 constexpr size_t sbt_smem_bytes(bool multi, int SBT_STAGES) {

@@ -173,9 +173,13 @@ class Engine:
                                                   ptr(rev), ptr(cigar_ptr), ptr(cigar_len), ptr(seq_ptr), ptr(seq_from),
                                                   ptr(seq_to), int(n_threads)))
 
+    def prescore_begin(self) -> None:
+        """A batch has arrived: score every tile now, on a second stream, while the host prepares the batch
+        (`bossgpu_prescore_begin`); results do not depend on it."""
+        check(self.lib.bossgpu_prescore_begin(self.h))
+
     def prescore(self, contig, tstart, tend) -> None:
-        """Announce the coming batch's alignment intervals: tiles it does not touch are scored right away on a
-        second stream while the host packs the batch (`bossgpu_prescore`); results do not depend on it."""
+        """Announce the batch's alignment intervals: the update will only re-score the tiles they cover."""
         contig = as_c(contig, np.int32); tstart = as_c(tstart, np.int64); tend = as_c(tend, np.int64)
         check(self.lib.bossgpu_prescore(self.h, len(contig), ptr(contig), ptr(tstart), ptr(tend)))
 

@@ -471,6 +471,7 @@ class BossRuns:
         """`paf_dict` = mappings of the batch ({read id: [PafLine]}); `paf_dict_starts` (default: the same)
         is the subset that feeds the read-start distribution — the simulator passes accepted reads only
         (simulation.py:171)."""
+        self._prescore_begin()
         increments = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
         self._prescore(increments)
         self._effect_increments(increments=increments)
@@ -484,6 +485,7 @@ class BossRuns:
         `process_batch_runs` does after `map_sequences`, without materialising `{read id: [PafLine]}` — the text is
         tokenised once in C, the winning record of every read goes to the GPU, and the read starts are counted from
         the same arrays. `min_len` = mu/2 as `Mapper.map_sequences` passes it (mapper.py:64)."""
+        self._prescore_begin()
         b = self.cc.convert_text(paf_raw, seqs, min_len=min_len, barcodes=barcodes)
         self._prescore(b)
         self._effect_increments(increments=b)
@@ -500,9 +502,16 @@ class BossRuns:
     def _engines(self):
         return getattr(self, "engines", None) or [self.engine]
 
+    def _prescore_begin(self) -> None:
+        """Split score/bin pass, early half: the GPU scores every tile from the counters as they are while the host
+        prepares the batch (`bossgpu_prescore_begin`). Only called when an update is certain to follow."""
+        if self.use_prescore:
+            for e in self._engines():
+                if hasattr(e, "prescore_begin"):
+                    e.prescore_begin()
+
     def _prescore(self, b: PackedBatch) -> None:
-        """The GPU starts scoring every tile the batch will not touch while the host packs the batch (split score/bin
-        pass, `bossgpu_prescore`); only done when an update is certain to follow, i.e. from `process_batch_*`."""
+        """... and the announcement: the update re-scores only the tiles these intervals cover (`bossgpu_prescore`)."""
         if self.use_prescore:
             for e in self._engines():
                 if hasattr(e, "prescore"):

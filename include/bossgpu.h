@@ -154,14 +154,21 @@ int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads,
                                int n_threads);
 
 /* Multi-shard geometry and halo staging (see bossgpu_update_phase) */
-/* Early half of a split score/bin pass (optional; results are identical with and without it).
- * Announce the batch's alignment intervals (contig index, tstart, tend of every read's winning record — the numbers
- * CoverageConverter.convert_records derives, boss/runs/sequences.py:694-731) BEFORE the reads are packed and
- * ingested: every 2000-site tile the batch will not write to is scored at once on a second stream, with the dropout
- * thresholds the update will see (reference.py:157-158 on depth totals + the batch's reference span), while the
- * host is still busy with bossgpu_ingest_records*. The next update scores only the touched tiles. If the batch that
- * is then ingested differs from the announced one (or is rejected), the update silently redoes the whole pass.
+/* Split score/bin pass (optional; results are identical with and without it).
+ *   bossgpu_prescore_begin  when a batch arrives, before anything is known about it: every 2000-site tile is scored at
+ *                           once on a second stream from the counters as they are, with the dropout thresholds of the
+ *                           current depth totals (reference.py:157-158), while the host picks records, packs bases and
+ *                           copies (bossgpu_ingest_records*).
+ *   bossgpu_prescore        once the batch's alignment intervals are known (contig index, tstart, tend of every read's
+ *                           winning record — what CoverageConverter.convert_records derives, sequences.py:694-731):
+ *                           marks the tiles the batch will write to.
+ * The next update then scores only the marked tiles, plus every tile of a contig whose threshold moved with the new
+ * depth total; all other tiles keep the early pass' bins, depth totals and dropout counts, which are what the update
+ * would compute (same counters, same threshold). Every tile is scored from its counters in every update — nothing is
+ * carried over from one update to the next. If the batch that is ingested differs from the announced one (or is
+ * rejected, or arrives by another ingest route, or was never announced) the update scores every tile again.
  * No-op with barcodes (the row rules Q6/Q8 need the pre-pass over all planes). */
+int bossgpu_prescore_begin(bossgpu_handle* h);
 int bossgpu_prescore(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart, const int64_t* tend);
 
 int bossgpu_set_shards(bossgpu_handle* h, int32_t n_shards, int32_t shard_index, const int64_t* row_start);
