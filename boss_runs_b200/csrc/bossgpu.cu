@@ -324,6 +324,7 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         BOSS_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_thr, cudaEventDisableTiming));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_done, cudaEventDisableTiming));
+        BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
         h->prescore_ok = one_each && h->nb == 1 && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
         BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
     }
@@ -373,6 +374,7 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->ev_pre_thr) cudaEventDestroy(h->ev_pre_thr);
     if (h->ev_pre_done) cudaEventDestroy(h->ev_pre_done);
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     delete h;
     return 0;
@@ -907,6 +909,9 @@ extern "C" int bossgpu_prescore_begin(bossgpu_handle* h) {
     h->prescore_state = 0;
     if (!h->prescore_ok || h->score_kernel_ldg || h->score_stages != 2 || h->fused_open) return 0;
     cudaStream_t st = h->stream2;
+    // whatever the main stream still has queued (a previous ingest, set/synth_coverage) comes first
+    BOSS_CUDA(cudaEventRecord(h->ev_main, h->stream));
+    BOSS_CUDA(cudaStreamWaitEvent(st, h->ev_main, 0));
     k_drop_thresholds<<<(unsigned)ceil_div(h->n_contigs_total, 128), 128, 0, st>>>(
         h->n_contigs_total, h->d_contig_len, h->nb, h->d_cov_total, h->d_drop_thr_spec);
     BOSS_KERNEL_CHECK();

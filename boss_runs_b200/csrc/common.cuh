@@ -204,7 +204,7 @@ struct bossgpu_handle {
     // split score/bin pass (bossgpu_prescore): tiles the coming batch does not touch are scored on `stream2` while the
     // host is still packing the batch; the update then only scores the touched tiles
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_pre_thr = nullptr, ev_pre_done = nullptr;
+    cudaEvent_t ev_pre_thr = nullptr, ev_pre_done = nullptr, ev_main = nullptr;
     int  spec_state = 0;                     // 1: an early pass over every tile is in flight / done on stream2
     int  prescore_state = 0;                 // batch announcement: 0 none, 1 announced, 2 confirmed by the ingest, -1 differs
     int32_t*  d_drop_thr_spec = nullptr;     // [n_contigs_total] thresholds the early pass used
