@@ -568,7 +568,11 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
     if (h->prescore_state == 1)       // is this the batch that was announced? Same reads, same intervals -> its tile marks hold
         h->prescore_state = (n_all == h->pre_n_reads && batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
     const int64_t n_reads = (int64_t)sel.size();
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {       // one process per GPU (torchrun): share the host's cores
+        const int n_local = atoi(lws);
+        if (n_local > 1) hw = std::max(4u, hw / (unsigned)n_local);
+    }
     int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(hw > 2 ? hw - 1 : hw, 32u);   // one thread keeps issuing copies
     if (n_reads < 64) T = 1;
     T = (int)std::max<int64_t>(1, std::min<int64_t>(T, n_reads));

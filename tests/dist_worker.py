@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--case", default="hap_nb1")
     ap.add_argument("--halo", type=int, default=160)
     ap.add_argument("--exchange", default="auto")
+    ap.add_argument("--text", action="store_true", help="feed the raw PAF text (process_batch_text) instead of parsed records")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.backend == "nccl":
@@ -52,7 +53,12 @@ def main():
     n_upd = 0
     for bi, (paf, seqs, bcs) in enumerate(g.batches):
         pd = H.parse_batch(paf, bcs, g.barcodes is not None)
-        updated = H.product_step(run, pd, seqs)
+        if a.text:
+            run.rl_dist.update({rid: recs[0].qlen for rid, recs in pd.items()})
+            run.process_batch_text(paf, seqs, barcodes=bcs if g.barcodes is not None else None, min_len=1)
+            updated = bool(run.last.switched_on)
+        else:
+            updated = H.product_step(run, pd, seqs)
         if rank != 0:
             continue
         assert H.oracle_step(orc, pd, seqs) == updated, f"b{bi}: switched_on differs"

@@ -72,6 +72,12 @@ def test_sharded_update_gloo_world2(case):
     assert r.returncode == 0 and "SHARDED-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
 
 
+def test_sharded_text_batches_gloo_world2():
+    """The raw-PAF-text entry point (`process_batch_text`: C tokeniser, read starts from arrays) through the sharded run."""
+    r = _torchrun(2, "--backend", "gloo", "--case", "hap_nb3", "--text")
+    assert r.returncode == 0 and "SHARDED-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+
+
 def test_virtual_shards_numpy_model():
     """The same protocol with every shard in one process (LocalGroup), three shards: exercises a shard that lies
     between two cuts and contigs split in the middle."""
