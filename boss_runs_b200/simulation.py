@@ -15,53 +15,81 @@ import logging
 from collections import defaultdict
 from io import StringIO
 
+import numpy as np
+
 from .hostmodel import choose_best_mapper, parse_PAF
 from .runs import BossRuns
+
+
+def _lookup(contigs_filt: dict, picks: list, barcodes: dict, window: int) -> np.ndarray:
+    """Decision bit of every picked record: `strat[start // window, rev, barcode]` with NumPy's index rules (negative
+    indices wrap, anything outside raises IndexError upstream -> reject; a target without a strategy raises KeyError ->
+    reject). One gather per target instead of one Python lookup per read."""
+    n = len(picks)
+    out = np.zeros(n, dtype=bool)
+    by_target: dict[str, list[int]] = defaultdict(list)
+    for i, rec in enumerate(picks):
+        by_target[str(rec.tname)].append(i)
+    for tname, idx in by_target.items():
+        cont = contigs_filt.get(tname)
+        if cont is None:
+            continue
+        strat = np.asarray(cont.strat)
+        if strat.ndim != 3:
+            continue                                                 # `zeros(1)` of a reject ref: IndexError upstream
+        rows_n, _, nb = strat.shape
+        recs = [picks[i] for i in idx]
+        row = np.array([((r.tend - 1) if r.rev else r.tstart) // window for r in recs], dtype=np.int64)
+        rev = np.array([int(r.rev) for r in recs], dtype=np.int64)
+        bc = np.array([barcodes[r.qname] for r in recs], dtype=np.int64)
+        ok = (row >= -rows_n) & (row < rows_n) & (bc >= -nb) & (bc < nb)
+        sel = np.asarray(idx)[ok]
+        out[sel] = strat[row[ok], rev[ok], bc[ok]]
+    return out
 
 
 def make_decisions(contigs_filt: dict, seqs: dict[str, str], paf_full: str, paf_trunc: str, barcodes: dict[str, int],
                    mu: int = 400, accept_unmapped: bool = False, all_read_ids: set | None = None, window: int = 100):
     """`BossRunsSim.make_decisions` (simulation.py:37-120): -> (paf_dict, reads_decision, n_mapped, n_unmapped,
     n_accepted, n_rejected). `contigs_filt[name].strat` is bool `(L//100, 2, nb)`; `all_read_ids` stands for
-    `sampler.fq_stream.read_ids` (default: the ids of this batch)."""
+    `sampler.fq_stream.read_ids` (default: the ids of this batch).
+
+    Upstream walks the mu-sized mappings one by one; here the winning truncated record of every read is picked first,
+    all decisions are gathered from the masks at once, and the outcome is assembled in upstream's order: reads in
+    order of first appearance in `paf_trunc`, then (if unmapped reads are accepted) the unmapped ones that do have a
+    full-length record, in `seqs` order."""
+    full = parse_PAF(StringIO(paf_full))
+    trunc = parse_PAF(StringIO(paf_trunc))
+    rids = list(trunc)
+    picks = [choose_best_mapper(trunc[rid])[0] for rid in rids]
+    for rec in picks:
+        rec.barcode = barcodes[rec.qname]                            # KeyError for a read without a barcode entry, as upstream
+    accept = _lookup(contigs_filt, picks, barcodes, window)
     paf_dict = defaultdict(list)
-    mapped_reads = set()
-    n_rejected = n_accepted = 0
-    reads_decision = dict(seqs)                                      # deepcopy of a dict of immutable strings
-    paf_dict_full = parse_PAF(StringIO(paf_full))
-    paf_dict_trunc = parse_PAF(StringIO(paf_trunc))
-    for rid, rlist in paf_dict_trunc.items():                        # decisions come from the mu-sized mappings
-        rec = choose_best_mapper(rlist)[0]
-        rec.barcode = barcodes[rec.qname]
-        mapped_reads.add(rid)
-        start_pos = rec.tend - 1 if rec.rev else rec.tstart
-        try:
-            strat = contigs_filt[str(rec.tname)].strat
-            decision = strat[start_pos // window, rec.rev, barcodes[rec.qname]]
-        except (KeyError, IndexError):
-            decision = 0                                             # no strategy for that target: reject
-        if decision:
-            rec_full = choose_best_mapper(paf_dict_full[str(rec.qname)])[0]      # IndexError upstream if it never mapped in full
-            rec_full.barcode = barcodes[rec_full.qname]
-            paf_dict[str(rec.qname)].append(rec_full)
-            n_accepted += 1
+    reads_decision = dict(seqs)                                      # upstream deep-copies; the values are immutable
+    for rid, rec, yes in zip(rids, picks, accept):
+        if yes:
+            winner = choose_best_mapper(full[str(rec.qname)])[0]     # IndexError upstream if the read never mapped in full
+            winner.barcode = barcodes[winner.qname]
         else:
-            paf_dict[str(rec.qname)].append(rec)
-            n_rejected += 1
-            reads_decision[rid] = reads_decision[rid][:mu]
-    for read_id, seq in seqs.items():                                # unmapped reads are accepted or rejected wholesale
-        if read_id in mapped_reads:
-            continue
-        if accept_unmapped:
-            reads_decision[read_id] = seq
-            if read_id in paf_dict_full:
-                paf_dict[read_id].append(choose_best_mapper(paf_dict_full[read_id])[0])
-            n_accepted += 1
-        else:
-            reads_decision[read_id] = seq[:mu]
-            n_rejected += 1
+            winner = rec
+            reads_decision[rid] = reads_decision[rid][:mu]           # ejected after mu bases
+        paf_dict[str(rec.qname)].append(winner)
+    mapped = set(rids)
+    n_accepted = int(accept.sum())
+    n_rejected = len(rids) - n_accepted
+    loose = [rid for rid in seqs if rid not in mapped]               # unmapped at mu bases: wholesale accept or reject
+    if accept_unmapped:
+        for rid in loose:
+            if rid in full:
+                paf_dict[rid].append(choose_best_mapper(full[rid])[0])
+        n_accepted += len(loose)
+    else:
+        for rid in loose:
+            reads_decision[rid] = seqs[rid][:mu]
+        n_rejected += len(loose)
     ids = set(seqs) if all_read_ids is None else all_read_ids
-    return paf_dict, reads_decision, len(mapped_reads), len(ids - mapped_reads), n_accepted, n_rejected
+    return paf_dict, reads_decision, len(mapped), len(ids - mapped), n_accepted, n_rejected
 
 
 def filter_paf_dict(paf_dict: dict, mu: int = 400) -> dict:
