@@ -7,7 +7,13 @@ that carries exactly the attributes they read (`contigs_filt[...].strat`, `mu`, 
 data/BOSS_test_data/ERR3152366_10k.fq with their full-length and mu-truncated minimap2 records, against seeded random
 strategies for the zymo contigs. CIGAR tags are dropped from the stored PAF text (the decision step never reads them).
 
-    python -m oracle.make_golden_sim        # writes tests/golden/sim_decisions.npz
+A second fixture pins the whole simulated flow (simulation.py:139-190 minus sampler and read cache): on the inputs of
+tests/golden/case_real_zymo.npz (real reads + their full-length records) plus the same reads' mu-truncated records,
+the reference's `BossRuns` is driven batch by batch — decisions from its current strategies, read lengths and read
+starts from the accepted reads, coverage from every record (Q12: rejected reverse-strand reads are sliced from the
+whole read with qlen = 400 coordinates) — and its strategies, thresholds and counts are recorded.
+
+    python -m oracle.make_golden_sim        # writes tests/golden/sim_decisions.npz and tests/golden/sim_flow_zymo.npz
 """
 from __future__ import annotations
 
@@ -118,5 +124,80 @@ def main():
     print(path.name, f"{path.stat().st_size / 1e3:.0f} kB")
 
 
+def trunc_text_for(rids) -> str:
+    keep, out = set(rids), []
+    with open(REFERENCE / "data" / "BOSS_test_data" / "ERR3152366_10k_trunc.paf") as fh:
+        for line in fh:
+            if line.split("\t", 1)[0] in keep:
+                out.append(line)
+    return "".join(out)
+
+
+def main_flow():
+    import hashlib
+    import io
+    import logging
+    import tempfile
+    logging.disable(logging.CRITICAL)
+    from oracle import make_golden as mg
+    from boss.config import Config
+    from boss.runs.core import BossRuns
+    from boss.runs.simulation import BossRunsSim
+
+    spec, names, seqs, kinds, batches = mg.real_case_inputs()
+    out = {"n_batches": np.int64(len(batches))}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        work = Path(td)
+        fa = work / "ref.fa"
+        with open(fa, "w") as fh:
+            for n in names:
+                fh.write(f">{n}\n{seqs[n]}\n")
+        (work / "ref.mmi").touch()
+        os.chdir(work)
+        try:
+            args = Config().args
+            args.general.name = "golden"
+            args.general.ref = str(fa)
+            args.general.mmi = str(work / "ref.mmi")
+            args.optional.ploidy = 1
+            args.optional.bucket_threshold = 0
+            exp = BossRuns(args)
+            exp.init()
+            all_ids = set(r for rb in batches for r in rb.seqs)
+            stub = SimpleNamespace(contigs_filt=exp.contigs_filt, mu=400, accept_unmapped=False, read_cache=SimpleNamespace(mu=400),
+                                   sampler=SimpleNamespace(fq_stream=SimpleNamespace(read_ids=all_ids)))
+            for bi, rb in enumerate(batches):
+                paf_t = trunc_text_for(rb.seqs)
+                barcodes = {r: 0 for r in rb.seqs}
+                paf_dict, reads_decision, n_mapped, n_unmapped, n_acc, n_rej = BossRunsSim.make_decisions(
+                    stub, seqs=rb.seqs, paf_full=rb.paf_text, paf_trunc=paf_t, barcodes=barcodes)
+                acc = BossRunsSim.filter_paf_dict(stub, paf_dict=paf_dict)
+                exp.rl_dist.update(read_lengths={n: r[0].qlen for n, r in acc.items()})
+                quals = {rid: "5" * len(s) for rid, s in rb.seqs.items()}
+                inc = exp.cc.convert_records(paf_dict=paf_dict, seqs=rb.seqs, quals=quals, barcodes=barcodes)
+                exp._effect_increments(increments=inc)
+                exp.read_starts.count_read_starts(paf_dict=acc)
+                exp.update_wrapper()
+                p = f"b{bi}_"
+                out[p + "paf_trunc"] = np.frombuffer(paf_t.encode(), np.uint8)
+                out[p + "counts"] = np.array([n_mapped, n_unmapped, n_acc, n_rej], dtype=np.int64)
+                out[p + "accepted_keys"] = np.array(list(acc))
+                out[p + "decision_len"] = np.array([len(reads_decision[r]) for r in rb.seqs], dtype=np.int64)
+                out[p + "approx_ccl"] = exp.rl_dist.approx_ccl.copy()
+                for cname, c in exp.contigs_filt.items():
+                    out[f"{p}{cname}_strat"] = np.packbits(c.strat.ravel())
+                    out[f"{p}{cname}_coverage_sha"] = np.array(hashlib.sha256(np.ascontiguousarray(c.coverage).tobytes()).hexdigest())
+                    out[f"{p}{cname}_scores_sum"] = np.float64(c.scores.sum())
+                print(p, "mapped/unmapped/accepted/rejected", n_mapped, n_unmapped, n_acc, n_rej,
+                      "accept fraction now", float(np.mean([c.strat.mean() for c in exp.contigs_filt.values()])))
+        finally:
+            os.chdir(cwd)
+    path = GOLDEN / "sim_flow_zymo.npz"
+    np.savez_compressed(path, **out)
+    print(path.name, f"{path.stat().st_size / 1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     main()
+    main_flow()

@@ -86,3 +86,17 @@ def compare_state(prod, orc, updated: bool, tag: str):
             ben = orc.benefit_adj[i: i + n]
             assert_masks_match(pc.strat, oc.strat, ben, orc.threshold, f"{tag}/{name}: strat")
             i += n
+
+
+def oracle_sim_step(orc, seqs, paf_full, paf_trunc, barcodes, all_ids):
+    """One simulated batch on the oracle (simulation.py:139-190 minus sampler / read cache): decisions from the oracle's
+    current strategies, read lengths and read starts from the accepted reads, coverage from every record."""
+    from boss_runs_b200.simulation import filter_paf_dict, make_decisions
+    paf_dict, reads_decision, n_mapped, n_unmapped, n_acc, n_rej = make_decisions(
+        orc.contigs_filt, seqs, paf_full, paf_trunc, barcodes, all_read_ids=all_ids)
+    acc = filter_paf_dict(paf_dict)
+    orc.rl.update({n: r[0].qlen for n, r in acc.items()})
+    orc.ingest(paf_dict, seqs)
+    orc.read_starts.count(acc)
+    updated = orc.update()
+    return updated, (n_mapped, n_unmapped, n_acc, n_rej), acc, reads_decision

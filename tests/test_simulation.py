@@ -52,3 +52,59 @@ def test_accepted_read_without_full_mapping_raises_like_upstream():
     for text in (far, other):
         pd, dec, n_mapped, n_unmapped, n_acc, n_rej = make_decisions(contigs, {"r1": "A" * 900}, line, text, {"r1": 0})
         assert (n_acc, n_rej) == (0, 1) and len(dec["r1"]) == 400 and pd["r1"][0].qlen == 400
+
+
+# ---- the whole simulated flow on the reference's real data --------------------------------------------------------
+import hashlib  # noqa: E402
+
+import helpers as H  # noqa: E402
+from golden_io import load_case  # noqa: E402
+
+FLOW = dict(np.load(Path(__file__).resolve().parent / "golden" / "sim_flow_zymo.npz", allow_pickle=False))
+
+
+def flow_inputs():
+    g = load_case("real_zymo")
+    all_ids = set(r for _, seqs, _ in g.batches for r in seqs)
+    truncs = [FLOW[f"b{bi}_paf_trunc"].tobytes().decode() for bi in range(len(g.batches))]
+    return g, all_ids, truncs
+
+
+def test_simulated_flow_oracle_equals_reference():
+    """Oracle + this package's decision step reproduce what the reference's BossRuns produced when driven by its own
+    `make_decisions` (oracle/make_golden_sim.py:main_flow): counts, accepted reads, coverage, thresholds and every
+    strategy bit, batch after batch — including batches where most reads are rejected and contribute only their
+    first 400 bases (Q12)."""
+    g, all_ids, truncs = flow_inputs()
+    orc = H.oracle_run(g.records, 1, [], None, 0)
+    for bi, (paf, seqs, _) in enumerate(g.batches):
+        updated, counts, acc, dec = H.oracle_sim_step(orc, seqs, paf, truncs[bi], {r: 0 for r in seqs}, all_ids)
+        p = f"b{bi}_"
+        assert updated
+        assert list(counts) == FLOW[p + "counts"].tolist()
+        assert list(acc) == [str(k) for k in FLOW[p + "accepted_keys"]]
+        assert [len(dec[r]) for r in seqs] == FLOW[p + "decision_len"].tolist()
+        assert np.array_equal(orc.rl.approx_ccl, FLOW[p + "approx_ccl"])
+        for name, c in orc.contigs_filt.items():
+            assert hashlib.sha256(np.ascontiguousarray(c.coverage).tobytes()).hexdigest() == str(FLOW[f"{p}{name}_coverage_sha"]), name
+            assert np.array_equal(np.packbits(c.strat.ravel()), FLOW[f"{p}{name}_strat"]), f"b{bi}/{name}"
+    assert FLOW["b2_counts"][3] > FLOW["b2_counts"][2] > 0               # mostly rejections by the third batch
+
+
+@pytest.mark.gpu
+def test_simulated_flow_gpu_equals_oracle(lib):
+    """`BossRunsSim.process_batch_runs_sim` on the GPU against the oracle flow above, state by state, and against the
+    reference's recorded strategies."""
+    from boss_runs_b200.simulation import BossRunsSim
+    g, all_ids, truncs = flow_inputs()
+    orc = H.oracle_run(g.records, 1, [], None, 0)
+    sim = BossRunsSim(contigs=g.records, ploidy=1, bucket_threshold=0, write_debug=True)
+    for bi, (paf, seqs, _) in enumerate(g.batches):
+        updated, counts, acc, dec_o = H.oracle_sim_step(orc, seqs, paf, truncs[bi], {r: 0 for r in seqs}, all_ids)
+        dec_p = sim.process_batch_runs_sim(seqs, None, {r: "" for r in seqs}, paf, truncs[bi], all_read_ids=all_ids)
+        assert (sim.n_accepted, sim.n_rejected) == counts[2:]
+        assert dec_p == dec_o
+        assert bool(sim.last.switched_on) == updated
+        H.compare_state(sim, orc, updated, f"sim/b{bi}")
+        for name, c in sim.contigs_filt.items():
+            assert np.array_equal(np.packbits(np.asarray(c.strat).ravel()), FLOW[f"b{bi}_{name}_strat"]), f"b{bi}/{name}"
