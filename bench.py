@@ -336,13 +336,13 @@ def run_b200(args, spec):
         run.ingest_device(d)
         return run.device_update(fhat_windows=None, **upd_kwargs)
 
+    sampler = ClockSampler(local)
+    sampler.start()                     # nvidia-smi needs ~100 ms to deliver its first line: start it ahead of the warm-up
     for i in range(args.warmup):
         step(i)
-    sampler = ClockSampler(local)
     l0 = eng.launch_count()
     score_ms, all_ms = [], []
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     mirror_steps = []
@@ -354,7 +354,6 @@ def run_b200(args, spec):
         mirror_steps.append(int(out.mirror_bytes))
     ev1.record()
     barrier()
-    clocks = sampler.stop()
     launches = eng.launch_count() - l0
     ms = ev0.elapsed_time(ev1) / args.steps
     ms_t = torch.tensor([ms], device="cuda")
@@ -362,6 +361,17 @@ def run_b200(args, spec):
         import torch.distributed as dist
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
+    # A timed region of a few milliseconds is shorter than nvidia-smi's 100 ms sampling period: keep the same workload
+    # running (untimed; the same number of extra updates on every rank, derived from the agreed ms) until the sampler has
+    # seen ~0.5 s of it, so that the clocks line always describes the GPU under this load.
+    n_extra = 0
+    if ms * (args.steps + args.warmup) < 500.0:
+        n_extra = min(int(500.0 / max(ms, 0.05)) + 1, 5000)
+        for i in range(n_extra):
+            step(args.warmup + args.steps + i)
+        barrier()
+    clocks = sampler.stop()
+    clocks["sampled_over"] = f"warm-up + timed updates + {n_extra} untimed updates of the same workload"
 
     if rank != 0:
         return

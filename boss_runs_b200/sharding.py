@@ -329,10 +329,13 @@ class DistGroup:
             self._shm = None
             try:
                 shm.close()
-                if self.rank == 0:
-                    shm.unlink()
-            except Exception:
+            except Exception:                  # a view of the segment is still alive somewhere: leave the mapping to the OS
                 pass
+            if self.rank == 0:
+                try:
+                    shm.unlink()
+                except Exception:
+                    pass
 
     def agree(self, ok: bool) -> bool:
         if getattr(self, "_ctl", None) is not None:
@@ -608,11 +611,18 @@ class ShardedRun(BossRuns):
     def close(self) -> None:
         for e in getattr(self, "engines", []):
             e.close()
+            e._mirror = None
         if getattr(self, "_strat_global", None) is not None:
             try:
                 self.engine.host_unregister(self._strat_global)
             except Exception:
                 pass
+            # every view of the shared mirror has to go before the segment can be unmapped: contigs keep copies
+            for c in self.contigs_filt.values():
+                if isinstance(getattr(c, "strat", None), np.ndarray):
+                    c.strat = np.array(c.strat)
+            self._global_views = None
+            self._strat_views = None
             self._strat_global = None
-        if hasattr(self.group, "close"):
+        if hasattr(getattr(self, "group", None), "close"):
             self.group.close()
