@@ -90,14 +90,17 @@ static PyObject* convert(PyObject* self, PyObject* args) {
             }
             int rev = 0;
             if (ok) { rev = PyObject_IsTrue(revo); if (rev < 0) ok = 0; }
-            if (ok && cig == Py_None) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); ok = 0; }   /* sequences.py:718 */
+            if (ok && cig == Py_None && qstart >= 0 && qend >= 0 && (!rev || (qlen - qend >= 0 && qlen - qstart >= 0))) {
+                PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR");   /* sequences.py:718, after the slicing */
+                ok = 0;
+            }
             Py_ssize_t clen = 0, slen = 0;
             const char *cptr = NULL, *sptr = NULL;
             if (ok) {
-                cptr = PyUnicode_AsUTF8AndSize(cig, &clen);
-                sptr = cptr ? PyUnicode_AsUTF8AndSize(s, &slen) : NULL;
+                sptr = PyUnicode_AsUTF8AndSize(s, &slen);
+                cptr = (sptr && cig != Py_None) ? PyUnicode_AsUTF8AndSize(cig, &clen) : "";
                 if (!cptr || !sptr) ok = 0;
-                else if (slen != PyUnicode_GET_LENGTH(s) || clen != PyUnicode_GET_LENGTH(cig)) {
+                else if (slen != PyUnicode_GET_LENGTH(s) || (cig != Py_None && clen != PyUnicode_GET_LENGTH(cig))) {
                     PyErr_SetString(PyExc_ValueError, "read and CIGAR strings must be ASCII");
                     ok = 0;
                 }
@@ -165,6 +168,7 @@ typedef struct {
     span_t tname, cigar;
     long long qlen, qstart, qend, tstart, tend, mapq, as;
     int rev, has_cigar;
+    unsigned bad;             /* 1: a coordinate column is not an integer, 2: mapq is not */
     Py_ssize_t next;          /* next record of the same read, -1 at the end */
 } rec_t;
 
@@ -179,7 +183,7 @@ static span_t strip_span(span_t s) {
 }
 
 /* Python's int(str) for the forms a PAF can hold: optional surrounding whitespace, optional sign, decimal digits.
- * 0 = parsed, -1 = not an integer (upstream would keep the string). */
+ * 0 = parsed, -1 = not an integer (upstream would keep the string). Values beyond 64 bits count as "not an integer". */
 static int parse_int(span_t s, long long* out) {
     s = strip_span(s);
     if (s.n == 0) return -1;
@@ -188,12 +192,20 @@ static int parse_int(span_t s, long long* out) {
     if (s.p[0] == '+' || s.p[0] == '-') { neg = s.p[0] == '-'; i = 1; }
     if (i >= s.n) return -1;
     unsigned long long v = 0;
+    int prev_digit = 0;
     for (; i < s.n; ++i) {
+        if (s.p[i] == '_') {                     /* PEP 515: single underscores between digits ("1_0" == 10) */
+            if (!prev_digit || i + 1 >= s.n) return -1;
+            prev_digit = 0;
+            continue;
+        }
         unsigned c = (unsigned char)s.p[i] - '0';
         if (c > 9) return -1;
         if (v > (unsigned long long)(INT64_MAX / 10 - 1)) return -1;
         v = v * 10 + c;
+        prev_digit = 1;
     }
+    if (!prev_digit) return -1;
     *out = neg ? -(long long)v : (long long)v;
     return 0;
 }
@@ -245,7 +257,9 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
         memset(&r, 0, sizeof r);
         r.next = -1;
         long long as = 0, blocklen = 0;
-        int primary = 0;
+        int primary = 0, has_as = 0;
+        char as_typ = 'i';
+        span_t as_val = {NULL, 0};
         for (;;) {
             {
                 const char* tb = (const char*)memchr(line.p + c0, '\t', (size_t)(line.n - c0));
@@ -276,7 +290,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                         goto done;
                     }
                     if (key.n == 2 && key.p[0] == 'A' && key.p[1] == 'S') {
-                        if (parse_int(val, &as) != 0) { PyErr_SetString(PyExc_ValueError, "AS tag is not an integer"); goto done; }
+                        as_val = val; as_typ = typ.p[0]; has_as = 1;      /* a repeated key keeps its LAST value (dict) */
                     } else if (key.n == 2 && key.p[0] == 't' && key.p[1] == 'p') {
                         primary = val.n == 1 && val.p[0] == 'P';
                     } else if (key.n == 2 && key.p[0] == 'c' && key.p[1] == 'g') {
@@ -290,11 +304,42 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
             }
         }
         if (nc < 12) { PyErr_SetString(PyExc_IndexError, "list index out of range (PAF line with fewer than 12 columns)"); goto done; }
-        if (parse_int(col[1], &r.qlen) || parse_int(col[2], &r.qstart) || parse_int(col[3], &r.qend) || parse_int(col[7], &r.tstart) ||
-            parse_int(col[8], &r.tend) || parse_int(col[10], &blocklen) || parse_int(col[11], &r.mapq)) {
-            PyErr_SetString(PyExc_ValueError, "PAF line with a non-integer coordinate column");
+        if (has_as) {
+            /* int(conv_type(val, c[type])): an 'f' value goes through float first (paf.py:62,93-99) */
+            const span_t val = as_val;
+            int ok = 0;
+            if (as_typ == 'f') {
+                span_t v = strip_span(val);
+                char buf[64];
+                if (v.n > 0 && v.n < (Py_ssize_t)sizeof buf) {
+                    memcpy(buf, v.p, (size_t)v.n);
+                    buf[v.n] = 0;
+                    char* end = NULL;
+                    const double d = PyOS_string_to_double(buf, &end, NULL);
+                    if (!(d == -1.0 && PyErr_Occurred()) && end == buf + v.n) {
+                        if (d != d) { PyErr_SetString(PyExc_ValueError, "cannot convert float NaN to integer"); goto done; }
+                        if (d > 9.2e18 || d < -9.2e18) { PyErr_SetString(PyExc_OverflowError, "cannot convert float infinity to integer"); goto done; }
+                        as = (long long)d;               /* truncation toward zero, like int(float) */
+                        ok = 1;
+                    } else {
+                        PyErr_Clear();
+                    }
+                }
+            }
+            if (!ok && parse_int(val, &as) != 0) { PyErr_SetString(PyExc_ValueError, "AS tag is not an integer"); goto done; }
+        }
+
+        /* conv_type keeps a column that is not an integer as a string; upstream only trips over it where the value is used:
+         * the block length in the filter below (TypeError: str < int), mapq when several records of a read compete, the
+         * coordinates when the record wins. Same here: remember what is unusable, complain when it is needed. */
+        if (parse_int(col[10], &blocklen)) {
+            PyErr_SetString(PyExc_TypeError, "'<' not supported between instances of 'str' and 'int' (alignment block length column)");
             goto done;
         }
+        if (parse_int(col[1], &r.qlen) | parse_int(col[2], &r.qstart) | parse_int(col[3], &r.qend) | parse_int(col[7], &r.tstart) |
+            parse_int(col[8], &r.tend))
+            r.bad |= 1;
+        if (parse_int(col[11], &r.mapq)) r.bad |= 2;
         r.rev = !(col[4].n == 1 && col[4].p[0] == '+');
         r.tname = col[5];
         r.as = as;
@@ -356,6 +401,9 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                 for (Py_ssize_t x = recs[w].next; x >= 0; x = recs[x].next)
                     if (recs[x].mapq > recs[w].mapq || (recs[x].mapq == recs[w].mapq && recs[x].as >= recs[w].as)) w = x;
             }
+            if (grps[g].count > 1)
+                for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next)
+                    if (recs[x].bad & 2) { PyErr_SetString(PyExc_ValueError, "mapq column is not an integer (np.array of (mapq, AS) upstream)"); goto done; }
             const rec_t* r = &recs[w];
             PyObject* tn = name_object(r->tname);
             if (!tn) goto done;
@@ -367,9 +415,9 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                 continue;
             }
             const long long ki = PyLong_AsLongLong(k);
+            if (r->bad & 1) { PyErr_SetString(PyExc_ValueError, "PAF record with a non-integer coordinate column"); goto done; }
             PyObject* s = PyDict_GetItemWithError(seqs, grps[g].qname);    /* borrowed; KeyError like seqs[rec.qname] */
             if (!s) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, grps[g].qname); goto done; }
-            if (!r->has_cigar) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); goto done; }   /* sequences.py:718 */
             if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "reads must be str"); goto done; }
             Py_ssize_t slen = 0;
             const char* sptr = PyUnicode_AsUTF8AndSize(s, &slen);
@@ -387,6 +435,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                 PyErr_SetString(PyExc_ValueError, "negative query coordinates");
                 goto done;
             }
+            if (!r->has_cigar) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); goto done; }   /* sequences.py:718, after the slicing */
             if (r->rev) {                                                   /* Q12, as in convert() above */
                 const long long a = r->qlen - r->qend, b = r->qlen - r->qstart;
                 lo = len - (b < len ? b : len); if (lo < 0) lo = 0;

@@ -151,8 +151,13 @@ class CoverageConverter:
                 # (sequences.py:707-711; Q12): rc[a:b] == revcomp(s[n-b:n-a]), with Python's slice clamping
                 n = len(s)
                 a, b = rec.qlen - rec.qend, rec.qlen - rec.qstart
+                if a < 0 or b < 0 or rec.qstart < 0 or rec.qend < 0:
+                    # qend beyond qlen: upstream's slice would wrap around from the end of the read; not a mapping
+                    raise ValueError("negative query coordinates")
                 lo, hi = max(n - min(b, n), 0), max(n - min(a, n), 0)
             else:
+                if rec.qstart < 0 or rec.qend < 0:
+                    raise ValueError("negative query coordinates")
                 lo, hi = min(rec.qstart, len(s)), min(rec.qend, len(s))
             cig = rec.cigar
             assert cig is not None
