@@ -217,32 +217,39 @@ static PyObject* name_object(span_t s) {
     return PyUnicode_FromStringAndSize(s.p, s.n);
 }
 
-static PyObject* convert_text(PyObject* self, PyObject* args) {
-    PyObject *text, *seqs, *contig_index, *best_index, *barcodes, *bufs, *keep;
-    long long min_len;
-    if (!PyArg_ParseTuple(args, "UO!O!LOOO!O!", &text, &PyDict_Type, &seqs, &PyDict_Type, &contig_index, &min_len, &barcodes,
-                          &best_index, &PyTuple_Type, &bufs, &PyList_Type, &keep))
-        return NULL;
-    if (barcodes != Py_None && !PyDict_Check(barcodes)) { PyErr_SetString(PyExc_TypeError, "barcodes must be a dict or None"); return NULL; }
-    if (PyTuple_GET_SIZE(bufs) != 10) { PyErr_SetString(PyExc_ValueError, "expected 10 output buffers"); return NULL; }
+/* every surviving record of one PAF text, grouped by read in order of first appearance */
+typedef struct {
+    rec_t* recs; grp_t* grps; PyObject* gindex;      /* gindex: {qname: group number} */
+    Py_ssize_t n_rec, n_grp;
+} paf_table_t;
+
+static void table_free(paf_table_t* T) {
+    for (Py_ssize_t g = 0; g < T->n_grp; ++g) Py_XDECREF(T->grps[g].qname);
+    Py_XDECREF(T->gindex);
+    PyMem_Free(T->recs);
+    PyMem_Free(T->grps);
+    memset(T, 0, sizeof *T);
+}
+
+/* pass 1: tokenise every line, filter, group by read. 0 = ok, -1 = Python error set (the caller frees the table). */
+static int tokenise_paf(PyObject* text, long long min_len, paf_table_t* T) {
+    memset(T, 0, sizeof *T);
     Py_ssize_t tlen = 0;
     const char* tp = PyUnicode_AsUTF8AndSize(text, &tlen);
-    if (!tp) return NULL;
-    if (tlen != PyUnicode_GET_LENGTH(text)) { PyErr_SetString(PyExc_ValueError, "PAF text must be ASCII"); return NULL; }
-
+    if (!tp) return -1;
+    if (tlen != PyUnicode_GET_LENGTH(text)) { PyErr_SetString(PyExc_ValueError, "PAF text must be ASCII"); return -1; }
     Py_ssize_t n_lines = 0;
     for (const char* q = tp; (q = (const char*)memchr(q, '\n', (size_t)(tp + tlen - q))) != NULL; ++q) ++n_lines;
     if (tlen > 0 && tp[tlen - 1] != '\n') ++n_lines;
-
-    rec_t* recs = (rec_t*)PyMem_Malloc(sizeof(rec_t) * (size_t)(n_lines ? n_lines : 1));
-    grp_t* grps = (grp_t*)PyMem_Malloc(sizeof(grp_t) * (size_t)(n_lines ? n_lines : 1));
-    PyObject* gindex = PyDict_New();
-    Py_ssize_t n_rec = 0, n_grp = 0;
-    Py_buffer vb[10];
-    int got = 0;
-    PyObject* result = NULL;
-    if (!recs || !grps || !gindex) { PyErr_NoMemory(); goto done; }
-
+    T->recs = (rec_t*)PyMem_Malloc(sizeof(rec_t) * (size_t)(n_lines ? n_lines : 1));
+    T->grps = (grp_t*)PyMem_Malloc(sizeof(grp_t) * (size_t)(n_lines ? n_lines : 1));
+    T->gindex = PyDict_New();
+    if (!T->recs || !T->grps || !T->gindex) { PyErr_NoMemory(); return -1; }
+    rec_t* const recs = T->recs;
+    grp_t* const grps = T->grps;
+    PyObject* const gindex = T->gindex;
+#define n_rec (T->n_rec)
+#define n_grp (T->n_grp)
     /* ---- pass 1: tokenise every line, filter, group by read ---- */
     for (Py_ssize_t pos = 0; pos < tlen;) {
         const char* nl = (const char*)memchr(tp + pos, '\n', (size_t)(tlen - pos));
@@ -281,13 +288,13 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                     }
                     if (colons != 2) {
                         PyErr_SetString(PyExc_ValueError, colons < 2 ? "not enough values to unpack (expected 3)" : "too many values to unpack (expected 3)");
-                        goto done;
+                        return -1;
                     }
                     span_t key = {f.p, a}, typ = {f.p + a + 1, b - a - 1}, val = {f.p + b + 1, f.n - b - 1};
                     if (typ.n != 1 || !(typ.p[0] == 'i' || typ.p[0] == 'A' || typ.p[0] == 'f' || typ.p[0] == 'Z')) {
                         PyObject* ko = PyUnicode_FromStringAndSize(typ.p, typ.n);
                         if (ko) { PyErr_SetObject(PyExc_KeyError, ko); Py_DECREF(ko); }
-                        goto done;
+                        return -1;
                     }
                     if (key.n == 2 && key.p[0] == 'A' && key.p[1] == 'S') {
                         as_val = val; as_typ = typ.p[0]; has_as = 1;      /* a repeated key keeps its LAST value (dict) */
@@ -303,7 +310,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                 if (i == line.n) break;
             }
         }
-        if (nc < 12) { PyErr_SetString(PyExc_IndexError, "list index out of range (PAF line with fewer than 12 columns)"); goto done; }
+        if (nc < 12) { PyErr_SetString(PyExc_IndexError, "list index out of range (PAF line with fewer than 12 columns)"); return -1; }
         if (has_as) {
             /* int(conv_type(val, c[type])): an 'f' value goes through float first (paf.py:62,93-99) */
             const span_t val = as_val;
@@ -317,8 +324,8 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                     char* end = NULL;
                     const double d = PyOS_string_to_double(buf, &end, NULL);
                     if (!(d == -1.0 && PyErr_Occurred()) && end == buf + v.n) {
-                        if (d != d) { PyErr_SetString(PyExc_ValueError, "cannot convert float NaN to integer"); goto done; }
-                        if (d > 9.2e18 || d < -9.2e18) { PyErr_SetString(PyExc_OverflowError, "cannot convert float infinity to integer"); goto done; }
+                        if (d != d) { PyErr_SetString(PyExc_ValueError, "cannot convert float NaN to integer"); return -1; }
+                        if (d > 9.2e18 || d < -9.2e18) { PyErr_SetString(PyExc_OverflowError, "cannot convert float infinity to integer"); return -1; }
                         as = (long long)d;               /* truncation toward zero, like int(float) */
                         ok = 1;
                     } else {
@@ -326,7 +333,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
                     }
                 }
             }
-            if (!ok && parse_int(val, &as) != 0) { PyErr_SetString(PyExc_ValueError, "AS tag is not an integer"); goto done; }
+            if (!ok && parse_int(val, &as) != 0) { PyErr_SetString(PyExc_ValueError, "AS tag is not an integer"); return -1; }
         }
 
         /* conv_type keeps a column that is not an integer as a string; upstream only trips over it where the value is used:
@@ -334,7 +341,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
          * coordinates when the record wins. Same here: remember what is unusable, complain when it is needed. */
         if (parse_int(col[10], &blocklen)) {
             PyErr_SetString(PyExc_TypeError, "'<' not supported between instances of 'str' and 'int' (alignment block length column)");
-            goto done;
+            return -1;
         }
         if (parse_int(col[1], &r.qlen) | parse_int(col[2], &r.qstart) | parse_int(col[3], &r.qend) | parse_int(col[7], &r.tstart) |
             parse_int(col[8], &r.tend))
@@ -345,9 +352,9 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
         r.as = as;
         if (blocklen < min_len || !primary) continue;              /* paf.py:664-669 */
         PyObject* qn = name_object(col[0]);
-        if (!qn) goto done;
+        if (!qn) return -1;
         PyObject* gi = PyDict_GetItemWithError(gindex, qn);         /* borrowed */
-        if (!gi && PyErr_Occurred()) { Py_DECREF(qn); goto done; }
+        if (!gi && PyErr_Occurred()) { Py_DECREF(qn); return -1; }
         Py_ssize_t g;
         if (gi) {
             g = PyLong_AsSsize_t(gi);
@@ -358,7 +365,7 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
         } else {
             g = n_grp++;
             PyObject* go = PyLong_FromSsize_t(g);
-            if (!go || PyDict_SetItem(gindex, qn, go) < 0) { Py_XDECREF(go); Py_DECREF(qn); --n_grp; goto done; }
+            if (!go || PyDict_SetItem(gindex, qn, go) < 0) { Py_XDECREF(go); Py_DECREF(qn); --n_grp; return -1; }
             Py_DECREF(go);
             grps[g].first = grps[g].last = n_rec;
             grps[g].count = 1;
@@ -367,99 +374,146 @@ static PyObject* convert_text(PyObject* self, PyObject* args) {
         recs[n_rec++] = r;
     }
 
-    /* ---- pass 2: winner of every read -> the ten arrays ---- */
-    {
-        static const Py_ssize_t item[10] = {4, 8, 8, 4, 1, 8, 8, 8, 8, 8};
-        Py_ssize_t cap = 0;          /* entries the caller's buffers hold: len(seqs) always suffices (every used read is a key of seqs) */
-        for (; got < 10; ++got) {
-            if (PyObject_GetBuffer(PyTuple_GET_ITEM(bufs, got), &vb[got], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) goto done;
-            const Py_ssize_t c = vb[got].len / item[got];
-            if (got == 0 || c < cap) cap = c;
-        }
-        int32_t* o_contig = (int32_t*)vb[0].buf;   int64_t* o_tstart = (int64_t*)vb[1].buf;  int64_t* o_tend = (int64_t*)vb[2].buf;
-        int32_t* o_bc = (int32_t*)vb[3].buf;       uint8_t* o_rev = (uint8_t*)vb[4].buf;     uint64_t* o_cp = (uint64_t*)vb[5].buf;
-        int64_t* o_cl = (int64_t*)vb[6].buf;       uint64_t* o_sp = (uint64_t*)vb[7].buf;    int64_t* o_sf = (int64_t*)vb[8].buf;
-        int64_t* o_st = (int64_t*)vb[9].buf;
-        Py_ssize_t n = 0, skipped = 0;
-        if (n_grp > 0 && PyList_Append(keep, text) < 0) goto done;  /* the CIGAR pointers live inside the text */
-        for (Py_ssize_t g = 0; g < n_grp; ++g) {
-            Py_ssize_t w = grps[g].first;
-            if (grps[g].count > 16) {
-                PyObject* keys = PyList_New(grps[g].count);
-                if (!keys) goto done;
-                Py_ssize_t k = 0;
-                for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next, ++k)
-                    PyList_SET_ITEM(keys, k, Py_BuildValue("(LL)", recs[x].mapq, recs[x].as));
-                PyObject* bi = PyObject_CallOneArg(best_index, keys);
-                Py_DECREF(keys);
-                if (!bi) goto done;
-                Py_ssize_t want = PyLong_AsSsize_t(bi);
-                Py_DECREF(bi);
-                if (want < 0 || want >= grps[g].count) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "best_index out of range"); goto done; }
-                for (k = 0; k < want; ++k) w = recs[w].next;
-            } else {
-                for (Py_ssize_t x = recs[w].next; x >= 0; x = recs[x].next)
-                    if (recs[x].mapq > recs[w].mapq || (recs[x].mapq == recs[w].mapq && recs[x].as >= recs[w].as)) w = x;
-            }
-            if (grps[g].count > 1)
-                for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next)
-                    if (recs[x].bad & 2) { PyErr_SetString(PyExc_ValueError, "mapq column is not an integer (np.array of (mapq, AS) upstream)"); goto done; }
-            const rec_t* r = &recs[w];
-            PyObject* tn = name_object(r->tname);
-            if (!tn) goto done;
-            PyObject* k = PyDict_GetItemWithError(contig_index, tn);      /* borrowed */
-            Py_DECREF(tn);
-            if (!k) {
-                if (PyErr_Occurred()) goto done;
-                ++skipped;                                                  /* core.py:83-86 */
-                continue;
-            }
-            const long long ki = PyLong_AsLongLong(k);
-            if (r->bad & 1) { PyErr_SetString(PyExc_ValueError, "PAF record with a non-integer coordinate column"); goto done; }
-            PyObject* s = PyDict_GetItemWithError(seqs, grps[g].qname);    /* borrowed; KeyError like seqs[rec.qname] */
-            if (!s) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, grps[g].qname); goto done; }
-            if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "reads must be str"); goto done; }
-            Py_ssize_t slen = 0;
-            const char* sptr = PyUnicode_AsUTF8AndSize(s, &slen);
-            if (!sptr) goto done;
-            if (slen != PyUnicode_GET_LENGTH(s)) { PyErr_SetString(PyExc_ValueError, "read and CIGAR strings must be ASCII"); goto done; }
-            long long bc = 0;
-            if (barcodes != Py_None) {
-                PyObject* bo = PyDict_GetItemWithError(barcodes, grps[g].qname);
-                if (!bo && PyErr_Occurred()) goto done;
-                if (bo && bo != Py_None) { bc = PyLong_AsLongLong(bo); if (bc == -1 && PyErr_Occurred()) goto done; }
-            }
-            long long lo, hi;
-            const long long len = (long long)slen;
-            if (r->qstart < 0 || r->qend < 0 || r->qlen - r->qend < 0 && r->rev || r->qlen - r->qstart < 0 && r->rev) {
-                PyErr_SetString(PyExc_ValueError, "negative query coordinates");
-                goto done;
-            }
-            if (!r->has_cigar) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); goto done; }   /* sequences.py:718, after the slicing */
-            if (r->rev) {                                                   /* Q12, as in convert() above */
-                const long long a = r->qlen - r->qend, b = r->qlen - r->qstart;
-                lo = len - (b < len ? b : len); if (lo < 0) lo = 0;
-                hi = len - (a < len ? a : len); if (hi < 0) hi = 0;
-            } else {
-                lo = clampll(r->qstart, 0, len);
-                hi = clampll(r->qend, 0, len);
-            }
-            if (hi < lo) hi = lo;
-            if (n >= cap) { PyErr_SetString(PyExc_ValueError, "output buffer too small"); goto done; }
-            o_contig[n] = (int32_t)ki; o_tstart[n] = r->tstart; o_tend[n] = r->tend; o_bc[n] = (int32_t)bc; o_rev[n] = (uint8_t)r->rev;
-            o_cp[n] = (uint64_t)(uintptr_t)r->cigar.p; o_cl[n] = (int64_t)r->cigar.n;
-            o_sp[n] = (uint64_t)(uintptr_t)sptr; o_sf[n] = lo; o_st[n] = hi;
-            if (PyList_Append(keep, s) < 0) goto done;
-            ++n;
-        }
-        result = Py_BuildValue("nnn", n, skipped, n_grp);
+#undef n_rec
+#undef n_grp
+    return 0;
+}
+
+/* Paf.choose_best_mapper over group g (paf.py:710-722): index of the winning record, -1 = Python error set */
+static Py_ssize_t pick_winner(const paf_table_t* T, Py_ssize_t g, PyObject* best_index) {
+    const rec_t* recs = T->recs;
+    const grp_t* grps = T->grps;
+    Py_ssize_t w = grps[g].first;
+    if (grps[g].count > 16) {
+        PyObject* keys = PyList_New(grps[g].count);
+        if (!keys) return -1;
+        Py_ssize_t k = 0;
+        for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next, ++k)
+            PyList_SET_ITEM(keys, k, Py_BuildValue("(LL)", recs[x].mapq, recs[x].as));
+        PyObject* bi = PyObject_CallOneArg(best_index, keys);
+        Py_DECREF(keys);
+        if (!bi) return -1;
+        Py_ssize_t want = PyLong_AsSsize_t(bi);
+        Py_DECREF(bi);
+        if (want < 0 || want >= grps[g].count) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "best_index out of range"); return -1; }
+        for (k = 0; k < want; ++k) w = recs[w].next;
+    } else {
+        for (Py_ssize_t x = recs[w].next; x >= 0; x = recs[x].next)
+            if (recs[x].mapq > recs[w].mapq || (recs[x].mapq == recs[w].mapq && recs[x].as >= recs[w].as)) w = x;
     }
+    if (grps[g].count > 1)
+        for (Py_ssize_t x = grps[g].first; x >= 0; x = recs[x].next)
+            if (recs[x].bad & 2) { PyErr_SetString(PyExc_ValueError, "mapq column is not an integer (np.array of (mapq, AS) upstream)"); return -1; }
+    return w;
+}
+
+/* the ten caller-provided arrays of a batch */
+typedef struct {
+    Py_buffer vb[10];
+    int got;
+    Py_ssize_t cap, n;        /* entries the buffers hold / entries written */
+} out_t;
+
+static int out_open(PyObject* bufs, out_t* O) {
+    static const Py_ssize_t item[10] = {4, 8, 8, 4, 1, 8, 8, 8, 8, 8};
+    O->got = 0; O->cap = 0; O->n = 0;
+    if (PyTuple_GET_SIZE(bufs) != 10) { PyErr_SetString(PyExc_ValueError, "expected 10 output buffers"); return -1; }
+    for (; O->got < 10; ++O->got) {
+        if (PyObject_GetBuffer(PyTuple_GET_ITEM(bufs, O->got), &O->vb[O->got], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) return -1;
+        const Py_ssize_t c = O->vb[O->got].len / item[O->got];
+        if (O->got == 0 || c < O->cap) O->cap = c;
+    }
+    return 0;
+}
+
+static void out_close(out_t* O) {
+    for (int i = 0; i < O->got; ++i) PyBuffer_Release(&O->vb[i]);
+    O->got = 0;
+}
+
+static int barcode_of(PyObject* barcodes, PyObject* qname, long long* bc) {
+    *bc = 0;
+    if (barcodes == Py_None) return 0;
+    PyObject* bo = PyDict_GetItemWithError(barcodes, qname);
+    if (!bo) return PyErr_Occurred() ? -1 : 0;
+    if (bo != Py_None) { *bc = PyLong_AsLongLong(bo); if (*bc == -1 && PyErr_Occurred()) return -1; }
+    return 0;
+}
+
+/* One winning record -> one row of the batch (the body of upstream's convert_records loop, sequences.py:700-738, minus the
+ * CIGAR walk). 1 = written, 0 = its target is not tracked (core.py:83-86), -1 = Python error set. */
+static int emit_record(const rec_t* r, PyObject* qname, PyObject* seqs, PyObject* contig_index, PyObject* barcodes, out_t* O, PyObject* keep) {
+    PyObject* tn = name_object(r->tname);
+    if (!tn) return -1;
+    PyObject* k = PyDict_GetItemWithError(contig_index, tn);      /* borrowed */
+    Py_DECREF(tn);
+    if (!k) return PyErr_Occurred() ? -1 : 0;
+    const long long ki = PyLong_AsLongLong(k);
+    if (r->bad & 1) { PyErr_SetString(PyExc_ValueError, "PAF record with a non-integer coordinate column"); return -1; }
+    PyObject* s = PyDict_GetItemWithError(seqs, qname);           /* borrowed; KeyError like seqs[rec.qname] */
+    if (!s) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, qname); return -1; }
+    if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "reads must be str"); return -1; }
+    Py_ssize_t slen = 0;
+    const char* sptr = PyUnicode_AsUTF8AndSize(s, &slen);
+    if (!sptr) return -1;
+    if (slen != PyUnicode_GET_LENGTH(s)) { PyErr_SetString(PyExc_ValueError, "read and CIGAR strings must be ASCII"); return -1; }
+    long long bc = 0;
+    if (barcode_of(barcodes, qname, &bc) < 0) return -1;
+    long long lo, hi;
+    const long long len = (long long)slen;
+    if (r->qstart < 0 || r->qend < 0 || (r->rev && (r->qlen - r->qend < 0 || r->qlen - r->qstart < 0))) {
+        PyErr_SetString(PyExc_ValueError, "negative query coordinates");
+        return -1;
+    }
+    if (!r->has_cigar) { PyErr_SetString(PyExc_AssertionError, "record without a cg:Z: CIGAR"); return -1; }   /* sequences.py:718, after the slicing */
+    if (r->rev) {                                                   /* Q12, as in convert() above */
+        const long long a = r->qlen - r->qend, b = r->qlen - r->qstart;
+        lo = len - (b < len ? b : len); if (lo < 0) lo = 0;
+        hi = len - (a < len ? a : len); if (hi < 0) hi = 0;
+    } else {
+        lo = clampll(r->qstart, 0, len);
+        hi = clampll(r->qend, 0, len);
+    }
+    if (hi < lo) hi = lo;
+    const Py_ssize_t n = O->n;
+    if (n >= O->cap) { PyErr_SetString(PyExc_ValueError, "output buffer too small"); return -1; }
+    ((int32_t*)O->vb[0].buf)[n] = (int32_t)ki;   ((int64_t*)O->vb[1].buf)[n] = r->tstart;   ((int64_t*)O->vb[2].buf)[n] = r->tend;
+    ((int32_t*)O->vb[3].buf)[n] = (int32_t)bc;   ((uint8_t*)O->vb[4].buf)[n] = (uint8_t)r->rev;
+    ((uint64_t*)O->vb[5].buf)[n] = (uint64_t)(uintptr_t)r->cigar.p;   ((int64_t*)O->vb[6].buf)[n] = (int64_t)r->cigar.n;
+    ((uint64_t*)O->vb[7].buf)[n] = (uint64_t)(uintptr_t)sptr;   ((int64_t*)O->vb[8].buf)[n] = lo;   ((int64_t*)O->vb[9].buf)[n] = hi;
+    if (PyList_Append(keep, s) < 0) return -1;
+    O->n = n + 1;
+    return 1;
+}
+
+static PyObject* convert_text(PyObject* self, PyObject* args) {
+    PyObject *text, *seqs, *contig_index, *best_index, *barcodes, *bufs, *keep;
+    long long min_len;
+    if (!PyArg_ParseTuple(args, "UO!O!LOOO!O!", &text, &PyDict_Type, &seqs, &PyDict_Type, &contig_index, &min_len, &barcodes,
+                          &best_index, &PyTuple_Type, &bufs, &PyList_Type, &keep))
+        return NULL;
+    if (barcodes != Py_None && !PyDict_Check(barcodes)) { PyErr_SetString(PyExc_TypeError, "barcodes must be a dict or None"); return NULL; }
+    if (PyTuple_GET_SIZE(bufs) != 10) { PyErr_SetString(PyExc_ValueError, "expected 10 output buffers"); return NULL; }
+    paf_table_t T;
+    out_t O;
+    O.got = 0;
+    PyObject* result = NULL;
+    Py_ssize_t skipped = 0;
+    if (tokenise_paf(text, min_len, &T) < 0) goto done;
+    /* pass 2: winner of every read -> the ten arrays (len(seqs) entries always suffice: every used read is a key of seqs) */
+    if (out_open(bufs, &O) < 0) goto done;
+    if (T.n_grp > 0 && PyList_Append(keep, text) < 0) goto done;    /* the CIGAR pointers live inside the text */
+    for (Py_ssize_t g = 0; g < T.n_grp; ++g) {
+        const Py_ssize_t w = pick_winner(&T, g, best_index);
+        if (w < 0) goto done;
+        const int rc = emit_record(&T.recs[w], T.grps[g].qname, seqs, contig_index, barcodes, &O, keep);
+        if (rc < 0) goto done;
+        if (rc == 0) ++skipped;
+    }
+    result = Py_BuildValue("nnn", O.n, skipped, T.n_grp);
 done:
-    for (int i = 0; i < got; ++i) PyBuffer_Release(&vb[i]);
-    for (Py_ssize_t g = 0; g < n_grp; ++g) Py_XDECREF(grps[g].qname);
-    Py_XDECREF(gindex);
-    PyMem_Free(recs);
-    PyMem_Free(grps);
+    out_close(&O);
+    table_free(&T);
     return result;
 }
 
