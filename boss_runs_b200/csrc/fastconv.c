@@ -517,10 +517,152 @@ done:
     return result;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * decide_text — the simulator's decision step and the batch it produces, straight from the two PAF texts.
+ *
+ * BossRunsSim.make_decisions + filter_paf_dict + convert_records (boss/runs/simulation.py:37-135,160-163): for every read
+ * with a mu-sized mapping the winning truncated record is looked up in the current strategy
+ * (strat[start // window, rev, barcode]; NumPy's index rules: negative indices wrap, out of range or no strategy for the
+ * target -> reject); accepted reads contribute their winning FULL-length record, rejected ones the truncated record (and
+ * only their first mu bases count later, Q12); reads without a mu-sized mapping are accepted or rejected wholesale.
+ * Semantics pinned by tests/test_simulation.py against boss_runs_b200/simulation.py:make_decisions, which is itself pinned
+ * against upstream's function on the reference's data.
+ *
+ * decide_text(paf_full, paf_trunc, seqs, contig_index, barcodes, strat, window, mu, accept_unmapped, best_index, bufs, keep,
+ *             row_accepted)
+ *   -> (n_rows, n_skipped, mapped: list[str], rejected: list[str], accepted_qlen: list[int], n_accepted, n_rejected)
+ * row_accepted: writable u8 buffer, one flag per emitted row (1 = the row is an accepted read: record length != mu).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static long long floordiv(long long a, long long b) { long long q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+/* strat[row, rev, bc] under NumPy's rules; 0 when anything is out of range or the array is not 3-d (reject refs hold zeros(1)) */
+static int strat_bit(PyObject* arr, long long row, int rev, long long bc) {
+    Py_buffer v;
+    if (PyObject_GetBuffer(arr, &v, PyBUF_STRIDES | PyBUF_FORMAT) < 0) { PyErr_Clear(); return 0; }
+    int d = 0;
+    if (v.ndim == 3 && v.itemsize == 1 && v.shape[1] == 2) {
+        const long long rows = v.shape[0], nb = v.shape[2];
+        if (row < 0) row += rows;
+        if (bc < 0) bc += nb;
+        if (row >= 0 && row < rows && bc >= 0 && bc < nb)
+            d = ((const unsigned char*)v.buf)[row * v.strides[0] + (long long)rev * v.strides[1] + bc * v.strides[2]] != 0;
+    }
+    PyBuffer_Release(&v);
+    return d;
+}
+
+static PyObject* decide_text(PyObject* self, PyObject* args) {
+    PyObject *full, *trunc, *seqs, *contig_index, *barcodes, *strat, *best_index, *bufs, *keep, *rowacc;
+    long long window, mu;
+    int accept_unmapped;
+    if (!PyArg_ParseTuple(args, "UUO!O!O!O!LLpOO!O!O", &full, &trunc, &PyDict_Type, &seqs, &PyDict_Type, &contig_index, &PyDict_Type, &barcodes,
+                          &PyDict_Type, &strat, &window, &mu, &accept_unmapped, &best_index, &PyTuple_Type, &bufs, &PyList_Type, &keep, &rowacc))
+        return NULL;
+    if (window <= 0) { PyErr_SetString(PyExc_ValueError, "window must be positive"); return NULL; }
+    paf_table_t F, T;
+    memset(&F, 0, sizeof F); memset(&T, 0, sizeof T);
+    out_t O;
+    O.got = 0;
+    Py_buffer ra;
+    int have_ra = 0;
+    PyObject *result = NULL, *mapped = PyList_New(0), *rejected = PyList_New(0), *acc_qlen = PyList_New(0);
+    Py_ssize_t skipped = 0, n_acc = 0, n_rej = 0;
+    if (!mapped || !rejected || !acc_qlen) goto done;
+    if (tokenise_paf(full, 1, &F) < 0 || tokenise_paf(trunc, 1, &T) < 0) goto done;       /* make_decisions parses with min_len = 1 */
+    if (out_open(bufs, &O) < 0) goto done;
+    if (PyObject_GetBuffer(rowacc, &ra, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) goto done;
+    have_ra = 1;
+    if (PyList_Append(keep, full) < 0 || PyList_Append(keep, trunc) < 0) goto done;       /* CIGAR pointers live inside the texts */
+    for (Py_ssize_t g = 0; g < T.n_grp; ++g) {
+        PyObject* qn = T.grps[g].qname;
+        const Py_ssize_t w = pick_winner(&T, g, best_index);
+        if (w < 0) goto done;
+        const rec_t* r = &T.recs[w];
+        PyObject* bo = PyDict_GetItemWithError(barcodes, qn);                              /* rec.barcode = barcodes[rec.qname] */
+        if (!bo) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, qn); goto done; }
+        const long long bc = PyLong_AsLongLong(bo);
+        if (bc == -1 && PyErr_Occurred()) goto done;
+        if (PyList_Append(mapped, qn) < 0) goto done;
+        if (r->bad & 1) { PyErr_SetString(PyExc_ValueError, "PAF record with a non-integer coordinate column"); goto done; }
+        int decision = 0;
+        {
+            PyObject* tn = name_object(r->tname);
+            if (!tn) goto done;
+            PyObject* arr = PyDict_GetItemWithError(strat, tn);                            /* borrowed; missing -> KeyError -> reject */
+            Py_DECREF(tn);
+            if (!arr && PyErr_Occurred()) goto done;
+            if (arr) decision = strat_bit(arr, floordiv(r->rev ? r->tend - 1 : r->tstart, window), r->rev ? 1 : 0, bc);
+        }
+        const rec_t* use = r;
+        if (decision) {
+            PyObject* gi = PyDict_GetItemWithError(F.gindex, qn);
+            if (!gi) {
+                if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "index -1 is out of bounds for axis 0 with size 0 (read without a full-length record)");
+                goto done;
+            }
+            const Py_ssize_t wf = pick_winner(&F, PyLong_AsSsize_t(gi), best_index);
+            if (wf < 0) goto done;
+            use = &F.recs[wf];
+            ++n_acc;
+        } else {
+            if (PyList_Append(rejected, qn) < 0) goto done;
+            ++n_rej;
+        }
+        const int is_acc = !(use->bad & 1) && use->qlen != mu;                             /* filter_paf_dict: record length != mu */
+        if (is_acc) {
+            PyObject* q = PyLong_FromLongLong(use->qlen);
+            if (!q || PyList_Append(acc_qlen, q) < 0) { Py_XDECREF(q); goto done; }
+            Py_DECREF(q);
+        }
+        const int rc = emit_record(use, qn, seqs, contig_index, barcodes, &O, keep);
+        if (rc < 0) goto done;
+        if (rc == 0) { ++skipped; continue; }
+        if (O.n > ra.len) { PyErr_SetString(PyExc_ValueError, "row_accepted buffer too small"); goto done; }
+        ((unsigned char*)ra.buf)[O.n - 1] = (unsigned char)is_acc;
+    }
+    if (accept_unmapped) {
+        /* reads without a mu-sized mapping that do have a full-length record join the batch (no barcode: index 0) */
+        PyObject *rid, *seq;
+        Py_ssize_t pos = 0;
+        while (PyDict_Next(seqs, &pos, &rid, &seq)) {
+            int in_t = PyDict_Contains(T.gindex, rid);
+            if (in_t < 0) goto done;
+            if (in_t) continue;
+            PyObject* gi = PyDict_GetItemWithError(F.gindex, rid);
+            if (!gi) { if (PyErr_Occurred()) goto done; continue; }
+            const Py_ssize_t wf = pick_winner(&F, PyLong_AsSsize_t(gi), best_index);
+            if (wf < 0) goto done;
+            const rec_t* use = &F.recs[wf];
+            const int is_acc = !(use->bad & 1) && use->qlen != mu;
+            if (is_acc) {
+                PyObject* q = PyLong_FromLongLong(use->qlen);
+                if (!q || PyList_Append(acc_qlen, q) < 0) { Py_XDECREF(q); goto done; }
+                Py_DECREF(q);
+            }
+            const int rc = emit_record(use, rid, seqs, contig_index, Py_None, &O, keep);
+            if (rc < 0) goto done;
+            if (rc == 0) { ++skipped; continue; }
+            if (O.n > ra.len) { PyErr_SetString(PyExc_ValueError, "row_accepted buffer too small"); goto done; }
+            ((unsigned char*)ra.buf)[O.n - 1] = (unsigned char)is_acc;
+        }
+    }
+    result = Py_BuildValue("nnOOOnn", O.n, skipped, mapped, rejected, acc_qlen, n_acc, n_rej);
+done:
+    if (have_ra) PyBuffer_Release(&ra);
+    out_close(&O);
+    table_free(&F);
+    table_free(&T);
+    Py_XDECREF(mapped); Py_XDECREF(rejected); Py_XDECREF(acc_qlen);
+    return result;
+}
+
 static PyMethodDef methods[] = {
     {"convert", convert, METH_VARARGS, "convert(paf_dict, seqs, contig_index, best_record, bufs, keep) -> (n_used, n_skipped)"},
     {"convert_text", convert_text, METH_VARARGS,
      "convert_text(paf_text, seqs, contig_index, min_len, barcodes, best_index, bufs, keep) -> (n_used, n_skipped, n_reads)"},
+    {"decide_text", decide_text, METH_VARARGS,
+     "decide_text(paf_full, paf_trunc, seqs, contig_index, barcodes, strat, window, mu, accept_unmapped, best_index, bufs, keep, row_accepted)"
+     " -> (n_rows, n_skipped, mapped, rejected, accepted_qlen, n_accepted, n_rejected)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_fastconv", "host half of the coverage update (C API walk)", -1, methods};

@@ -18,7 +18,7 @@ from io import StringIO
 import numpy as np
 
 from .hostmodel import choose_best_mapper, parse_PAF
-from .runs import BossRuns
+from .runs import BossRuns, PackedBatch, _best_index, _fastconv
 
 
 def _lookup(contigs_filt: dict, picks: list, barcodes: dict, window: int) -> np.ndarray:
@@ -97,12 +97,49 @@ def filter_paf_dict(paf_dict: dict, mu: int = 400) -> dict:
     return {rid: recs for rid, recs in paf_dict.items() if recs[0].qlen != mu}
 
 
+def decide_text(contig_index: dict, contigs_filt: dict, seqs: dict[str, str], paf_full: str, paf_trunc: str,
+                barcodes: dict[str, int], mu: int = 400, accept_unmapped: bool = False, window: int = 100):
+    """`make_decisions` + `filter_paf_dict` + `convert_records` in one C pass over the two PAF texts (csrc/fastconv.c
+    `decide_text`): no PafLine objects. Returns (batch, row_accepted, accepted_qlen, reads_decision, n_mapped, mapped,
+    n_accepted, n_rejected) where `batch` is the PackedBatch of every record of `paf_dict` on a tracked contig,
+    `row_accepted[i]` says whether row i belongs to an accepted read, and `accepted_qlen` lists the read lengths of all
+    accepted reads (tracked contig or not) for the read-length distribution. None if the helper is not built."""
+    fc = _fastconv()
+    if fc is None or not hasattr(fc, "decide_text"):
+        return None
+    n = len(seqs) + 1
+    contig, bc = np.empty(n, np.int32), np.empty(n, np.int32)
+    tstart, tend, cl, sf, st = (np.empty(n, np.int64) for _ in range(5))
+    rev, row_acc = np.empty(n, np.uint8), np.zeros(n, np.uint8)
+    cp, sp = np.empty(n, np.uint64), np.empty(n, np.uint64)
+    keep: list = []
+    strat = {name: np.asarray(c.strat) for name, c in contigs_filt.items()}
+    used, skipped, mapped, rejected, acc_qlen, n_acc, n_rej = fc.decide_text(
+        paf_full, paf_trunc, seqs, contig_index, barcodes, strat, int(window), int(mu), bool(accept_unmapped), _best_index,
+        (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st), keep, row_acc)
+    batch = PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
+                        sf[:used], st[:used], keep, skipped)
+    reads_decision = dict(seqs)
+    for rid in rejected:
+        reads_decision[rid] = reads_decision[rid][:mu]
+    mapped_set = set(mapped)
+    loose = [rid for rid in seqs if rid not in mapped_set]
+    if accept_unmapped:
+        n_acc += len(loose)
+    else:
+        for rid in loose:
+            reads_decision[rid] = seqs[rid][:mu]
+        n_rej += len(loose)
+    return batch, row_acc[:used].astype(bool), acc_qlen, reads_decision, len(mapped), mapped_set, n_acc, n_rej
+
+
 class BossRunsSim(BossRuns):
     """`BossRuns` driven by sampled reads with accept/reject decisions taken from the current strategy."""
 
-    def __init__(self, *args, accept_unmapped: bool = False, mu: int = 400, **kw):
+    def __init__(self, *args, accept_unmapped: bool = False, mu: int = 400, text_decisions: bool = True, **kw):
         super().__init__(*args, **kw)
         self.accept_unmapped, self.mu = accept_unmapped, mu
+        self.text_decisions = text_decisions           # decisions + batch in one C pass over the PAF texts (fastconv.decide_text)
         self.n_accepted = self.n_rejected = 0
 
     def make_decisions(self, seqs, paf_full, paf_trunc, barcodes, window: int = 100, all_read_ids=None):
@@ -119,6 +156,22 @@ class BossRunsSim(BossRuns):
         Q12), read starts from the accepted ones. Returns `reads_decision` for the caller's read cache."""
         self._prescore_begin()                                       # the GPU scores while the host decides and converts
         read_barcodes = {rid: self.barcodes_index.get(bc, 0) for rid, bc in read_barcodes_names.items()}
+        fast = decide_text(self.cc.contig_index, self.contigs_filt, read_seqs, paf_f, paf_t, read_barcodes, mu=self.mu,
+                           accept_unmapped=self.accept_unmapped) if self.text_decisions else None
+        if fast is not None:
+            b, row_acc, acc_qlen, reads_decision, n_mapped, mapped, n_acc, n_rej = fast
+            ids = set(read_seqs) if all_read_ids is None else all_read_ids
+            logging.info(f"mapped {n_mapped}, not mapped {len(ids - mapped)}")
+            logging.info(f"accepted {n_acc}, rejected {n_rej}")
+            self.n_accepted, self.n_rejected = n_acc, n_rej
+            self.rl_dist.update(read_lengths=dict(enumerate(acc_qlen)))
+            self._prescore(b)
+            self._effect_increments(increments=b)
+            wins, strands = self.read_starts.count_read_starts_arrays(b.contig[row_acc], b.tstart[row_acc], b.tend[row_acc], b.rev[row_acc])
+            self._read_starts_to_device(wins, strands)
+            self.update_wrapper()
+            self.batch += 1
+            return reads_decision
         paf_dict, reads_decision, n_mapped, n_unmapped, n_acc, n_rej = self.make_decisions(
             seqs=read_seqs, paf_full=paf_f, paf_trunc=paf_t, barcodes=read_barcodes, all_read_ids=all_read_ids)
         logging.info(f"mapped {n_mapped}, not mapped {n_unmapped}")

@@ -92,13 +92,14 @@ def test_simulated_flow_oracle_equals_reference():
 
 
 @pytest.mark.gpu
-def test_simulated_flow_gpu_equals_oracle(lib):
+@pytest.mark.parametrize("text_decisions", [False, True])
+def test_simulated_flow_gpu_equals_oracle(lib, text_decisions):
     """`BossRunsSim.process_batch_runs_sim` on the GPU against the oracle flow above, state by state, and against the
     reference's recorded strategies."""
     from boss_runs_b200.simulation import BossRunsSim
     g, all_ids, truncs = flow_inputs()
     orc = H.oracle_run(g.records, 1, [], None, 0)
-    sim = BossRunsSim(contigs=g.records, ploidy=1, bucket_threshold=0, write_debug=True)
+    sim = BossRunsSim(contigs=g.records, ploidy=1, bucket_threshold=0, write_debug=True, text_decisions=text_decisions)
     for bi, (paf, seqs, _) in enumerate(g.batches):
         updated, counts, acc, dec_o = H.oracle_sim_step(orc, seqs, paf, truncs[bi], {r: 0 for r in seqs}, all_ids)
         dec_p = sim.process_batch_runs_sim(seqs, None, {r: "" for r in seqs}, paf, truncs[bi], all_read_ids=all_ids)
@@ -108,3 +109,69 @@ def test_simulated_flow_gpu_equals_oracle(lib):
         H.compare_state(sim, orc, updated, f"sim/b{bi}")
         for name, c in sim.contigs_filt.items():
             assert np.array_equal(np.packbits(np.asarray(c.strat).ravel()), FLOW[f"b{bi}_{name}_strat"]), f"b{bi}/{name}"
+
+
+# ---- decisions + batch in one C pass over the PAF texts (fastconv.decide_text) --------------------------------------
+def _rows(b):
+    return [(int(b.contig[i]), int(b.tstart[i]), int(b.tend[i]), int(b.barcode[i]), int(b.rev[i]), b.cigar_bytes(i), b.slice_bytes(i))
+            for i in range(len(b))]
+
+
+@pytest.mark.parametrize("nb,accept_unmapped", [(1, False), (1, True), (3, False), (3, True)])
+def test_text_decisions_equal_object_decisions(nb, accept_unmapped):
+    """On the reference's real reads with their full-length and truncated records (CIGARs included), against seeded
+    strategies: the C pass yields the same batch rows, accepted flags, read lengths, truncations and counts as
+    `make_decisions` + `filter_paf_dict` + the Python `convert_records` loop."""
+    from boss_runs_b200 import build
+    from boss_runs_b200.runs import CoverageConverter
+    from boss_runs_b200.simulation import decide_text
+    build.build_fastconv()
+    g, all_ids, truncs = flow_inputs()
+    tracked = [n for n, s in g.records if len(s) >= 100_000]
+    lengths = {n: len(s) for n, s in g.records if n in tracked}
+    cc = CoverageConverter({n: i for i, n in enumerate(tracked[:1])})        # the second tracked contig is "not tracked" here
+    rng = np.random.default_rng(nb)
+    for bi, (paf, seqs, _) in enumerate(g.batches):
+        strat = strategies(lengths, nb, 20 + bi + nb)
+        contigs = {k: SimpleNamespace(strat=v) for k, v in strat.items()}
+        if bi == 1:
+            contigs[tracked[0]] = SimpleNamespace(strat=np.zeros(1, dtype=bool))     # a reject ref's zeros(1): IndexError upstream -> reject
+        barcodes = {r: int(rng.integers(nb)) for r in seqs}
+        paf_dict, dec, n_mapped, n_unmapped, n_acc, n_rej = make_decisions(
+            contigs, seqs, paf, truncs[bi], barcodes, accept_unmapped=accept_unmapped, all_read_ids=all_ids)
+        acc = filter_paf_dict(paf_dict)
+        want = cc._convert_records_py(paf_dict, seqs)
+        got = decide_text(cc.contig_index, contigs, seqs, paf, truncs[bi], barcodes, accept_unmapped=accept_unmapped)
+        assert got is not None
+        b, row_acc, acc_qlen, dec2, n_mapped2, mapped, n_acc2, n_rej2 = got
+        assert _rows(b) == _rows(want) and b.n_skipped == want.n_skipped and len(b) > 100
+        assert (n_mapped2, n_acc2, n_rej2) == (n_mapped, n_acc, n_rej) and len(all_ids - mapped) == n_unmapped
+        assert dec2 == dec
+        assert acc_qlen == [r[0].qlen for r in acc.values()]
+        on_tracked = [rid for rid, recs in paf_dict.items() if recs[0].tname in cc.contig_index]
+        assert row_acc.tolist() == [rid in acc for rid in on_tracked]
+        assert n_acc < len(seqs) and (n_acc > 0 or bi == 1)
+
+
+def test_text_decisions_errors_like_object_path():
+    from boss_runs_b200.runs import CoverageConverter
+    from boss_runs_b200.simulation import decide_text
+    line = "r1\t400\t0\t400\t+\tctg\t200000\t5000\t5400\t400\t400\t60\tAS:i:400\ttp:A:P\tcg:Z:400M\n"
+    contigs = {"ctg": SimpleNamespace(strat=np.ones((2000, 2, 1), dtype=bool))}
+    cc = CoverageConverter({"ctg": 0})
+    with pytest.raises(IndexError):                                 # accepted, but never mapped in full
+        decide_text(cc.contig_index, contigs, {"r1": "A" * 900}, "", line, {"r1": 0})
+    with pytest.raises(KeyError):                                   # barcodes[rec.qname]
+        decide_text(cc.contig_index, contigs, {"r1": "A" * 900}, line, line, {})
+    far = line.replace("\t5000\t5400\t", "\t250000\t250400\t")
+    b, row_acc, acc_qlen, dec, n_mapped, mapped, n_acc, n_rej = decide_text(cc.contig_index, contigs, {"r1": "A" * 900}, line, far, {"r1": 0})
+    assert (n_acc, n_rej, len(dec["r1"]), row_acc.tolist(), acc_qlen) == (0, 1, 400, [False], [])
+    # tend == 0 on the reverse strand: start = -1 -> row -1 wraps to the last row, like NumPy
+    wrap = line.replace("\t+\t", "\t-\t").replace("\t5000\t5400\t", "\t-400\t0\t")
+    last_off = {"ctg": SimpleNamespace(strat=np.ones((2000, 2, 1), dtype=bool))}
+    last_off["ctg"].strat[-1, 1, 0] = False
+    full900 = line.replace("r1\t400\t0\t400", "r1\t900\t0\t400")
+    for cont, want_acc in ((contigs, 1), (last_off, 0)):
+        pd, *_rest, a, r = make_decisions(cont, {"r1": "A" * 900}, full900, wrap, {"r1": 0})
+        got = decide_text(cc.contig_index, cont, {"r1": "A" * 900}, full900, wrap, {"r1": 0})
+        assert (a, got[6]) == (want_acc, want_acc)
