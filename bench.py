@@ -210,8 +210,7 @@ def run_b200(args, spec):
     from boss_runs_b200 import build, synth
     from boss_runs_b200.hostmodel import parse_PAF
     from boss_runs_b200.runs import BossRuns
-    from boss_runs_b200 import _lib
-
+    
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -288,6 +287,7 @@ def run_b200(args, spec):
             e2e_parts.append((t1 - t0, t1b - t1, t2 - t1b, time.perf_counter() - t2))
             # what the library staged and copied: per-read scalars + CIGAR op slots (4 B) + read bases packed 2 bits each
             h2d = sum(e.ingest_bytes() for e in getattr(run, "engines", [eng]))
+            h2d += 20 * len(inc) * len(getattr(run, "engines", [eng]))     # the announced intervals (contig i32, tstart/tend i64)
             # masks reach the host as the 4 KB chunks that changed (written by the distribution kernel into the
             # pinned mirror Contig.strat views) + bucket switches + the result record
             d2h = int(run.last.mirror_bytes) + int(sum(c.bucket_switches.size for c in run.contigs_filt.values())) + 256
