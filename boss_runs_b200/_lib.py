@@ -17,7 +17,7 @@ ABI_VERSION = 1
 BIN, BUCKET, RSD_WINDOW, FREEZE = 100, 20_000, 2000, 30
 N_PATTERNS, N_STEPS, HIST_BINS, N_TIMERS = 278_256, 10, 1088, 8
 
-OK, EINVAL, ECUDA, ENOMEM, EBASE, ESHAPE, ESTATE, EEMPTY, EPEER = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, EINVAL, ECUDA, ENOMEM, EBASE, ESHAPE, ESTATE, EEMPTY, EPEER, ENOTC = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 BUF_SWITCH, BUF_NORM, BUF_HIST, BUF_MASK, BUF_HALO_SEND, BUF_HALO_RECV, BUF_STRAT, BUF_COV_TOTAL = range(8)
 
 
@@ -107,6 +107,7 @@ SYMBOLS = {
     "bossgpu_get_buckets": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P]),
     "bossgpu_set_buckets": (C.c_int, [_P, C.c_int32, _P, C.c_int64]),
     "bossgpu_get_hist": (C.c_int, [_P, _P, _P]),
+    "bossgpu_get_fhat": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "bossgpu_get_score_table": (C.c_int, [_P, _P, _P]),
     "bossgpu_pattern_rank": (C.c_int64, [_P]),
     "bossgpu_timing": (C.c_int, [_P, _P]),
@@ -157,6 +158,8 @@ def check(rc: int) -> None:
         raise ValueError(msg)
     if rc == ENOMEM:
         raise MemoryError(msg)
+    if rc == ENOTC:
+        raise AttributeError("'ReadlengthDist' object has no attribute 'time_cost'")     # readlengthdist.py:68, core.py:192 (Q14)
     if rc == EPEER:
         raise PeerTimeout(msg)
     raise BossGpuError(f"libbossgpu error {rc}: {msg}")

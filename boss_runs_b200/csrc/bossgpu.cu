@@ -116,11 +116,9 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     h->score0 = cfg->score0_contig;
     h->ent0 = cfg->entropy0_contig;
     h->contig_len_all.assign(cfg->contig_len_all, cfg->contig_len_all + cfg->n_contigs_total);
-    {   // fhat * 2^shift summed over everything must stay below 2^63: sum(fhat) ~ nb (+ tail copies)
-        int lg = 0;
-        while ((1 << lg) < h->nb) ++lg;
-        h->fhat_shift = 60 - lg;
-    }
+    // F-hat terms enter the exact sums as fhat * 2^50 (strategy.cuh, to_limbs_small: one term stays below 2^51 since the
+    // normalised F-hat is <= 1; all of them together stay below 2^63: sum(fhat) = 1 per barcode plus tail copies)
+    h->fhat_shift = 50;
 
     // ---- global axes --------------------------------------------------------------------------
     std::vector<int64_t> o_row(h->n_contigs_total + 1, 0), o_srow(h->n_contigs_total + 1, 0);
@@ -213,6 +211,7 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     A(dev_alloc(&h->d_drop_thr, (size_t)h->n_contigs_total));
     A(dev_alloc(&h->d_ds, (size_t)h->nb * ds));
     A(dev_alloc(&h->d_benefit, (size_t)h->nb * rows));
+    A(dev_alloc(&h->d_codes, (size_t)h->nb * rows * 2 + 16));
     A(dev_alloc(&h->d_bucket_sum, (size_t)sw * h->nb));
     A(dev_alloc(&h->d_bucket_sw, (size_t)sw * h->nb));
     A(dev_alloc(&h->d_fhat_w, (size_t)h->n_windows_total * 2));
@@ -357,11 +356,11 @@ extern "C" int bossgpu_destroy(bossgpu_handle* h) {
     cudaDeviceSynchronize();
     void* ptrs[] = {h->d_segs, h->d_tile_start, h->d_row_start, h->d_srow_start, h->d_ref, h->d_cov, h->d_rowflag,
                     h->d_table, h->d_etable, h->d_phi, h->d_priors, h->d_phi_pow, h->d_cov_total, h->d_drop_thr,
-                    h->d_ds, h->d_benefit, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
+                    h->d_ds, h->d_benefit, h->d_codes, h->d_smu, h->d_expected, h->d_bucket_sum, h->d_bucket_sw, h->d_fhat_w,
                     h->d_hist, h->d_strat_alloc, h->d_upd, h->stage_d, h->scratch_d, h->d_ingest_err, h->d_mask_all, h->d_tiles,
                     h->d_shard_row_start, h->d_halo, h->d_sm_tile_start, h->d_contig_len, h->d_seg_accept, h->d_rs_counts,
                     h->d_mask_ptrs, h->d_fabric, h->d_peer_ptrs, h->d_fab_mask_ptrs, h->d_seg_of_contig, h->d_touched,
-                    h->d_touched_list, h->d_pre_misc, h->d_drop_thr_spec, h->d_tile_cov, h->d_tile_drop, h->pre_stage_d};
+                    h->d_touched_list, h->d_pre_misc, h->d_drop_thr_spec, h->d_tile_cov, h->d_tile_drop, h->pre_stage_d, h->ingest_d};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_upd) cudaFreeHost(h->h_upd);
     if (h->h_ingest_err) cudaFreeHost(h->h_ingest_err);
@@ -389,39 +388,83 @@ extern "C" int bossgpu_synchronize(bossgpu_handle* h) {
 // ------------------------------------------------------------------------------------------------
 // ingest
 // ------------------------------------------------------------------------------------------------
-static int launch_scatter(bossgpu_handle* h, int64_t n_reads, const int32_t* d_seg, const int64_t* d_tstart,
+// per batch: an OpRec (32 B), its read offset and its read id per op slot, plus every read's reference span
+struct IngestBuf {
+    OpRec* rec; int32_t* q0; int32_t* read; int64_t* span;
+};
+static int ensure_ingest_buf(bossgpu_handle* h, size_t slots, size_t reads, IngestBuf* out) {
+    slots = std::max<size_t>(slots, 1); reads = std::max<size_t>(reads, 1);
+    const size_t o_q0 = round_up(sizeof(OpRec) * slots, 256), o_rd = o_q0 + round_up(sizeof(int32_t) * slots, 256);
+    const size_t o_sp = o_rd + round_up(sizeof(int32_t) * slots, 256), bytes = o_sp + sizeof(int64_t) * reads;
+    if (bytes > h->ingest_d_bytes) {
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->ingest_d) cudaFree(h->ingest_d);
+        h->ingest_d = nullptr; h->ingest_d_bytes = 0;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&h->ingest_d, want);
+        if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "op-record cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        h->ingest_d_bytes = want;
+    }
+    char* base = (char*)h->ingest_d;
+    out->rec = (OpRec*)base; out->q0 = (int32_t*)(base + o_q0); out->read = (int32_t*)(base + o_rd); out->span = (int64_t*)(base + o_sp);
+    return 0;
+}
+
+// Everything of the coverage update that runs once the ops are on the device (scatter.cuh): per-op records, the
+// aligned-column check of characters outside ACGT (which settles the batch's error flag), the depth totals, the
+// scatter. `d_cig_off` holds n_reads + 1 entries; `n_slots` is its last one. `totals_src` (device, may be NULL):
+// reference span of the batch per global contig, added only if the batch is accepted.
+static int launch_scatter(bossgpu_handle* h, int64_t n_reads, int64_t n_slots, const int32_t* d_seg, const int64_t* d_tstart,
                           const int32_t* d_bc, const int64_t* d_cig_off, const int64_t* d_cig_end, const uint32_t* d_cig,
                           const int64_t* d_base_off, const uint8_t* d_bases, const uint8_t* d_rev, int ascii, bool count_totals,
-                          bool check_spans = true, PackedBases pk = PackedBases{nullptr, nullptr, nullptr, nullptr, nullptr},
+                          bool check_q, const unsigned long long* totals_src,
+                          PackedBases pk = PackedBases{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, int64_t n_exc = 0,
                           bool record_begin = true) {
     if (record_begin) BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    if (check_spans) {
-        k_check_spans<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_cig_off, d_cig_end, d_cig, d_base_off,
-                                                                              h->d_ingest_err);
+    IngestBuf ib;
+    TRY(ensure_ingest_buf(h, (size_t)n_slots, (size_t)n_reads, &ib));
+    PrefixArgs pa;
+    pa.n_reads = n_reads; pa.cig_off = d_cig_off; pa.cig_end = d_cig_end; pa.cigar = d_cig; pa.seg_of = d_seg; pa.tstart = d_tstart;
+    pa.barcode = d_bc; pa.base_off = d_base_off; pa.rev = d_rev; pa.pk_off = pk.data ? pk.off : nullptr; pa.segs = h->d_segs;
+    pa.n_seg = h->n_seg; pa.nb = h->nb; pa.P = h->P; pa.check_q = check_q ? 1 : 0; pa.rec = ib.rec; pa.rec_q0 = ib.q0;
+    pa.rec_read = (pk.data && n_exc > 0) ? ib.read : nullptr; pa.read_span = ib.span; pa.err = h->d_ingest_err;
+    k_op_prefix<<<(unsigned)std::min<int64_t>(n_reads, 1 << 20), PX_THREADS, 0, h->stream>>>(pa);
+    BOSS_KERNEL_CHECK();
+    h->launches++;
+    if (pk.data) {
+        if (n_exc > 0) {
+            k_check_exc<<<(unsigned)ceil_div(n_exc, 128), 128, 0, h->stream>>>(n_exc, pk, d_rev, d_base_off, d_cig_off, d_cig_end, ib.q0,
+                                                                               d_cig, h->d_ingest_err);
+            BOSS_KERNEL_CHECK();
+            h->launches++;
+        }
+    } else {
+        k_check_bases<<<(unsigned)(h->n_sm * 8), 256, 0, h->stream>>>(n_reads, d_base_off, d_bases, ascii, d_cig_off, d_cig_end, ib.q0,
+                                                                      d_cig, h->d_ingest_err);
         BOSS_KERNEL_CHECK();
         h->launches++;
     }
-    unsigned grid = (unsigned)std::min<int64_t>(n_reads, 1 << 20);
-    k_scatter<<<grid, SC_THREADS, 0, h->stream>>>(n_reads, d_seg, d_tstart, d_bc, d_cig_off, d_cig_end, d_cig, d_base_off, d_bases,
-                                                  d_rev, ascii, pk, h->d_segs, h->n_seg, h->nb, h->P, h->d_cov, h->d_cov_total,
-                                                  count_totals ? 1 : 0, h->d_ingest_err);
+    if (totals_src) {
+        k_add_u64_if_ok<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total, totals_src,
+                                                                                          h->n_contigs_total, h->d_ingest_err);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
+    if (count_totals) {
+        k_add_read_totals<<<(unsigned)ceil_div(n_reads, 256), 256, 0, h->stream>>>(n_reads, d_seg, d_tstart, ib.span, h->d_segs,
+                                                                                  h->n_seg, h->d_cov_total, h->d_ingest_err);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
+    ScatterArgs a;
+    a.n_slots = d_cig_off + n_reads; a.rec = ib.rec; a.rec_read = pa.rec_read; a.bases = d_bases; a.base_is_ascii = ascii; a.pk = pk;
+    a.P = h->P; a.cov = h->d_cov; a.err = h->d_ingest_err;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_slots, SC_THREADS), (int64_t)h->n_sm * 32));
+    k_scatter_ops<<<grid, SC_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     BOSS_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->ev_valid[0] = true;
     h->launches++;
-    return 0;
-}
-
-static int add_contig_totals(bossgpu_handle* h, const int64_t* contig_cov_add) {
-    // tiny: n_contigs values; done with a device-side add so it stays ordered on the stream
-    size_t bytes = sizeof(int64_t) * h->n_contigs_total;
-    TRY(ensure_scratch(h, bytes));
-    BOSS_CUDA(cudaMemcpyAsync(h->scratch_d, contig_cov_add, bytes, cudaMemcpyHostToDevice, h->stream));
-    k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total,
-                                                                                 (const unsigned long long*)h->scratch_d,
-                                                                                 h->n_contigs_total);
-    BOSS_KERNEL_CHECK();
-    BOSS_CUDA(cudaStreamSynchronize(h->stream));   // scratch is reused by later calls
     return 0;
 }
 
@@ -470,32 +513,43 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
     H_CHECK(h);
     if (n_reads < 0) return fail(BOSSGPU_EINVAL, "negative read count");
     TRY(prescore_invalidate(h));
-    if (contig_cov_add) {
-        if (on_device) {
-            k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
-                h->d_cov_total, (const unsigned long long*)contig_cov_add, h->n_contigs_total);
-            BOSS_KERNEL_CHECK();
-            h->launches++;
-        } else {
-            TRY(add_contig_totals(h, contig_cov_add));
+    if (n_reads == 0) {
+        if (!contig_cov_add) return 0;
+        const unsigned long long* src = (const unsigned long long*)contig_cov_add;
+        if (!on_device) {
+            const size_t bytes = sizeof(int64_t) * h->n_contigs_total;
+            TRY(ensure_stage(h, bytes));
+            memcpy(h->stage_h, contig_cov_add, bytes);
+            BOSS_CUDA(cudaMemcpyAsync(h->stage_d, h->stage_h, bytes, cudaMemcpyHostToDevice, h->stream));
+            src = (const unsigned long long*)h->stage_d;
         }
+        k_add_u64<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(h->d_cov_total, src, h->n_contigs_total);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+        if (!on_device) BOSS_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
     }
-    if (n_reads == 0) return 0;
     if (!seg || !tstart || !barcode || !cig_off || !cigar || !base_off || !bases) return fail(BOSSGPU_EINVAL, "null batch array");
     if (on_device) {
-        TRY(launch_scatter(h, n_reads, seg, tstart, barcode, cig_off, cig_off + 1, cigar, base_off, bases, nullptr, base_is_ascii,
-                           contig_cov_add == nullptr));
+        // the grid and the op-record buffer are sized by the number of ops, which only the device knows here
+        int64_t n_ops = 0;
+        BOSS_CUDA(cudaMemcpyAsync(&n_ops, cig_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        BOSS_CUDA(cudaStreamSynchronize(h->stream));
+        if (n_ops < 0) return fail(BOSSGPU_EINVAL, "offset arrays must be non-decreasing");
+        TRY(launch_scatter(h, n_reads, n_ops, seg, tstart, barcode, cig_off, cig_off + 1, cigar, base_off, bases, nullptr, base_is_ascii,
+                           contig_cov_add == nullptr, /*check_q=*/true, (const unsigned long long*)contig_cov_add));
         return 0;   // errors surface at the next update / synchronize-checked call
     }
     const int64_t n_ops = cig_off[n_reads], n_bases = base_off[n_reads];
     if (cig_off[0] != 0 || base_off[0] != 0 || n_ops < 0 || n_bases < 0) return fail(BOSSGPU_EINVAL, "offset arrays must start at 0");
-    // one staging blob: [seg | barcode | tstart | cig_off | base_off | cigar | bases]
+    // one staging blob: [seg | barcode | tstart | cig_off | base_off | cov_add | cigar | bases]
     size_t o_seg = 0;
     size_t o_bc = o_seg + round_up(sizeof(int32_t) * n_reads, 16);
     size_t o_ts = o_bc + round_up(sizeof(int32_t) * n_reads, 16);
     size_t o_co = o_ts + round_up(sizeof(int64_t) * n_reads, 16);
     size_t o_bo = o_co + round_up(sizeof(int64_t) * (n_reads + 1), 16);
-    size_t o_cg = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_ca = o_bo + round_up(sizeof(int64_t) * (n_reads + 1), 16);
+    size_t o_cg = o_ca + round_up(sizeof(int64_t) * h->n_contigs_total, 16);
     size_t o_bs = o_cg + round_up(sizeof(uint32_t) * std::max<int64_t>(n_ops, 1), 16);
     size_t total = o_bs + round_up(std::max<int64_t>(n_bases, 1), 16);
     TRY(ensure_stage(h, total));
@@ -505,13 +559,15 @@ extern "C" int bossgpu_ingest_packed(bossgpu_handle* h, int64_t n_reads, const i
     memcpy(hs + o_ts, tstart, sizeof(int64_t) * n_reads);
     memcpy(hs + o_co, cig_off, sizeof(int64_t) * (n_reads + 1));
     memcpy(hs + o_bo, base_off, sizeof(int64_t) * (n_reads + 1));
+    if (contig_cov_add) memcpy(hs + o_ca, contig_cov_add, sizeof(int64_t) * h->n_contigs_total);
     memcpy(hs + o_cg, cigar, sizeof(uint32_t) * n_ops);
     memcpy(hs + o_bs, bases, (size_t)n_bases);
     BOSS_CUDA(cudaMemcpyAsync(h->stage_d, hs, total, cudaMemcpyHostToDevice, h->stream));
     char* ds = (char*)h->stage_d;
-    TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+    TRY(launch_scatter(h, n_reads, n_ops, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
                        (const int64_t*)(ds + o_co), (const int64_t*)(ds + o_co) + 1, (const uint32_t*)(ds + o_cg),
-                       (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), nullptr, base_is_ascii, contig_cov_add == nullptr));
+                       (const int64_t*)(ds + o_bo), (const uint8_t*)(ds + o_bs), nullptr, base_is_ascii, contig_cov_add == nullptr,
+                       /*check_q=*/true, contig_cov_add ? (const unsigned long long*)(ds + o_ca) : nullptr));
     return check_ingest_error(h);
 }
 
@@ -567,6 +623,8 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
     TRY(spec_order_totals(h));
     if (h->prescore_state == 1)       // is this the batch that was announced? Same reads, same intervals -> its tile marks hold
         h->prescore_state = (n_all == h->pre_n_reads && batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
+    else if (h->prescore_state != 0)  // a second ingest after the announced one: its tiles carry no marks -> score every tile
+        h->prescore_state = -1;
     const int64_t n_reads = (int64_t)sel.size();
     unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {       // one process per GPU (torchrun): share the host's cores
@@ -608,8 +666,8 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
     size_t o_seg = 0;
     size_t o_bc = o_seg + round_up(sizeof(int32_t) * nr1, 16);
     size_t o_ts = o_bc + round_up(sizeof(int32_t) * nr1, 16);
-    size_t o_co = o_ts + round_up(sizeof(int64_t) * nr1, 16);          // first op slot of each read
-    size_t o_to = o_co + round_up(sizeof(int64_t) * nr1, 16);          // CIGAR text offsets [n+1]
+    size_t o_co = o_ts + round_up(sizeof(int64_t) * nr1, 16);          // first op slot of each read [n+1]
+    size_t o_to = o_co + round_up(sizeof(int64_t) * (nr1 + 1), 16);    // CIGAR text offsets [n+1]
     size_t o_sp = o_to + round_up(sizeof(int64_t) * (nr1 + 1), 16);    // reference span tend - tstart
     size_t o_bo = o_sp + round_up(sizeof(int64_t) * nr1, 16);          // base offsets [n+1] (slice lengths)
     size_t o_po = o_bo + round_up(sizeof(int64_t) * (nr1 + 1), 16);    // byte offset of each read's packed bases
@@ -658,6 +716,7 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         }
         s_bo[n_reads] = bo;
         s_to[n_reads] = to;
+        s_co[n_reads] = co;
     }
     BOSS_CUDA(cudaMemcpyAsync(ds, hs, small_bytes, cudaMemcpyHostToDevice, h->stream));
     const double ms_layout = ms_since(t_begin);
@@ -703,16 +762,18 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
     }
     const double ms_pass2 = ms_since(t_begin);
     char* xs = (char*)h->scratch_d;
-    PackedBases pk{(const uint8_t*)(ds + o_pk), (const int64_t*)(ds + o_po), nullptr, nullptr, nullptr};
+    PackedBases pk{(const uint8_t*)(ds + o_pk), (const int64_t*)(ds + o_po), nullptr, nullptr, nullptr, nullptr};
     size_t n_exc = 0;
     for (auto& v : exc) n_exc += v.size();
     std::vector<char> exc_blob;
     if (n_exc) {
-        // characters outside ACGT (rare): [exc_off i64[n+1] | pos i32[n_exc] | ch u8[n_exc]]
-        const size_t e_pos = round_up(sizeof(int64_t) * (n_reads + 1), 16), e_ch = e_pos + round_up(sizeof(int32_t) * n_exc, 16);
+        // characters outside ACGT (rare): [exc_off i64[n+1] | pos i32[n_exc] | read i32[n_exc] | ch u8[n_exc]]
+        const size_t e_pos = round_up(sizeof(int64_t) * (n_reads + 1), 16), e_rd = e_pos + round_up(sizeof(int32_t) * n_exc, 16);
+        const size_t e_ch = e_rd + round_up(sizeof(int32_t) * n_exc, 16);
         exc_blob.assign(e_ch + round_up(n_exc, 16), 0);
         int64_t* eo = (int64_t*)exc_blob.data();
         int32_t* ep = (int32_t*)(exc_blob.data() + e_pos);
+        int32_t* er = (int32_t*)(exc_blob.data() + e_rd);
         uint8_t* ec = (uint8_t*)(exc_blob.data() + e_ch);
         std::vector<Exc> all;
         all.reserve(n_exc);
@@ -723,13 +784,14 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
             while (x < all.size() && all[x].read < j) ++x;
             eo[j] = (int64_t)x;
         }
-        for (size_t q = 0; q < all.size(); ++q) { ep[q] = all[q].pos; ec[q] = all[q].ch; }
+        for (size_t q = 0; q < all.size(); ++q) { ep[q] = all[q].pos; er[q] = (int32_t)all[q].read; ec[q] = all[q].ch; }
         TRY(ensure_scratch(h, x_exc + exc_blob.size()));
         xs = (char*)h->scratch_d;
         BOSS_CUDA(cudaMemcpyAsync(xs + x_exc, exc_blob.data(), exc_blob.size(), cudaMemcpyHostToDevice, h->stream));
         pk.exc_off = (const int64_t*)(xs + x_exc);
         pk.exc_pos = (const int32_t*)(xs + x_exc + e_pos);
         pk.exc_char = (const uint8_t*)(xs + x_exc + e_ch);
+        pk.exc_read = (const int32_t*)(xs + x_exc + e_rd);
     }
     if (n_reads > 0) {
         BOSS_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -739,15 +801,20 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         BOSS_KERNEL_CHECK();
         h->launches++;
     }
-    k_add_u64_if_ok<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
-        h->d_cov_total, (const unsigned long long*)(ds + o_ca), h->n_contigs_total, h->d_ingest_err);
-    BOSS_KERNEL_CHECK();
-    h->launches++;
-    if (n_reads > 0)
-        TRY(launch_scatter(h, n_reads, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
+    if (n_reads > 0) {
+        // every contig's depth total advances by the whole batch's reference span on it (whichever shard holds the
+        // reads), once the aligned-column check has accepted the batch
+        TRY(launch_scatter(h, n_reads, ops_cap, (const int32_t*)(ds + o_seg), (const int64_t*)(ds + o_ts), (const int32_t*)(ds + o_bc),
                            (const int64_t*)(ds + o_co), (const int64_t*)(xs + x_end), (const uint32_t*)(xs + x_ops),
                            (const int64_t*)(ds + o_bo), nullptr, (const uint8_t*)(ds + o_rv), /*ascii=*/1,
-                           /*count_totals=*/false, /*check_spans=*/false, pk, /*record_begin=*/false));
+                           /*count_totals=*/false, /*check_q=*/false, (const unsigned long long*)(ds + o_ca), pk, (int64_t)n_exc,
+                           /*record_begin=*/false));
+    } else {
+        k_add_u64_if_ok<<<(unsigned)ceil_div(h->n_contigs_total, 256), 256, 0, h->stream>>>(
+            h->d_cov_total, (const unsigned long long*)(ds + o_ca), h->n_contigs_total, h->d_ingest_err);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
+    }
     int rc = check_ingest_error(h);       // synchronises: exc_blob, the staging buffer and the scratch are free again
     if (rc != 0 && h->prescore_state == 2) h->prescore_state = -1;    // a rejected batch adds nothing to the totals
     h->last_ingest_h2d = (int64_t)(small_bytes + (size_t)total_text + (size_t)total_packed + exc_blob.size());
@@ -1053,8 +1120,9 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
     BOSS_CUDA(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned long long) * (3 * HBINS + 4), h->stream));
     HistArgs a;
     a.benefit = h->d_benefit; a.n_rows = h->n_rows; a.nb = h->nb; a.R0 = h->R0; a.M = h->M_rows; a.target = h->target_rows;
-    a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.hist = h->d_hist; a.upd = h->d_upd;
-    unsigned gx = (unsigned)ceil_div(h->n_rows, HIST_THREADS * HIST_ROWS_PER_THREAD);
+    a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.hist = h->d_hist; a.upd = h->d_upd; a.codes = h->d_codes;
+    const int64_t n_groups = (h->R0 + h->n_rows - 1) / HIST_GROUP - h->R0 / HIST_GROUP + 1;     // groups of the global row axis
+    unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_groups, HIST_THREADS), (int64_t)h->n_sm * 10));
     k_hist<<<dim3(gx, (unsigned)h->nb), HIST_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     h->launches += 3;
@@ -1075,6 +1143,7 @@ static int phase4_distribute(bossgpu_handle* h, const uint8_t* const* mask_ptrs)
     EV_BEGIN(6);
     DistArgs a;
     a.segs = h->d_segs; a.srow_start = h->d_srow_start; a.n_seg = h->n_seg; a.nb = h->nb; a.benefit = h->d_benefit;
+    a.codes = h->d_codes;
     a.n_rows = h->n_rows; a.R0 = h->R0; a.D0 = h->D0; a.mask_ptrs = mask_ptrs; a.bucket_sw = h->d_bucket_sw;
     a.shard_row_start = h->d_shard_row_start; a.n_shards = h->n_shards;
     a.strat = h->d_strat; a.strat_host = h->h_strat_dev; a.shift = h->strat_shift;
@@ -1131,6 +1200,11 @@ extern "C" int bossgpu_update(bossgpu_handle* h, const bossgpu_update_params* p,
     BOSS_CUDA(cudaMemcpyAsync(&h->h_upd->switched_on, &h->d_upd->switched_on, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     if (h->h_upd->switched_on) {
+        if (p->tc != p->tc) {                  // Q14: upstream raises before find_strat_thread, every strategy stays as it is
+            EV_END(7);
+            fetch_result(h, r);
+            return fail(BOSSGPU_ENOTC, "a bucket is on but there is no time_cost yet (no read length has been observed)");
+        }
         TRY(upload_fhat(h, p));
         TRY(phase1_smooth(h, p));
         TRY(phase2_hist(h, p));
@@ -1175,9 +1249,11 @@ extern "C" int bossgpu_update_phase(bossgpu_handle* h, int phase, const bossgpu_
             }
             if (h->phase_done != 3) return fail(BOSSGPU_ESTATE, "a bucket is on but phases 1-3 were skipped");
             if (h->h_upd->empty) {
+                const int why = h->h_upd->empty;
                 EV_END(7);
                 h->phase_done = -1;
                 fetch_result(h, r);
+                if (why == 2) return fail(BOSSGPU_ENOTC, "a bucket is on but there is no time_cost yet (no read length has been observed)");
                 return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
             }
             TRY(phase4_distribute(h, h->n_shards > 1 ? h->d_mask_ptrs : nullptr));
@@ -1242,7 +1318,7 @@ static int pack_own_mask(bossgpu_handle* h, uint8_t* dst) {
     if (h->n_shards <= 1) return 0;
     int64_t n_bits = h->n_rows * 2 * h->nb;
     k_pack_mask<<<(unsigned)ceil_div(ceil_div(n_bits, 8), 256), 256, 0, h->stream>>>(
-        h->d_benefit, h->n_rows, h->nb, h->R0, h->target_rows, h->d_upd, dst, n_bits);
+        h->d_benefit, h->d_codes, h->n_rows, h->nb, h->R0, h->target_rows, h->d_upd, dst, n_bits);
     BOSS_KERNEL_CHECK();
     h->launches++;
     return 0;
@@ -1456,6 +1532,8 @@ extern "C" int bossgpu_update_fused_end(bossgpu_handle* h, bossgpu_update_result
     TRY(fetch_result(h, r));
     if (h->last.fabric_err) return fail(BOSSGPU_EPEER, "shard %d of %d: a peer did not reach an exchange step of update %u within %.1f s",
                                         h->shard_index, h->n_shards, h->fabric_epoch, h->fabric_timeout_ns * 1e-9);
+    if (h->last.switched_on && h->last.empty == 2)
+        return fail(BOSSGPU_ENOTC, "a bucket is on but there is no time_cost yet (no read length has been observed)");
     if (h->last.switched_on && h->last.empty)
         return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
     return 0;
@@ -1638,6 +1716,20 @@ extern "C" int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_gr
     return 0;
 }
 
+extern "C" int bossgpu_get_fhat(bossgpu_handle* h, int64_t row0, int64_t n_rows, double* out) {
+    H_CHECK(h);
+    if (!out || n_rows < 0 || row0 < 0) return fail(BOSSGPU_EINVAL, "bad row range");
+    if (!h->have_fhat) return fail(BOSSGPU_ESTATE, "no F-hat on the device yet (no update has derived a strategy)");
+    if (n_rows == 0) return 0;
+    TRY(ensure_scratch(h, sizeof(double) * 2 * (size_t)n_rows));
+    FhatGeom fg{h->n_windows_total, h->Tf_rows, h->target_rows};
+    k_fhat_rows<<<(unsigned)ceil_div(2 * n_rows, 256), 256, 0, h->stream>>>(fg, h->d_fhat_w, h->d_upd, row0, n_rows, (double*)h->scratch_d);
+    BOSS_KERNEL_CHECK();
+    BOSS_CUDA(cudaMemcpyAsync(out, h->scratch_d, sizeof(double) * 2 * (size_t)n_rows, cudaMemcpyDeviceToHost, h->stream));
+    BOSS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int bossgpu_get_score_table(bossgpu_handle* h, double* scores, double* entropies) {
     H_CHECK(h);
     if (scores) {
@@ -1672,6 +1764,7 @@ extern "C" int64_t bossgpu_ingest_bytes(bossgpu_handle* h) { return h ? h->last_
 extern "C" int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double mean_depth, double p_ref, double p_del,
                                       double frac_dropout, double frac_deep) {
     H_CHECK(h);
+    TRY(prescore_invalidate(h));            // counters change under an early pass: the update scores every tile again
     BOSS_CUDA(cudaMemsetAsync(h->d_cov_total, 0, sizeof(unsigned long long) * h->n_contigs_total, h->stream));
     for (const auto& S : h->segs) {
         unsigned grid = (unsigned)std::min<int64_t>(ceil_div(S.len, 256), 148 * 32);

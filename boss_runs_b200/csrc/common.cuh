@@ -85,7 +85,9 @@ struct UpdateDev {
     unsigned long long n_accept[2];
     unsigned long long fsum_hi, fsum_lo;   // exact limbs of sum(fhat_exp)
     unsigned long long mirror_bytes;       // bytes the distribution kernel wrote into the host mirror
-    int32_t  empty;                  // every benefit is zero (upstream: np.max of an empty array raises)
+    int32_t  e_thr;                  // exponent bin of the threshold: threshold = 2^-e_thr * normaliser
+    int32_t  use_codes;              // the one-byte bin codes k_hist left behind decide the masks (else: the benefits)
+    int32_t  empty;                  // 1: every benefit is zero (upstream: np.max of an empty array raises); 2: no time_cost (Q14)
     int32_t  fabric_err;             // BOSSGPU_EPEER: a peer shard did not show up at an exchange step (fabric.cuh)
     int32_t  error;                  // BOSSGPU_E* raised on the device; survives the per-update reset
     int32_t  pad_;
@@ -146,6 +148,7 @@ struct bossgpu_handle {
     int32_t*  d_drop_thr = nullptr;              // [n_contigs_total]  -1 = dropout rule inactive
     double*   d_ds = nullptr;                    // [nb][ds_len]
     double2*  d_benefit = nullptr;               // [nb][n_rows]  (.x forward, .y reverse)
+    uint8_t*  d_codes = nullptr;                 // [nb][n_rows][2] exponent-bin code of every benefit entry (k_hist -> k_distribute)
     double2*  d_smu = nullptr;                   // debug
     double2*  d_expected = nullptr;              // debug
     unsigned long long* d_bucket_sum = nullptr;  // [n_sw][nb]
@@ -169,6 +172,7 @@ struct bossgpu_handle {
     void*  stage_h = nullptr;  size_t stage_h_bytes = 0;   // pinned
     void*  stage_d = nullptr;  size_t stage_d_bytes = 0;
     void*  scratch_d = nullptr; size_t scratch_d_bytes = 0;
+    void*  ingest_d = nullptr;  size_t ingest_d_bytes = 0;     // op records of the batch being ingested (scatter.cuh)
     int32_t* d_ingest_err = nullptr;
     int32_t* h_ingest_err = nullptr;
     // timing

@@ -236,6 +236,16 @@ __device__ __forceinline__ void to_limbs(double v, unsigned long long& hi, unsig
         lo = (unsigned long long)((v - (double)hi) * 4294967296.0);
     }
 }
+// The same for values known to be below 2^51 (every F-hat term: F-hat <= 1 and the scale is at most 2^50).
+__device__ __forceinline__ void to_limbs_small(double v, unsigned long long& hi, unsigned long long& lo) {
+    const double M = 6755399441055744.0;                             // 2^52 + 2^51
+    const double t = __dadd_rn(v, M);
+    const long long h = __double_as_longlong(t) - __double_as_longlong(M);
+    const double rem = __dadd_rn(v, -__dadd_rn(t, -M));              // exact: |rem| <= 0.5
+    const double t2 = __dadd_rn(__dmul_rn(rem, 4294967296.0), M);
+    hi = (unsigned long long)h;
+    lo = (unsigned long long)(__double_as_longlong(t2) - __double_as_longlong(M));
+}
 __host__ __device__ inline double from_limbs(unsigned long long hi, unsigned long long lo, int shift) {
     // hi + lo*2^-32 (both signed sums), scaled back by 2^-shift
     double v = (double)(long long)hi + (double)(long long)lo * (1.0 / 4294967296.0);
@@ -297,6 +307,16 @@ __global__ void k_fhat_finish(int shift, UpdateDev* upd) {
     upd->fhat_scale = s != 0.0 ? 1.0 / s : 1.0;        // readstartdist.py:145-150, on_target = 1
 }
 
+// F-hat of the rows [row0, row0 + n) of the merged, length-adjusted axis, exactly as k_hist consumes it: window value
+// x normaliser (readstartdist.py:121-152 + adjust_length, core.py:184-185). For bossgpu_get_fhat (parity tests).
+__global__ void k_fhat_rows(FhatGeom g, const double* __restrict__ fw, const UpdateDev* __restrict__ upd, int64_t row0, int64_t n,
+                            double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const int64_t r = row0 + (i >> 1);
+    out[i] = (r >= 0 && r < g.target) ? fw[2 * fhat_window_of_row(g, r) + (i & 1)] * upd->fhat_scale : 0.0;
+}
+
 // ---- exponent histogram (sequences.py:584-624) -----------------------------------------------------------
 struct HistArgs {
     const double2* benefit;       // [nb][n_rows]
@@ -307,6 +327,7 @@ struct HistArgs {
     const double* fw;             // [W][2]
     int shift;                    // limbs hold fhat * 2^shift
     unsigned long long* hist;     // [3*HBINS + 4]: counts | hi | lo | ubar_hi, ubar_lo, n_nonzero, -
+    uint8_t* codes;               // [nb][n_rows][2] exponent-bin code of every entry (see k_hist), or NULL
     UpdateDev* upd;
 };
 
@@ -326,41 +347,48 @@ __device__ __forceinline__ int abs_exponent_of_ratio(double x, double norm, unsi
     return e < 0 ? -e : e;
 }
 
-constexpr int HIST_THREADS = 256;
-constexpr int HIST_ROWS_PER_THREAD = 32;
+constexpr int HIST_THREADS = 128;
+constexpr int HIST_GROUP = 20;        // rows per thread: one 2 kb read-start window spans 20 bins (readstartdist.py:13,129)
+constexpr int HIST_SLOTS = 4;         // exponent bins a thread counts in registers, starting one below its first row's
 
-// Adds one element per lane (bin e < 0 = nothing) to the CTA's shared histogram. Lanes hold neighbouring rows,
-// whose smoothed benefits mostly share a binary exponent, so the warp first groups its lanes by bin and sums each
-// group with warp reductions; only the group's leader touches shared memory (64-bit shared atomics are CAS
-// loops, and 32 lanes hitting one bin would serialise 32-fold). Must be called by all 32 lanes.
-__device__ __forceinline__ void warp_hist_add(int e, unsigned long long h, unsigned long long l, unsigned* s_cnt,
+// Adds one weighted entry per lane (bin e < 0 = nothing) to the CTA's shared histogram: `cnt` elements whose F-hat
+// limbs sum to (h, l), h < 2^63, |l| < 2^37. Lanes hold neighbouring row groups, whose smoothed benefits mostly share
+// a binary exponent, so the warp first groups its lanes by bin and sums each group with warp reductions; only the
+// group's leader touches shared memory (64-bit shared atomics are CAS loops, and 32 lanes hitting one bin would
+// serialise 32-fold). Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_hist_add(int e, unsigned cnt, unsigned long long h, unsigned long long l, unsigned* s_cnt,
                                               unsigned long long* s_hi, unsigned long long* s_lo) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    // h < 2^63 in three 21-bit pieces; l in [-2^31, 2^31] biased to [0, 2^32] in a 16- and a 17-bit piece
-    const unsigned long long lb = l + 0x80000000ull;
+    const unsigned long long BIAS = 1ull << 37;
+    const unsigned long long lb = l + BIAS;                    // (0, 2^38): a 21- and a 17-bit piece
     unsigned remaining = __ballot_sync(FULL, e >= 0);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
         const int le = __shfl_sync(FULL, e, leader);
         const bool mine = e == le;
         const unsigned grp = __ballot_sync(FULL, mine);
+        const unsigned n = __reduce_add_sync(FULL, mine ? cnt : 0u);
         const unsigned c0 = __reduce_add_sync(FULL, mine ? (unsigned)(h & 0x1FFFFFull) : 0u);
         const unsigned c1 = __reduce_add_sync(FULL, mine ? (unsigned)((h >> 21) & 0x1FFFFFull) : 0u);
         const unsigned c2 = __reduce_add_sync(FULL, mine ? (unsigned)(h >> 42) : 0u);
-        const unsigned c3 = __reduce_add_sync(FULL, mine ? (unsigned)(lb & 0xFFFFull) : 0u);
-        const unsigned c4 = __reduce_add_sync(FULL, mine ? (unsigned)(lb >> 16) : 0u);
+        const unsigned c3 = __reduce_add_sync(FULL, mine ? (unsigned)(lb & 0x1FFFFFull) : 0u);
+        const unsigned c4 = __reduce_add_sync(FULL, mine ? (unsigned)(lb >> 21) : 0u);
         if (lane == leader) {
-            const unsigned n = __popc(grp);
             atomicAdd(&s_cnt[le], n);
             atomicAdd(&s_hi[le], (unsigned long long)c0 + ((unsigned long long)c1 << 21) + ((unsigned long long)c2 << 42));
-            atomicAdd(&s_lo[le], (unsigned long long)c3 + ((unsigned long long)c4 << 16) - ((unsigned long long)n << 31));
+            atomicAdd(&s_lo[le], (unsigned long long)c3 + ((unsigned long long)c4 << 21) - (unsigned long long)__popc(grp) * BIAS);
         }
         remaining &= ~grp;
     }
 }
 
-// One thread walks rows base+t, base+t+256, ... (coalesced 16-byte loads); a warp holds 32 neighbouring rows.
+// One thread walks the 20 rows of one group of the GLOBAL merged axis (rows 20G .. 20G+19): they share one read-start
+// window, so F-hat is converted to limbs once per group and strand, and the bins are counted in registers (a run of
+// neighbouring rows spans one or two binary exponents); the warp merges its 32 groups at the end. Entries outside the
+// four register slots, and groups that straddle a window edge (only in the tail-fixed part of F-hat), take the direct
+// path. Also leaves the bin of every entry behind as a one-byte code (hist.codes) for the distribution kernel:
+// 0 = the maximum itself, c = entry in [norm 2^-c, norm 2^-(c-1)), 254 = anything smaller, 255 = zero / cut row.
 __global__ void __launch_bounds__(HIST_THREADS)
 k_hist(HistArgs a) {
     __shared__ unsigned s_cnt[HBINS];
@@ -385,40 +413,93 @@ k_hist(HistArgs a) {
     const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail (adjust_length pads)
     unsigned long long u_hi = 0, u_lo = 0, nnz = 0;
     const double2* ben = a.benefit + (size_t)b * a.n_rows;
+    uint16_t* codes = a.codes ? reinterpret_cast<uint16_t*>(a.codes) + (size_t)b * a.n_rows : nullptr;
 
-    const int64_t base = (int64_t)blockIdx.x * (HIST_THREADS * HIST_ROWS_PER_THREAD);
+    const int64_t n_groups = (a.R0 + a.n_rows - 1) / HIST_GROUP - a.R0 / HIST_GROUP + 1;         // groups of the global row axis here
+    for (int64_t g0 = (int64_t)blockIdx.x * HIST_THREADS; g0 < n_groups; g0 += (int64_t)gridDim.x * HIST_THREADS) {
+    const int64_t G = a.R0 / HIST_GROUP + g0 + threadIdx.x;                                      // global row group
+    const int64_t r_lo = max(G * HIST_GROUP, a.R0), r_hi = min((G + 1) * HIST_GROUP, a.R0 + a.n_rows);
+    // register state: the group's window, its F-hat limbs per strand, counts of HIST_SLOTS bins per strand
+    int64_t cur_win = -1;
+    double f[2] = {0.0, 0.0};
+    unsigned long long fh[2] = {0, 0}, fl[2] = {0, 0};
+    int ebase[2] = {-1, -1};
+    unsigned cnt[2][HIST_SLOTS] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    auto direct = [&](int e, unsigned n, unsigned long long h, unsigned long long l) {
+        atomicAdd(&s_cnt[e], n);
+        atomicAdd(&s_hi[e], h * n);
+        atomicAdd(&s_lo[e], l * n);
+    };
+    auto spill = [&]() {                        // window changes inside the group: empty the register slots
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int j = 0; j < HIST_SLOTS; ++j)
+                if (cnt[s][j]) { direct(ebase[s] + j, cnt[s][j], fh[s], fl[s]); cnt[s][j] = 0; }
+    };
     // pass 0: every row below `target`; pass 1 (only when adjust_length pads, core.py:179-181 with reject refs):
     // the last `extra` merged rows once more, at their appended positions
-    const int n_pass = (extra > 0 && a.R0 + base + HIST_THREADS * HIST_ROWS_PER_THREAD > a.M - extra) ? 2 : 1;
+    const int n_pass = (extra > 0 && r_hi > a.M - extra) ? 2 : 1;
+    // in the plain part of F-hat (before either tail fix) the whole group lies in window G
+    const bool plain = (G + 1) * HIST_GROUP <= min(min(20 * a.fg.W, a.fg.Tf), a.target);
     for (int pass = 0; pass < n_pass; ++pass) {
-#pragma unroll 2
-        for (int k = 0; k < HIST_ROWS_PER_THREAD; ++k) {
-            const int64_t i0 = base + (int64_t)k * HIST_THREADS;              // block-uniform
-            if (i0 >= a.n_rows) break;
-            const int64_t i = i0 + threadIdx.x;
-            const int64_t r = a.R0 + i;
-            bool live = i < a.n_rows && (pass == 0 ? r < a.target : r >= a.M - extra);
-            double2 v = make_double2(0.0, 0.0);
-            if (live) v = ben[i];
-            live = live && !(v.x == 0.0 && v.y == 0.0);                       // np.nonzero (sequences.py:585)
-            const int64_t win = live ? fhat_window_of_row(a.fg, pass == 0 ? r : r + extra) : 0;
+        for (int64_t r4 = r_lo; r4 < r_hi; r4 += 4) {
+        double2 v4[4];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const double x = s == 0 ? v.x : v.y;
-                const bool on = live && x != 0.0;
-                int e = -1;
-                unsigned long long h = 0, l = 0;
-                if (on) {
-                    const double f = a.fw[2 * win + s] * scale;               // np.multiply(fhat_exp, normalizer)
-                    e = abs_exponent_of_ratio(x, norm, nbits);
-                    to_limbs(f * two_shift, h, l);
-                    const double t = f * x;                                   // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
+        for (int j = 0; j < 4; ++j) {                         // four independent loads in flight per thread
+            const int64_t r = r4 + j;
+            const bool in = r < r_hi && (pass == 0 ? r < a.target : r >= a.M - extra);
+            v4[j] = in ? ben[r - a.R0] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t r = r4 + j;
+            const double2 v = v4[j];
+            unsigned code2 = 0xFFFFu;
+            if (!(v.x == 0.0 && v.y == 0.0)) {                // np.nonzero (sequences.py:585); rows that are cut read 0
+                const int64_t win = (plain && pass == 0) ? G : fhat_window_of_row(a.fg, pass == 0 ? r : r + extra);
+                if (win != cur_win) {
+                    spill();
+                    cur_win = win;
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        f[s] = a.fw[2 * win + s] * scale;     // np.multiply(fhat_exp, normalizer)
+                        to_limbs_small(f[s] * two_shift, fh[s], fl[s]);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const double x = s == 0 ? v.x : v.y;
+                    if (x == 0.0) continue;
+                    const int e = abs_exponent_of_ratio(x, norm, nbits);
+                    // one-byte bin code: the maximum (the only entry whose ratio has exponent +1, Q3) gets 0
+                    const unsigned c = (x == norm) ? 0u : (unsigned)min(e + 1, 254);
+                    code2 = s == 0 ? ((code2 & 0xFF00u) | c) : ((code2 & 0x00FFu) | (c << 8));
+                    if (ebase[s] < 0) ebase[s] = max(e - 1, 0);
+                    const int rel = e - ebase[s];
+                    if ((unsigned)rel < (unsigned)HIST_SLOTS) {
+#pragma unroll
+                        for (int j = 0; j < HIST_SLOTS; ++j) cnt[s][j] += (rel == j) ? 1u : 0u;
+                    } else {
+                        direct(e, 1u, fh[s], fl[s]);
+                    }
+                    const double t = f[s] * x;                // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
                     unsigned long long uh, ul;
-                    to_limbs(ue_ok ? t * two_ue : ldexp(t, ue), uh, ul);
+                    to_limbs_small(ue_ok ? t * two_ue : ldexp(t, ue), uh, ul);
                     u_hi += uh; u_lo += ul; nnz++;
                 }
-                warp_hist_add(e, h, l, s_cnt, s_hi, s_lo);
             }
+            if (pass == 0 && codes && r < r_hi) codes[r - a.R0] = (uint16_t)code2;
+        }
+        }
+    }
+    // merge the warp's 32 groups, slot by slot
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int j = 0; j < HIST_SLOTS; ++j) {
+            const unsigned n = cnt[s][j];
+            warp_hist_add(n ? ebase[s] + j : -1, n, fh[s] * n, fl[s] * n, s_cnt, s_hi, s_lo);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -455,6 +536,13 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, U
         if (threadIdx.x == 0) {
             upd->normaliser = norm; upd->n_nonzero = nnz;
             upd->empty = 1; upd->threshold = 0.0; upd->strat_size = 0;
+        }
+        return;
+    }
+    if (tc != tc) {                                                        // Q14: upstream has no time_cost yet -> AttributeError
+        if (threadIdx.x == 0) {                                            // before find_strat_thread; no strategy is touched
+            upd->normaliser = norm; upd->n_nonzero = nnz;
+            upd->empty = 2; upd->threshold = 0.0; upd->strat_size = 0;
         }
         return;
     }
@@ -508,6 +596,10 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, U
         upd->ubar0 = ubar0;
         upd->strat_size = k;
         upd->threshold = ldexp(1.0, -e_thr) * norm;
+        upd->e_thr = e_thr;
+        // the bin codes of k_hist order like the benefits as long as the threshold bin is below their saturation
+        // point and the normaliser is a normal number (its exponent field drives the codes)
+        upd->use_codes = (e_thr <= 253 && (upd->norm_bits >> 52) != 0ull) ? 1 : 0;
     }
 }
 
@@ -525,6 +617,8 @@ struct DistArgs {
     const int64_t* srow_start;    // [n_seg+1]
     int n_seg, nb;
     const double2* benefit;       // [nb][n_rows], local merged rows
+    const uint8_t* codes;         // [nb][n_rows][2] bin code of every benefit entry (k_hist); read instead of the benefits
+                                  // when upd->use_codes: entry >= threshold  <=>  code <= upd->e_thr
     int64_t n_rows;
     int64_t R0, D0;
     const uint8_t* const* mask_ptrs; // multi-shard: [n_shards] packed mask of every shard, bit (i*2+s)*nb+b for the
@@ -554,6 +648,8 @@ k_distribute(DistArgs a) {
     const int64_t total = a.n_srows * 2 * nb;
     if (!a.upd->switched_on || a.upd->empty) return;      // strategy left as it is (core.py:172; sequences.py:588 raises)
     const double thr = a.upd->threshold;
+    const bool by_code = a.codes != nullptr && a.upd->use_codes != 0;
+    const unsigned e_thr = (unsigned)a.upd->e_thr;
     const int64_t n_vec = (total + a.shift + DIST_VEC - 1) / DIST_VEC;    // virtual byte axis: v = i + shift
     // every CTA owns one contiguous run of vectors, so a thread stays inside one segment (contig) for long
     // stretches: segment geometry lives in registers and the per-segment accept counters see few atomics
@@ -574,7 +670,49 @@ k_distribute(DistArgs a) {
         const bool part = !whole && i0 + DIST_VEC > 0 && i0 < total;
         uint32_t w[4] = {0, 0, 0, 0};
         bool changed = false;
-        if (whole || part) {
+        bool fast = false;
+        if (NB1 && whole && by_code && a.mask_ptrs == nullptr) {
+            // eight strategy rows of one barcode-less contig inside one bucket: sixteen code bytes against the threshold bin
+            const int64_t dl0 = i0 >> 1, dl1 = dl0 + 7;
+            if (dl0 >= row_hi || dl0 < row_lo) {
+                sg = find_segment(a.srow_start, a.n_seg, dl0);
+                row_lo = a.srow_start[sg]; row_hi = a.srow_start[sg + 1]; sw_off = a.segs[sg].sw_off;
+            }
+            const int64_t j0 = dl0 - row_lo;                               // row within the segment
+            const int64_t bk = j0 / (BUCKET / BIN);
+            const int64_t c0 = 2 * (a.D0 + dl0 - a.R0);                  // Q2: strategy row d reads merged row d
+            if (dl1 < row_hi && ((reinterpret_cast<uintptr_t>(a.codes) + c0) & 3) == 0) {
+                fast = true;
+                const uint4 ov = *reinterpret_cast<const uint4*>(a.strat + i0);
+                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+                // the eight rows lie in one bucket or straddle two: the first n0 rows follow bucket bk, the rest bk + 1
+                const int n0 = (int)min((int64_t)8, (bk + 1) * (BUCKET / BIN) - j0);
+                const bool g0 = a.bucket_sw[(size_t)(sw_off + bk)] != 0;
+                const bool g1 = n0 < 8 ? a.bucket_sw[(size_t)(sw_off + bk + 1)] != 0 : g0;
+                if (g0 || g1) {
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(a.codes + c0);
+                    const uint32_t et = e_thr * 0x01010101u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t gm = ((2 * q < n0 ? g0 : g1) ? 0x0000FFFFu : 0u) | ((2 * q + 1 < n0 ? g0 : g1) ? 0xFFFF0000u : 0u);
+                        w[q] = (__vcmpleu4(cw[q], et) & 0x01010101u & gm) | (ow[q] & ~gm);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[q] = ow[q];
+                }
+                if (sg != cur_sg) {
+                    if (acc0) atomicAdd(&a.seg_accept[2 * cur_sg], (unsigned long long)acc0);
+                    if (acc1) atomicAdd(&a.seg_accept[2 * cur_sg + 1], (unsigned long long)acc1);
+                    cur_sg = sg; acc0 = 0; acc1 = 0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { acc0 += __popc(w[q] & 0x00010001u); acc1 += __popc(w[q] & 0x01000100u); }
+                changed = (w[0] != ow[0]) | (w[1] != ow[1]) | (w[2] != ow[2]) | (w[3] != ow[3]);
+                if (changed) *reinterpret_cast<uint4*>(a.strat + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        if (!fast && (whole || part)) {
             uint4 ov = make_uint4(0, 0, 0, 0);
             if (whole) ov = *reinterpret_cast<const uint4*>(a.strat + i0);
             const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
@@ -602,6 +740,8 @@ k_distribute(DistArgs a) {
                             const int sh = find_segment(a.shard_row_start, a.n_shards, r);
                             const int64_t bit = ((r - a.shard_row_start[sh]) * 2 + s) * nb + b;
                             m = (__ldcg(a.mask_ptrs[sh] + (bit >> 3)) >> (bit & 7)) & 1;
+                        } else if (by_code) {
+                            m = (unsigned)a.codes[((size_t)b * a.n_rows + (r - a.R0)) * 2 + s] <= e_thr;
                         } else {
                             if (!NB1 || dl != row_cached) { v = a.benefit[(size_t)b * a.n_rows + (r - a.R0)]; row_cached = dl; }
                             m = (s == 0 ? v.x : v.y) >= thr;
@@ -679,11 +819,13 @@ __global__ void k_count_read_starts(int64_t n, const int64_t* __restrict__ win, 
 }
 
 // packed mask of this shard's merged rows: bit (i*2+s)*nb+b for local row i (rows cut by adjust_length are 0)
-__global__ void k_pack_mask(const double2* __restrict__ benefit, int64_t n_rows, int nb, int64_t R0, int64_t target,
-                            const UpdateDev* upd, uint8_t* __restrict__ out_bits, int64_t n_bits) {
+__global__ void k_pack_mask(const double2* __restrict__ benefit, const uint8_t* __restrict__ codes, int64_t n_rows, int nb, int64_t R0,
+                            int64_t target, const UpdateDev* upd, uint8_t* __restrict__ out_bits, int64_t n_bits) {
     int64_t byte = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (byte * 8 >= n_bits || !upd->switched_on) return;
     const double thr = upd->threshold;
+    const bool by_code = codes != nullptr && upd->use_codes != 0;
+    const unsigned e_thr = (unsigned)upd->e_thr;
     unsigned v = 0;
     for (int k = 0; k < 8; ++k) {
         int64_t bit = byte * 8 + k;
@@ -692,6 +834,10 @@ __global__ void k_pack_mask(const double2* __restrict__ benefit, int64_t n_rows,
         int s = (int)((bit / nb) & 1);
         int64_t i = bit / (2 * nb);
         if (R0 + i >= target) continue;
+        if (by_code) {
+            if ((unsigned)codes[((size_t)b * n_rows + i) * 2 + s] <= e_thr) v |= 1u << k;
+            continue;
+        }
         double2 x = benefit[(size_t)b * n_rows + i];
         if ((s == 0 ? x.x : x.y) >= thr) v |= 1u << k;
     }

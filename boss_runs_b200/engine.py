@@ -415,6 +415,13 @@ class Engine:
         check(self.lib.bossgpu_get_hist(self.h, ptr(counts), ptr(f_grid)))
         return counts, f_grid
 
+    def fhat_rows(self, row0: int, n_rows: int) -> np.ndarray:
+        """F-hat [n_rows][2] of the merged, length-adjusted rows [row0, row0 + n_rows) as the last update's histogram
+        read it (expanded, tail-fixed and normalised on the device)."""
+        out = np.empty((int(n_rows), 2), dtype=np.float64)
+        check(self.lib.bossgpu_get_fhat(self.h, int(row0), int(n_rows), ptr(out)))
+        return out
+
     def score_table(self) -> tuple[np.ndarray, np.ndarray]:
         s = np.empty((N_PATTERNS, 4))
         e = np.empty((N_PATTERNS, 4))

@@ -101,50 +101,65 @@ def adjust_length(original_size: int, expanded: np.ndarray) -> np.ndarray:
     return out
 
 
+def _sequential_sum(x: np.ndarray) -> float:
+    """Left-to-right fp64 sum. Upstream normalises its length distributions with Python's built-in `sum`
+    (readlengthdist.py:29,65), which adds element by element; np.sum's pairwise order differs in the last bits."""
+    return float(np.cumsum(x, dtype=np.float64)[-1])
+
+
 class ReadlengthDist:
-    """Histogram of accepted read lengths -> lambda, time_cost and the 10-step staircase approx_ccl."""
+    """Read-length model of the strategy update (boss/readlengthdist.py:7-97): a histogram of the lengths of accepted
+    reads -> mean length `lam`, `time_cost`, and `approx_ccl`, the ten lengths at which the survival function of the
+    read length drops below 0.95, 0.85, ..., 0.05 (the staircase `Contig.calc_u` convolves with, reference.py:241-260).
+    Before any read has been seen the lengths follow a Gaussian prior (lam 6000, sd 4000) cut at lam + 10 sd.
+
+    Same attributes as upstream (`read_lengths`, `L`, `ccl`, `approx_ccl`, `lam`, `longest_read`, and `time_cost` only
+    after the first successful update, Q14) and bit-identical values (tests/test_oracle_kats.py re-asserts upstream's
+    own vectors); the computation is array-shaped: lengths are counted with one scatter-add, the staircase is a
+    binary search on the (non-increasing) survival function instead of a scanning loop."""
+
+    MAX_LEN = 1_000_000          # longer reads are counted as MAX_LEN - 1 (readlengthdist.py:47-48)
+    CUTOFF = 1e-6                # survival below this is treated as 0 (readlengthdist.py:83)
 
     def __init__(self, mu: int = 400, sd: int = 4000, lam: int = 6000, eta: int = 11):
-        self.sd, self.lam, self.eta, self.mu = sd, lam, eta, mu
-        self.read_lengths = np.zeros(shape=int(1e6), dtype="uint16")
+        self.mu, self.sd, self.lam, self.eta = mu, sd, lam, eta
+        self.read_lengths = np.zeros(self.MAX_LEN, dtype=np.uint16)
         x = np.arange(int(lam + 10 * sd), dtype="int")
-        L = np.exp(-((x - lam + 1) ** 2) / (2 * (sd ** 2))) / (sd * np.sqrt(2 * np.pi))
-        L /= sum(L)
-        self.L = L
+        density = np.exp(-((x - lam + 1) ** 2) / (2 * (sd ** 2))) / (sd * np.sqrt(2 * np.pi))
+        self.L = density / _sequential_sum(density)
         self.approx_ccl = self.ccl_approx_constant()
 
     def update(self, read_lengths: dict) -> None:
+        """`read_lengths`: {read id: length}. Reads of at most 2 mu bases are rejected (truncated) ones and do not count."""
         lens = np.fromiter(read_lengths.values(), dtype=np.int64, count=len(read_lengths))
-        lens = lens[lens > self.mu * 2]                       # rejected (truncated) reads are ignored
-        lens = np.minimum(lens, int(1e6) - 1)                 # whales count as 1M - 1
-        np.add.at(self.read_lengths, lens, np.uint16(1))      # uint16 counters, as upstream
-        seen = np.nonzero(self.read_lengths)
-        if len(seen[0]) == 0:
+        lens = np.minimum(lens[lens > 2 * self.mu], self.MAX_LEN - 1)
+        np.add.at(self.read_lengths, lens, np.uint16(1))                   # uint16 counters wrap like upstream's
+        seen = np.flatnonzero(self.read_lengths)
+        if seen.size == 0:
             logging.info("Attempted update of read lengths before observing any reads")
             return
-        self.lam = np.sum(seen * self.read_lengths[seen]) / np.sum(self.read_lengths[seen])
-        self.longest_read = np.max(np.where(self.read_lengths))
-        self.L = np.copy(self.read_lengths[: self.longest_read + 1]).astype("float64")
-        self.L /= sum(self.L)
+        n = self.read_lengths[seen].astype(np.int64)
+        self.lam = np.float64(int(np.dot(seen, n))) / np.float64(int(n.sum()))   # exact integers, one rounding
+        self.longest_read = seen[-1]
+        hist = self.read_lengths[: self.longest_read + 1].astype(np.float64)
+        self.L = hist / _sequential_sum(hist)
         self.approx_ccl = self.ccl_approx_constant()
         logging.info(f"rld: {self.approx_ccl}")
-        self.time_cost = self.lam - 400 - 300                 # lambda - mu - rho; absent before the first update
+        self.time_cost = self.lam - 400 - 300                              # lambda - mu - rho (readlengthdist.py:68)
 
     def ccl_approx_constant(self) -> np.ndarray:
-        ccl = np.zeros(len(self.L) + 1)
-        ccl[0] = 1
-        ccl[1:] = 1 - np.concatenate((self.L[1:].cumsum(), np.ones(1)))
-        ccl[ccl < 1e-6] = 0
-        ccl = np.concatenate((np.trim_zeros(ccl, trim="b"), np.zeros(1)))
-        self.ccl = ccl
-        steps = np.zeros(self.eta - 1, dtype="int32")
-        i = 0
-        for part in range(self.eta - 1):
-            prob = 1 - (part + 0.5) / (self.eta - 1)
-            while (ccl[i] > prob) and (len(ccl) > i):
-                i += 1
-            steps[part] = i
-        return steps
+        """Survival function ccl[i] = P(length > i) (kept as `self.ccl`, cut below 1e-6 and closed with one 0) and its
+        `eta - 1` step positions: the first index where it is <= 1 - (k + 0.5) / (eta - 1)."""
+        survival = np.empty(len(self.L) + 1)
+        survival[0] = 1
+        survival[1:-1] = 1 - np.cumsum(self.L[1:])
+        survival[-1] = 0                                                   # 1 - 1: every read ends somewhere
+        survival[survival < self.CUTOFF] = 0
+        self.ccl = np.append(np.trim_zeros(survival, trim="b"), 0.0)
+        levels = 1 - (np.arange(self.eta - 1) + 0.5) / (self.eta - 1)
+        # non-increasing array: (entries > level) = len - (entries <= level), counted on the ascending view
+        above = len(self.ccl) - np.searchsorted(self.ccl[::-1], levels, side="right")
+        return above.astype("int32")
 
 
 class ReadStartDist:
@@ -256,21 +271,11 @@ class ReadStartDist:
         return self._merged
 
     def update_f_pointmass(self) -> np.ndarray:
-        merged = self.merge()
-        nw = merged.shape[0]
-        fhat = np.zeros(shape=merged.shape)
-        nzi = np.nonzero(merged)
-        nz = merged[nzi]
-        csum = np.sum(nz)
-        fhat[nzi] = np.divide(np.add(self.alpha, nz), 2 * nw * self.alpha + csum)
-        rhs = self.alpha / (2 * nw * self.alpha + csum)
-        beta_num = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha + csum)))
-        beta_denom = np.exp(betaln(self.alpha, ((2 * nw - 1) * self.alpha))) or 1e-20
-        p0_bit = self.p0 / (self.p0 + (1 - self.p0))
-        zero = np.ones(shape=fhat.shape, dtype="bool")
-        zero[nzi] = 0
-        fhat[zero] = (1 - p0_bit * (beta_num / beta_denom)) * rhs
-        return fhat
+        """F-hat per window and strand, compact (before expansion): (alpha + C) / denom where reads have started,
+        the point-mass posterior elsewhere (readstartdist.py:86-115) — the same three scalars the GPU is handed."""
+        counts = self.merge()
+        alpha, denom, zero_value = self.pointmass_scalars(csum=np.sum(counts[counts != 0]))
+        return np.where(counts != 0, np.divide(np.add(alpha, counts), denom), zero_value)
 
     def expand(self, fhat_windows: np.ndarray, downsample_window: int = 100) -> np.ndarray:
         f = np.repeat(fhat_windows, int(self.window_size // downsample_window), axis=0)

@@ -417,16 +417,19 @@ class BossRuns:
         # `time_cost` does not exist before the first successful read-length update (Q14). Upstream only
         # reads it once some bucket is on (core.py:172,192), so the AttributeError is raised at that point.
         time_cost = getattr(self.rl_dist, "time_cost", None)
-        out = self.engine.update(approx_ccl=self.rl_dist.approx_ccl,
-                                 time_cost=np.float64("nan") if time_cost is None else time_cost,
-                                 bucket_threshold=self.bucket_threshold, fhat_scalars=scalars, debug=self.write_debug)
+        try:
+            out = self.engine.update(approx_ccl=self.rl_dist.approx_ccl,
+                                     time_cost=np.float64("nan") if time_cost is None else time_cost,
+                                     bucket_threshold=self.bucket_threshold, fhat_scalars=scalars, debug=self.write_debug)
+        except AttributeError:
+            # a bucket is on and there is no time_cost: the library stopped after the switches (no strategy was touched)
+            self._pull_switches()
+            raise
         t2 = _t.perf_counter()
         self.last = out
         self._pull_switches()
         t3 = _t.perf_counter()
         if out.switched_on:
-            if time_cost is None:
-                self.rl_dist.time_cost      # AttributeError, as upstream
             self.threshold = out.threshold
             self._pull_strategies()
             t4 = _t.perf_counter()

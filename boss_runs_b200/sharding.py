@@ -559,13 +559,15 @@ class ShardedRun(BossRuns):
     def update_wrapper(self) -> None:
         scalars = self.read_starts.pointmass_scalars()
         time_cost = getattr(self.rl_dist, "time_cost", None)
-        out = self._phases(self.rl_dist.approx_ccl, np.float64("nan") if time_cost is None else time_cost,
-                           self.bucket_threshold, fhat_scalars=scalars)
+        try:
+            out = self._phases(self.rl_dist.approx_ccl, np.float64("nan") if time_cost is None else time_cost,
+                               self.bucket_threshold, fhat_scalars=scalars)
+        except AttributeError:              # Q14: a bucket is on, no time_cost — the library left every strategy as it was
+            self._pull_switches()
+            raise
         self.last = out
         self._pull_switches()
         if out.switched_on:
-            if time_cost is None:
-                self.rl_dist.time_cost      # AttributeError, as upstream (Q14)
             self.threshold = out.threshold
             self._pull_strategies()
             if self.group.rank == 0:

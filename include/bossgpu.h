@@ -41,6 +41,9 @@ extern "C" {
 #define BOSSGPU_EEMPTY       -7   /* all benefits are zero: upstream `np.max` of an empty array raises
                                      ValueError (sequences.py:588) */
 #define BOSSGPU_EPEER        -8   /* sharded update: a peer shard did not reach an exchange step in time */
+#define BOSSGPU_ENOTC        -9   /* a bucket is on but update_params.tc is NaN: upstream has no `time_cost` before the first
+                                     successful ReadlengthDist.update (readlengthdist.py:68) and raises AttributeError when
+                                     update_wrapper reads it (core.py:192); switches are updated, no strategy is touched */
 
 /* model constants of the reference (function defaults upstream, fixed here) */
 #define BOSSGPU_BIN          100     /* downsampling window: reference.py:109,215 ; sequences.py:577 */
@@ -328,6 +331,10 @@ int bossgpu_buckets_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes);
 /* exponent histogram of the last update: counts int64[HIST_BINS], f_grid float64[HIST_BINS]
  * (sequences.py:593-624, before the empty bins are dropped) */
 int bossgpu_get_hist(bossgpu_handle* h, int64_t* counts, double* f_grid);
+/* F-hat as the last update's histogram consumed it: float64 [n_rows][2] for rows [row0, row0 + n_rows) of the merged,
+ * length-adjusted axis (expansion x20 + both tail fixes + normalisation, readstartdist.py:121-152, core.py:184-185;
+ * identical for every barcode, core.py:175). Rows >= n_sites_total // 100 read 0. */
+int bossgpu_get_fhat(bossgpu_handle* h, int64_t row0, int64_t n_rows, double* out);
 /* the dense score table: float64 [N_PATTERNS][4] (replaces score_arr / entropy_arr, sequences.py:387-388) */
 int bossgpu_get_score_table(bossgpu_handle* h, double* scores, double* entropies);
 /* rank of a count pattern (c0..c4, sum <= 29) in that table; -1 if out of range */

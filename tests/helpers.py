@@ -86,6 +86,51 @@ def compare_state(prod, orc, updated: bool, tag: str):
             ben = orc.benefit_adj[i: i + n]
             assert_masks_match(pc.strat, oc.strat, ben, orc.threshold, f"{tag}/{name}: strat")
             i += n
+        compare_hist_stage(prod, orc, tag)
+
+
+def compare_hist_stage(prod, orc, tag: str):
+    """The histogram stage of the threshold derivation (sequences.py:584-630) against the oracle's own intermediates:
+    normaliser, per-exponent counts and F-hat mass, ubar0, and the F-hat array the device expanded by itself."""
+    from boss_runs_b200._lib import HIST_BINS
+    d = orc.diag
+    norm = float(d["normaliser"])
+    assert abs(prod.last.normaliser - norm) <= tol.NORM_RTOL * norm, f"{tag}: normaliser {prod.last.normaliser!r} vs {norm!r}"
+    # F-hat rows as k_hist reads them (expansion x20, tail fixes and normalisation happen on the device)
+    target = orc.fhat_adj.shape[0]
+    got_f = prod.engine.fhat_rows(0, target)
+    for b in range(orc.fhat_adj.shape[2]):
+        np.testing.assert_allclose(got_f, orc.fhat_adj[:, :, b], rtol=tol.FHAT_RTOL, atol=0, err_msg=f"{tag}: device F-hat")
+    counts, f_grid = prod.engine.hist()
+    want_c = np.zeros(HIST_BINS, dtype=np.int64)
+    want_f = np.zeros(HIST_BINS)
+    want_c[d["exponents"]] = d["counts"]
+    want_f[d["exponents"]] = d["f_grid"]
+    # an oracle entry may fall either side of a bin edge (a power of two times the normaliser) when it lies within the
+    # tolerance of the smoothed arrays of it: relative SMOOTH_RTOL plus the absolute floor SMOOTH_ATOL_FRAC * max
+    flat = orc.benefit_adj.flatten("F")
+    nz = flat[flat != 0]
+    ratio = nz / norm
+    m, e = np.frexp(ratio)
+    width = tol.SMOOTH_RTOL * ratio + tol.SMOOTH_ATOL_FRAC
+    near = (ratio - np.ldexp(0.5, e) <= width) | (np.ldexp(1.0, e) - ratio <= width)
+    e = np.abs(e)
+    slack = np.zeros(HIST_BINS + 1, dtype=np.int64)
+    if near.any():
+        k = np.bincount(e[near], minlength=HIST_BINS)[:HIST_BINS]
+        slack[:HIST_BINS] += k
+        slack[1:HIST_BINS + 1] += k
+        slack[:HIST_BINS - 1] += k[1:]
+    H = tol.HIST_HEAD
+    bad = np.abs(counts[:H] - want_c[:H]) > slack[:H]
+    assert not bad.any(), f"{tag}: histogram counts differ at exponents {np.nonzero(bad)[0]}: {counts[:H][bad]} vs {want_c[:H][bad]}"
+    clean = slack[:H] == 0
+    np.testing.assert_allclose(f_grid[:H][clean], want_f[:H][clean], rtol=tol.HIST_F_RTOL, atol=0, err_msg=f"{tag}: f_grid")
+    # tail: whatever the GPU still counts there must be (near-)zero in the oracle as well
+    n_small = int((flat < np.ldexp(norm, -(H - 1))).sum())
+    assert int(counts[H:].sum()) <= n_small, f"{tag}: {int(counts[H:].sum())} tail entries on the GPU, {n_small} near-zero in the oracle"
+    assert abs(prod.last.ubar0 - float(d["ubar0"])) <= tol.UBAR_RTOL * abs(float(d["ubar0"])), \
+        f"{tag}: ubar0 {prod.last.ubar0!r} vs {float(d['ubar0'])!r}"
 
 
 def oracle_sim_step(orc, seqs, paf_full, paf_trunc, barcodes, all_ids):

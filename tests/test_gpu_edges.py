@@ -215,6 +215,73 @@ def test_split_score_pass_is_invisible(lib):
     assert split.last.n_dropout > 0 and (split.contigs["a"].coverage.sum(axis=1) >= 30).any()
 
 
+def test_rejected_batch_leaves_no_trace(lib):
+    """A batch that upstream rejects with IndexError (a character outside ACGT in an aligned column) must not reach the
+    state at all: upstream discards `tmp_cov` of that contig (reference.py:128-146). The aligned-column check runs
+    before any counter or depth total is touched, so coverage, dropout thresholds and every later update equal the
+    oracle that never saw the batch — through the text ingest and through the pre-tokenised one."""
+    lens = {"a": 200_000}
+    contigs, run = make_run(lens, bucket_threshold=0)
+    orc = H.oracle_run(list(contigs.items()), 1, [], None, 0)
+    ref = contigs["a"]
+    for b in range(3):
+        rb = synth.read_batch(contigs, n_reads=900, seed=1200 + b, mean_len=3000.0, min_len=300, max_len=9000)
+        pd = parse_PAF(io.StringIO(rb.paf_text))
+        if b >= 1:
+            # the same batch plus one reverse-strand read with an N in an aligned column (the walk is mirrored)
+            seqs = dict(rb.seqs)
+            good = ref[7000:7200]
+            bad_fwd = good[:120] + "N" + good[121:]
+            seqs["bad"] = bad_fwd.translate(str.maketrans("ATGC", "TACG"))[::-1]
+            pd_bad = parse_PAF(io.StringIO(rb.paf_text + paf_line("bad", seqs["bad"], 0, 200, "-", "a", 200_000, 7000, 7200, "100M2I98M2D")))
+            before = run.contigs["a"].coverage
+            with pytest.raises(IndexError):
+                orc.ingest(pd_bad, seqs)
+            if b == 1:      # text ingest: 2-bit bases + the list of other characters
+                with pytest.raises(IndexError):
+                    run._effect_increments(run.cc.convert_records(pd_bad, seqs))
+            else:           # pre-tokenised ingest: bases as bytes
+                d = run.pack_for_device(run.cc.convert_records(pd_bad, seqs))
+                with pytest.raises(IndexError):
+                    run.engine.ingest_packed(d["seg"], d["tstart"], d["barcode"], d["cig_off"], d["cigar"], d["base_off"], d["bases"],
+                                             ascii_bases=True, contig_cov_add=d["cov_add"])
+            assert np.array_equal(run.contigs["a"].coverage, before), "a rejected batch must not touch the counters"
+            assert np.array_equal(orc.contigs["a"].coverage, before)
+        H.oracle_step(orc, pd, rb.seqs)
+        H.product_step(run, pd, rb.seqs)
+        H.compare_state(run, orc, True, f"after-reject/b{b}")
+    assert run.last.n_dropout > 0           # the depth rule is active: a leaked depth total would have moved its threshold
+
+
+def test_second_ingest_after_announced_batch(lib):
+    """Announce A, ingest A, ingest B, update (e.g. a caller that runs `_effect_increments` twice per batch): the tiles B
+    wrote to carry no marks, so the update has to score every tile again — results equal the run without the split pass."""
+    lens = {"a": 300_000, "b": 160_000}
+    contigs, split = make_run(lens, bucket_threshold=0)
+    _, whole = make_run(lens, bucket_threshold=0)
+    whole.use_prescore = False
+    for b in range(3):
+        rba = synth.read_batch(contigs, n_reads=300, seed=1500 + 2 * b, mean_len=2500.0, min_len=300, max_len=9000)
+        rbb = synth.read_batch(contigs, n_reads=300, seed=1501 + 2 * b, mean_len=2500.0, min_len=300, max_len=9000)
+        pda, pdb = parse_PAF(io.StringIO(rba.paf_text)), parse_PAF(io.StringIO(rbb.paf_text))
+        for run in (split, whole):
+            run.rl_dist.update({rid: recs[0].qlen for rid, recs in pda.items()})
+            run._prescore_begin()
+            inc_a = run.cc.convert_records(pda, rba.seqs)
+            run._prescore(inc_a)
+            run._effect_increments(inc_a)
+            run._effect_increments(run.cc.convert_records(pdb, rbb.seqs))
+            run.count_read_starts(pda)
+            run.update_wrapper()
+        assert (split.threshold, split.last.ubar0, split.last.n_nonzero, split.last.n_dropout) == \
+               (whole.threshold, whole.last.ubar0, whole.last.n_nonzero, whole.last.n_dropout), f"batch {b}"
+        for name in lens:
+            s, w = split.contigs[name], whole.contigs[name]
+            assert np.array_equal(s.coverage, w.coverage)
+            assert np.array_equal(s.scores_ds, w.scores_ds), f"batch {b}/{name}: bins differ"
+            assert np.array_equal(s.strat, w.strat), f"batch {b}/{name}: masks differ"
+
+
 def test_packed_strategy_file_matches_npz(lib, tmp_path):
     """`strategy_format="both"`: boss.bits (packed on the GPU) and upstream's boss.npz describe the same masks, for a
     reference with a reject ref and barcodes, before the first update and after every update."""

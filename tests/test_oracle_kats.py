@@ -5,6 +5,8 @@ by running the reference here (oracle/make_golden.py:make_kats)."""
 import hashlib
 import io
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -93,9 +95,46 @@ def test_readlength_update_matches_oracle():
         b.update(chunk)
         assert np.array_equal(a.approx_ccl, b.approx_ccl)
         assert a.lam == b.lam and a.time_cost == b.time_cost
+        assert np.array_equal(a.L, b.L) and a.longest_read == b.longest_read          # bit for bit
     empty = hostmodel.ReadlengthDist()
     empty.update({"r": 500})                                         # below 2*mu: ignored, no time_cost yet
     assert not hasattr(empty, "time_cost")
+
+
+def test_readlength_model_equals_upstream_class():
+    """The array-shaped `hostmodel.ReadlengthDist` against upstream's own class (imported when the reference is mounted;
+    boss/readlengthdist.py needs nothing but NumPy): prior, every attribute after each update, whales, short reads,
+    single-length and bimodal histograms."""
+    import sys
+    ref = Path("/root/reference")
+    if not (ref / "boss" / "readlengthdist.py").is_file():
+        pytest.skip("reference checkout not mounted (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_upstream_rld", ref / "boss" / "readlengthdist.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode, old = True, sys.dont_write_bytecode
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.dont_write_bytecode = old
+    rng = np.random.default_rng(11)
+    for kw in ({}, dict(sd=1000, lam=3000), dict(eta=6)):
+        up, mine = mod.ReadlengthDist(**kw), hostmodel.ReadlengthDist(**kw)
+        assert np.array_equal(up.L, mine.L) and np.array_equal(up.ccl, mine.ccl) and np.array_equal(up.approx_ccl, mine.approx_ccl)
+        assert mine.approx_ccl.dtype == up.approx_ccl.dtype
+        batches = [
+            {f"a{i}": int(x) for i, x in enumerate(np.clip(rng.gamma(4, 2500, size=500), 50, 3_000_000))},
+            {"w1": 1_000_000, "w2": 5_000_000, "s": 799, "t": 800, "u": 801},
+            {f"b{i}": 12_345 for i in range(70_000)},                                    # uint16 counter wraps
+            {f"c{i}": int(x) for i, x in enumerate(np.concatenate([rng.normal(1500, 50, 400), rng.normal(60_000, 3000, 400)]))},
+        ]
+        for bt in batches:
+            up.update(bt)
+            mine.update(bt)
+            for attr in ("lam", "longest_read", "time_cost"):
+                assert getattr(up, attr) == getattr(mine, attr), attr
+            for attr in ("read_lengths", "L", "ccl", "approx_ccl"):
+                assert np.array_equal(getattr(up, attr), getattr(mine, attr)), attr
 
 
 def _real_batch(kats):
