@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py — strategy-update latency and Gsites/s (BASELINE.json metric) on 1..N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c4|c5]
 
 One "step" = one strategy update over one batch of synthetic mappings: coverage scatter -> score/bin pass
 -> bucket switches -> smoothing -> exponent histogram -> threshold -> bucket-gated masks.
 
 * `value` / `ms_per_step`: inputs (tokenised batch, F-hat) already resident in HBM, timed with CUDA events
   on the launching stream, max over ranks.
-* `e2e`: the same update through the reference-facing API (`BossRuns.process_batch_runs`) with HOST
-  buffers: record marshalling, C++ CIGAR tokeniser, H2D, kernels, D2H of every contig's mask.
+* `e2e`: `BossRuns.process_batch_runs(paf_dict, seqs)` itself — the call a user makes — from Python objects and host
+  strings to every `Contig.strat` on the host (record choice, H2D, tokeniser, scatter, read starts, update, mirror).
 * `roofline`: the score/bin pass (dominant kernel) against the measured HBM peak of MEASURED_PEAKS.json.
-* `cpu_baseline` / `--impl reference`: the oracle port (NumPy restatement of the reference, oracle/) timed on
-  this box's host cores on a bounded sample of the same workload.
+* `cpu_baseline` / `--impl reference`: the oracle port (NumPy restatement of the reference CPU path, oracle/) on this
+  box's host cores — one worker process per core, each on its own contig of the same ploidy / depth / read model
+  (upstream's per-contig loops are independent, core.py:83-121), a bounded sample of the workload.
+* `checksum`: threshold bits + number of accepted entries over every contig's mask after the last update; identical for
+  every N (the sharded update is bit-identical to the one-GPU update).
 
 Workloads (BASELINE.json configs): c3 = 3.1 Gb diploid, 25 contigs (the metric's configuration; default),
-c2 = 4.6 Mb haploid, c4 = 24 barcodes x 5 Mb, c5 = many-contig metagenome. `--scale` shrinks a workload
-for development.
+c2 = 4.6 Mb haploid, c4 = 24 barcodes x 5 Mb, c5 = 2 000-contig metagenome with reject refs. `--scale` shrinks a
+workload for development.
 """
 from __future__ import annotations
 
@@ -46,20 +49,37 @@ def workload_spec(name: str, scale: float):
     from boss_runs_b200 import synth
     if name == "c3":
         lens = synth.grch38_like_lengths(int(3_100_000_000 * scale), 25)
-        return dict(name="c3: synthetic 3.1 Gb diploid, 25 contigs, state Poisson(8) + 2% dropout + 1% deep regions, 4000 x 10 kb read batches",
-                    lengths=lens, ploidy=2, nb=1, reads=4000, mean_len=10_000.0, depth=8.0)
+        return dict(key="c3", name="c3: synthetic 3.1 Gb diploid, 25 contigs, state Poisson(8) + 2% dropout + 1% deep regions, 4000 x 10 kb read batches",
+                    lengths=lens, ploidy=2, nb=1, reads=4000, mean_len=10_000.0, depth=8.0, reject=[])
     if name == "c2":
-        return dict(name="c2: synthetic 4.6 Mb haploid, 4000 x 10 kb read batches", lengths=[int(4_600_000 * scale)],
-                    ploidy=1, nb=1, reads=4000, mean_len=10_000.0, depth=8.0)
+        return dict(key="c2", name="c2: synthetic 4.6 Mb haploid, 4000 x 10 kb read batches", lengths=[int(4_600_000 * scale)],
+                    ploidy=1, nb=1, reads=4000, mean_len=10_000.0, depth=8.0, reject=[])
     if name == "c4":
-        return dict(name="c4: 24 barcodes x 5 Mb", lengths=[int(5_000_000 * scale)], ploidy=1, nb=24, reads=4000,
-                    mean_len=10_000.0, depth=4.0)
+        return dict(key="c4", name="c4: 24 barcodes x 5 Mb, 4000 x 10 kb read batches over all barcodes", lengths=[int(5_000_000 * scale)],
+                    ploidy=1, nb=24, reads=4000, mean_len=10_000.0, depth=4.0, reject=[])
     if name == "c5":
+        # BASELINE.json configs[4]: 2 000 contigs, lengths log-uniform 10 kb-5 Mb, 10 % of the names in reject_refs;
+        # contigs under 100 kb are dropped by the loader (reference.py:319,330) and rejected ones keep a (1,) mask
         rng = np.random.default_rng(13)
-        lens = np.exp(rng.uniform(np.log(100_000), np.log(5_000_000), size=int(150 * scale) or 1)).astype(np.int64)
-        return dict(name="c5: metagenome-style, 150 contigs 100 kb-5 Mb", lengths=[int(x) for x in lens], ploidy=1, nb=1,
-                    reads=4000, mean_len=10_000.0, depth=8.0)
+        n = max(int(2000 * scale), 4)
+        lens = np.exp(rng.uniform(np.log(10_000), np.log(5_000_000), size=n)).astype(np.int64)
+        rej = sorted(int(i) for i in rng.choice(n, size=n // 10, replace=False))
+        return dict(key="c5", name="c5: metagenome-style, 2000 contigs 10 kb-5 Mb (those under 100 kb dropped at load), 10 % reject refs, 4000 x 10 kb read batches",
+                    lengths=[int(x) for x in lens], ploidy=1, nb=1, reads=4000, mean_len=10_000.0, depth=8.0, reject=rej)
     raise SystemExit(f"unknown workload {name}")
+
+
+def tracked_lengths(spec) -> list[int]:
+    rej = set(spec["reject"])
+    return [L for i, L in enumerate(spec["lengths"]) if L >= 100_000 and i not in rej]
+
+
+def config_of(spec) -> dict:
+    """The workload as both arms print it (identical objects: the driver compares them)."""
+    trk = tracked_lengths(spec)
+    return {"workload": spec["name"], "sites": int(sum(trk)), "tracked_contigs": len(trk), "barcodes": spec["nb"],
+            "ploidy": spec["ploidy"], "reads_per_batch": spec["reads"],
+            "l2": "inputs exceed L2 (counters 10 B/site/barcode: 46 MB ... 31 GB vs 126 MB); 3 batches cycled"}
 
 
 def random_codes(lengths, seed=7):
@@ -117,32 +137,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on a bounded sample
+# CPU arm: the oracle port on a bounded sample, one worker process per host core
 # ------------------------------------------------------------------------------------------------------
-def cpu_sample(spec, steps: int, warmup: int, sample_sites: int = 20_000_000, sample_reads: int = 26):
-    """Oracle (NumPy restatement of the reference's CPU path) on ONE contig of `sample_sites` with the same
-    ploidy / read model / pre-loaded depth as the workload and a proportionally scaled batch.
-    Returns (sites per second, description, seconds per update)."""
+def _cpu_worker(wid, spec, L, n_reads, n_updates, go, done, out):
+    """One contig of L sites through the oracle, `n_updates` updates; every update waits for `go` so that all
+    workers run the same update at the same time (wall time of an update = the slowest worker)."""
     sys.path.insert(0, str(REPO / "tests"))
     from oracle import boss_oracle as bo
     from boss_runs_b200 import synth
     from boss_runs_b200.hostmodel import parse_PAF
-
-    L = int(min(sample_sites, sum(spec["lengths"])))
-    L = max(L, 120_000)
-    total = sum(spec["lengths"]) * spec["nb"]
-    n_reads = max(4, int(round(spec["reads"] * L * spec["nb"] / total))) if total > L else spec["reads"]
-    n_reads = min(n_reads, spec["reads"], sample_reads if total > L else spec["reads"])
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + wid)
     codes = rng.integers(0, 4, size=L, dtype=np.uint8)
-    barcodes = [f"barcode{i + 1:02d}" for i in range(spec["nb"])] if spec["nb"] > 1 else None
-
-    class _Seq(str):
-        pass
+    nb = spec["nb"]
+    barcodes = [f"barcode{i + 1:02d}" for i in range(nb)] if nb > 1 else None
     run = bo.OracleRun.__new__(bo.OracleRun)
-    run.barcodes, run.nb = barcodes, spec["nb"]
+    run.barcodes, run.nb = barcodes, nb
     hap = bo.ScoreModel(1)
-    c = bo.ContigState("s1", codes, nb=spec["nb"], score0=hap.score0, ent0=hap.ent0)
+    c = bo.ContigState("s1", codes, nb=nb, score0=hap.score0, ent0=hap.ent0)
     run.contigs = {"s1": c}
     run.contigs_filt = run.contigs
     run.n_sites = L
@@ -152,7 +163,7 @@ def cpu_sample(spec, steps: int, warmup: int, sample_sites: int = 20_000_000, sa
     run.rl = bo.ReadLengths()
     run.bucket_threshold = 5
     # pre-loaded sequencing state, as if earlier batches had been ingested
-    depth = rng.poisson(spec["depth"], size=(L, spec["nb"]))
+    depth = rng.poisson(spec["depth"], size=(L, nb))
     ref_cnt = rng.binomial(depth, 0.9)
     rest = depth - ref_cnt
     c.coverage[np.arange(L), codes, :] = ref_cnt.astype(np.uint16)
@@ -160,44 +171,82 @@ def cpu_sample(spec, steps: int, warmup: int, sample_sites: int = 20_000_000, sa
     c.coverage[np.arange(L), (codes + 1) & 3, :] += (rest - rest // 2).astype(np.uint16)
     c.change_mask[:] = True
     contigs = {"s1": codes}
-    times = []
-    for it in range(warmup + steps):
-        rb = synth.read_batch(contigs, n_reads=n_reads, seed=900 + it, mean_len=spec["mean_len"],
-                              n_barcodes=spec["nb"] if spec["nb"] > 1 else 0)
+    batches = []
+    for it in range(min(n_updates, 3)):
+        rb = synth.read_batch(contigs, n_reads=n_reads, seed=900 + 7 * wid + it, mean_len=spec["mean_len"], n_barcodes=nb if nb > 1 else 0)
         pd = parse_PAF(io.StringIO(rb.paf_text))
         for rid, recs in pd.items():
             for r in recs:
                 r.barcode = rb.barcodes.get(rid) if barcodes else None
+        batches.append((pd, rb.seqs))
+    out.put(("ready", wid, 0.0))
+    for it in range(n_updates):
+        pd, seqs = batches[it % len(batches)]
         run.rl.update({rid: recs[0].qlen for rid, recs in pd.items()})
+        go.wait()
         t0 = time.perf_counter()
         if it == 0:
             cm = c.change_mask.copy()
-        run.ingest(pd, rb.seqs)
+        run.ingest(pd, seqs)
         if it == 0:
-            c.change_mask |= cm           # first update scores the whole pre-loaded state
+            c.change_mask |= cm           # the first update scores the whole pre-loaded state
         run.read_starts.count(pd)
         run.update()
-        dt = time.perf_counter() - t0
+        out.put(("step", wid, time.perf_counter() - t0))
+        done.wait()
+
+
+def cpu_sample(spec, steps: int, warmup: int, sites_per_worker: int = 20_000_000, max_workers: int = 32):
+    """Returns (sites per second, description, seconds per update, workers)."""
+    import multiprocessing as mp
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    total = sum(tracked_lengths(spec)) * spec["nb"]
+    L = int(min(sites_per_worker, max(sum(tracked_lengths(spec)), 120_000)))
+    per_site = 110 * spec["nb"] + 20                     # oracle: counters + tmp, three fp64 arrays, masks, transients
+    workers = int(max(1, min(cores, max_workers, avail * 0.6 // (L * per_site), max(1, total // max(L * spec["nb"], 1)))))
+    n_reads = max(4, int(round(spec["reads"] * L * spec["nb"] / total))) if total > L * spec["nb"] else spec["reads"]
+    ctx = mp.get_context("spawn")                        # the parent may hold a CUDA context: never fork it
+    go, done, out = ctx.Barrier(workers + 1), ctx.Barrier(workers + 1), ctx.Queue()
+    n_updates = warmup + steps
+    procs = [ctx.Process(target=_cpu_worker, args=(w, spec, L, n_reads, n_updates, go, done, out), daemon=True) for w in range(workers)]
+    for p in procs:
+        p.start()
+    for _ in range(workers):
+        assert out.get(timeout=900)[0] == "ready"
+    walls = []
+    for it in range(n_updates):
+        go.wait()
+        t0 = time.perf_counter()
+        for _ in range(workers):
+            out.get(timeout=1800)
+        wall = time.perf_counter() - t0
+        done.wait()
         if it >= warmup:
-            times.append(dt)
-    sec = float(np.median(times))
-    desc = (f"oracle port (NumPy restatement of the reference CPU path): 1 contig of {L} sites x {spec['nb']} barcode(s), "
-            f"ploidy {spec['ploidy']}, pre-loaded depth ~{spec['depth']}, {n_reads} reads of ~{int(spec['mean_len'])} bp per update; "
-            f"median of {steps} updates after {warmup} warm-up")
-    return L * spec["nb"] / sec, desc, sec
+            walls.append(wall)
+    for p in procs:
+        p.join(timeout=30)
+    sec = float(np.mean(walls))
+    desc = (f"oracle port (NumPy restatement of the reference CPU path, single-threaded like upstream) in {workers} worker processes "
+            f"(host has {cores} cores, {avail / 2**30:.0f} GiB free), each on its own contig of {L} sites x {spec['nb']} barcode(s), ploidy "
+            f"{spec['ploidy']}, pre-loaded depth ~{spec['depth']}, {n_reads} reads of ~{int(spec['mean_len'])} bp per worker and update; "
+            f"wall time per update = slowest worker; mean of {steps} updates after {warmup} warm-up")
+    return workers * L * spec["nb"] / sec, desc, sec, workers
 
 
 def run_reference_arm(args, spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 5)
-    warm = min(args.warmup, 1)
-    v, desc, sec = cpu_sample(spec, steps=steps, warmup=max(warm, 1))
-    line = {"metric": METRIC, "value": v / 1e9, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(warm, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": spec["name"]},
-            "cpu_baseline": {"value": v / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
+    v, desc, sec, workers = cpu_sample(spec, steps=args.steps, warmup=args.warmup)
+    line = {"metric": METRIC, "value": v / 1e9, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(spec),
+            "cpu_baseline": {"value": v / 1e9, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc},
             "e2e": {"value": v / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -205,12 +254,20 @@ def run_reference_arm(args, spec):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def checksum_of(run) -> dict:
+    """Threshold bits + accepted entries over every tracked contig's mask (rank 0 sees all of them)."""
+    thr = run.threshold
+    acc = int(sum(int(np.count_nonzero(c.strat)) for c in run.contigs_filt.values()))
+    tot = int(sum(c.strat.size for c in run.contigs_filt.values()))
+    return {"threshold_hex": None if thr is None else float(thr).hex(), "accepted_entries": acc, "mask_entries": tot}
+
+
 def run_b200(args, spec):
     import torch
     from boss_runs_b200 import build, synth
     from boss_runs_b200.hostmodel import parse_PAF
     from boss_runs_b200.runs import BossRuns
-    
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,36 +283,38 @@ def run_b200(args, spec):
         from boss_runs_b200.sharding import ShardedRun
     lengths = spec["lengths"]
     names = [f"ctg{i + 1}" for i in range(len(lengths))]
-    codes = random_codes(lengths)
-    total_sites = int(sum(lengths)) * spec["nb"]
+    rej = set(spec["reject"])
+    kept = [i for i, L in enumerate(lengths) if L >= 100_000]             # the loader drops the rest (reference.py:319,330)
+    codes_kept = random_codes([lengths[i] for i in kept])               # reject refs keep their length at load (placeholder afterwards)
+    records = {names[i]: c for i, c in zip(kept, codes_kept)}
+    reject_refs = ",".join(names[i] for i in kept if i in rej) or None
+    tracked = {names[i]: c for i, c in zip(kept, codes_kept) if i not in rej}
+    total_sites = int(sum(len(c) for c in tracked.values())) * spec["nb"]
     barcodes = [f"barcode{i + 1:02d}" for i in range(spec["nb"])] if spec["nb"] > 1 else None
 
     t_setup = time.time()
+    kw = dict(contigs=records, ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5, reject_refs=reject_refs, device=local,
+              strict_upstream_asserts=False)
     if world > 1:
-        run = ShardedRun(contigs=dict(zip(names, codes)), ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5,
-                         device=local, strict_upstream_asserts=False, exchange=args.exchange, fabric_timeout_s=30.0)
+        run = ShardedRun(exchange=args.exchange, fabric_timeout_s=30.0, **kw)
     else:
-        run = BossRuns(contigs=dict(zip(names, codes)), ploidy=spec["ploidy"], barcodes=barcodes, bucket_threshold=5,
-                       device=local, strict_upstream_asserts=False)
+        run = BossRuns(**kw)
     eng = run.engine
     synth_kw = dict(seed=11, mean_depth=spec["depth"], p_ref=0.90, p_del=0.04, frac_dropout=0.02, frac_deep=0.01)
     (run if world > 1 else eng).synth_coverage(**synth_kw)
 
     # read batches: text form for the end-to-end leg, packed + device-resident for the kernel leg
     n_batches = 3
-    contig_arrays = dict(zip(names, codes))
     batches = []
     for b in range(n_batches):
-        rb = synth.read_batch(contig_arrays, n_reads=spec["reads"], seed=1000 + b, mean_len=spec["mean_len"],
-                              n_barcodes=spec["nb"] if spec["nb"] > 1 else 0)
+        rb = synth.read_batch(tracked, n_reads=spec["reads"], seed=1000 + b, mean_len=spec["mean_len"],
+                              n_barcodes=spec["nb"] if spec["nb"] > 1 else 0, codes=tracked)
         pd = parse_PAF(io.StringIO(rb.paf_text))
         for rid, recs in pd.items():
             for r in recs:
                 r.barcode = rb.barcodes.get(rid) if barcodes else None
         batches.append((pd, rb.seqs, rb))
     run.rl_dist.update({rid: recs[0].qlen for pd, _, _ in batches for rid, recs in pd.items()})
-    for pd, _, _ in batches:
-        run.count_read_starts(pd)
     setup_s = time.time() - t_setup
 
     def barrier():
@@ -264,38 +323,36 @@ def run_b200(args, spec):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- leg 1: end to end through the public API, host buffers ------------------------------------------
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    engines = getattr(run, "engines", [eng])
+
+    # ---- leg 1: end to end through the public API, host buffers: the call itself ------------------------------
     e2e_times, e2e_parts = [], []
     h2d = d2h = 0
     for it in range(args.warmup + args.steps):
         pd, seqs, rb = batches[it % n_batches]
         barrier()
         t0 = time.perf_counter()
-        # the body of BossRuns.process_batch_runs, statement by statement, so that its parts can be timed
-        run._prescore_begin()               # split score/bin pass: the GPU scores every tile while the host prepares the batch
-        inc = run.cc.convert_records(paf_dict=pd, seqs=seqs)
-        t1 = time.perf_counter()
-        run._prescore(inc)                  # ... and will re-score only the tiles this batch writes to
-        t1b = time.perf_counter()
-        run._effect_increments(inc)
-        t2 = time.perf_counter()
-        run.update_wrapper()
+        run.process_batch_runs(pd, seqs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             e2e_times.append(dt)
-            e2e_parts.append((t1 - t0, t1b - t1, t2 - t1b, time.perf_counter() - t2))
-            # what the library staged and copied: per-read scalars + CIGAR op slots (4 B) + read bases packed 2 bits each
-            h2d = sum(e.ingest_bytes() for e in getattr(run, "engines", [eng]))
-            h2d += 20 * len(inc) * len(getattr(run, "engines", [eng]))     # the announced intervals (contig i32, tstart/tend i64)
-            # masks reach the host as the 4 KB chunks that changed (written by the distribution kernel into the
+            e2e_parts.append(dict(run.last_batch_ms))
+            n_in = sum(len(v) for v in pd.values())
+            # what the library staged and copied: per-read scalars + CIGAR text + read bases packed 2 bits each, the announced
+            # intervals (contig i32, tstart/tend i64) and the read-start events (window i64, strand u8)
+            h2d = sum(e.ingest_bytes() for e in engines) + (20 + 9) * n_in * len(engines)
+            # masks reach the host as the 512-byte pieces that changed (written by the distribution kernel into the
             # pinned mirror Contig.strat views) + bucket switches + the result record
             d2h = int(run.last.mirror_bytes) + int(sum(c.bucket_switches.size for c in run.contigs_filt.values())) + 256
-    e2e_t = torch.tensor([float(np.mean(e2e_times))], device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+    e2e_s = max_over_ranks(float(np.mean(e2e_times)))
 
     # ---- leg 1b: the same, starting one step earlier — from the mapper's raw PAF text ----------
     # upstream: Paf.parse_PAF(StringIO(paf_raw)) builds {read: [PafLine]} in Python before convert_records
@@ -305,18 +362,14 @@ def run_b200(args, spec):
         pd, seqs, rb = batches[it % n_batches]
         barrier()
         t0 = time.perf_counter()
-        run.process_batch_text(rb.paf_text, seqs)
+        run.process_batch_text(rb.paf_text, seqs, barcodes=rb.barcodes if barcodes else None)
         torch.cuda.synchronize()
         if it >= args.warmup:
             txt_times.append(time.perf_counter() - t0)
     t0 = time.perf_counter()
     parse_PAF(io.StringIO(batches[0][2].paf_text), min_len=200)
     py_parse_ms = (time.perf_counter() - t0) * 1e3
-    txt_t = torch.tensor([float(np.mean(txt_times))], device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(txt_t, op=dist.ReduceOp.MAX)
-    txt_s = float(txt_t.item())
+    txt_s = max_over_ranks(float(np.mean(txt_times)))
 
     # ---- leg 2: inputs resident in HBM -------------------------------------------------------------------
     dev_batches = []
@@ -355,12 +408,7 @@ def run_b200(args, spec):
     ev1.record()
     barrier()
     launches = eng.launch_count() - l0
-    ms = ev0.elapsed_time(ev1) / args.steps
-    ms_t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
+    ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     # A timed region of a few milliseconds is shorter than nvidia-smi's 100 ms sampling period: keep the same workload
     # running (untimed; the same number of extra updates on every rank, derived from the agreed ms) until the sampler has
     # seen ~0.5 s of it, so that the clocks line always describes the GPU under this load.
@@ -372,6 +420,9 @@ def run_b200(args, spec):
         barrier()
     clocks = sampler.stop()
     clocks["sampled_over"] = f"warm-up + timed updates + {n_extra} untimed updates of the same workload"
+    # the state after every leg: the same sequence of batches on every N -> the same strategies
+    run._pull_strategies()
+    check = checksum_of(run)
 
     if rank != 0:
         return
@@ -383,9 +434,15 @@ def run_b200(args, spec):
     # algorithmic bytes of the score/bin pass on THIS rank: 10 B counters + 1 B reference base per
     # site*barcode (the reference base is re-read per barcode) + 8 B per 100-site bin written
     my_sites = run.local_sites() * spec["nb"]
-    alg_bytes = my_sites * 11 + (my_sites // 100) * 8
-    if spec["nb"] > 1:
-        alg_bytes += run.local_sites() * (10 * spec["nb"] + 4 + 4)     # row-summary pre-pass: counters again + 4 B flag write + read
+    if spec["nb"] == 1:
+        alg_bytes = my_sites * 11 + (my_sites // 100) * 8
+    elif spec["nb"] <= 24:
+        # barcodes: one CTA takes a tile through every barcode — counters once, the reference base once per site
+        alg_bytes = my_sites * 10 + run.local_sites() + (my_sites // 100) * 8
+    else:
+        # more barcodes than fit in shared memory: row summary over all barcodes first (counters twice, 4 B flag written
+        # once and read per barcode)
+        alg_bytes = my_sites * 11 + (my_sites // 100) * 8 + run.local_sites() * (10 * spec["nb"] + 4) + my_sites * 4
     k_ms = float(np.mean(score_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -398,34 +455,31 @@ def run_b200(args, spec):
         except Exception:
             traffic = None
     cpu = None
-    if not args.no_cpu:
-        v, desc, sec = cpu_sample(spec, steps=3, warmup=1)
-        cpu = {"value": v / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "s_per_update_on_sample": sec}
+    if not args.no_cpu and world == 1:
+        v, desc, sec, workers = cpu_sample(spec, steps=3, warmup=1)
+        cpu = {"value": v / 1e9, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc, "s_per_update_on_sample": sec}
     mean_t = {k: float(np.mean([t[k] for t in all_ms])) for k in all_ms[0]}
+    parts = {k: float(np.mean([p[k] for p in e2e_parts])) for k in e2e_parts[0]}
     line = {
         "metric": METRIC, "value": total_sites / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["name"], "sites": int(sum(lengths)), "barcodes": spec["nb"], "ploidy": spec["ploidy"],
-                   "reads_per_batch": spec["reads"], "l2": "inputs (counters >= 46 MB ... 31 GB) exceed L2; 3 batches cycled",
-                   "sharding": f"genome axis split over {world} GPU(s)",
-                   "exchange": getattr(run, "exchange_mode", "none")},
+        "dtype": "f64", "data": "synthetic", "config": config_of(spec),
+        "sharding": f"genome axis split over {world} GPU(s)", "exchange": getattr(run, "exchange_mode", "none"),
         "e2e": {"value": total_sites / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h),
-                "host_ms": dict(zip(("convert_records", "announce", "ingest", "update_wrapper"),
-                                    (float(x) * 1e3 for x in np.mean(np.array(e2e_parts), axis=0)))),
-                "update_wrapper_ms": getattr(run, "last_host_ms", None)},
+                "d2h_bytes_per_step": int(d2h), "what": "BossRuns.process_batch_runs(paf_dict, seqs), wall clock around the call",
+                "host_ms": parts, "update_wrapper_ms": getattr(run, "last_host_ms", None)},
         "e2e_from_paf_text": {"value": total_sites / txt_s / 1e9, "unit": UNIT, "ms_per_step": txt_s * 1e3,
                               "what": "BossRuns.process_batch_text: raw PAF text + read strings -> masks on the host (C tokeniser, no PafLine objects)",
                               "python_parse_PAF_ms_avoided": py_parse_ms},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_score_bin", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_score_bin_tma", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                      if pk.exists() else "fallback 6650 GB/s (of fallback)", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": int(alg_bytes)},
         "kernel_ms": mean_t,
         "kernel_ms_steps": {k: [round(t[k], 3) for t in all_ms] for k in ("score_bin", "smooth", "hist", "distribute", "scatter", "update")},
         "mirror_bytes_steps": mirror_steps,
+        "checksum": check,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "setup_s": setup_s,

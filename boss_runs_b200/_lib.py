@@ -74,6 +74,7 @@ SYMBOLS = {
     "bossgpu_prescore_begin": (C.c_int, [_P]),
     "bossgpu_prescore": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     "bossgpu_ingest_records_ptr": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
+    "bossgpu_ingest_records_routed": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
     "bossgpu_strat_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "bossgpu_buckets_host": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "bossgpu_set_strat_mirror": (C.c_int, [_P, _P, C.c_int64, C.c_int]),

@@ -119,6 +119,12 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
     // F-hat terms enter the exact sums as fhat * 2^50 (strategy.cuh, to_limbs_small: one term stays below 2^51 since the
     // normalised F-hat is <= 1; all of them together stay below 2^63: sum(fhat) = 1 per barcode plus tail copies)
     h->fhat_shift = 50;
+    {   // ubar0 = sum(fhat * benefit): each term < fhat * 2^ushift once scaled to the normaliser's binade, all of them
+        // together < n_barcodes * 2^ushift, kept below 2^62
+        int lg = 0;
+        while ((1 << lg) < h->nb) ++lg;
+        h->ubar_shift = 61 - lg;
+    }
 
     // ---- global axes --------------------------------------------------------------------------
     std::vector<int64_t> o_row(h->n_contigs_total + 1, 0), o_srow(h->n_contigs_total + 1, 0);
@@ -324,7 +330,12 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_thr, cudaEventDisableTiming));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_pre_done, cudaEventDisableTiming));
         BOSS_CUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
-        h->prescore_ok = one_each && h->nb == 1 && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
+        h->multi_fused = h->nb > 1 && h->nb <= SBM_MAX_NB && getenv("BOSSGPU_NO_FUSED_BARCODES") == nullptr;
+        h->prescore_ok = one_each && (h->nb == 1 || h->multi_fused) && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
+        if (h->multi_fused) {
+            BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
+            BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
+        }
         BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
     }
     BOSS_CUDA(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -460,7 +471,9 @@ static int launch_scatter(bossgpu_handle* h, int64_t n_reads, int64_t n_slots, c
     a.n_slots = d_cig_off + n_reads; a.rec = ib.rec; a.rec_read = pa.rec_read; a.bases = d_bases; a.base_is_ascii = ascii; a.pk = pk;
     a.P = h->P; a.cov = h->d_cov; a.err = h->d_ingest_err;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_slots, SC_THREADS), (int64_t)h->n_sm * 32));
-    k_scatter_ops<<<grid, SC_THREADS, 0, h->stream>>>(a);
+    if (pk.data) k_scatter_ops<0><<<grid, SC_THREADS, 0, h->stream>>>(a);
+    else if (ascii) k_scatter_ops<1><<<grid, SC_THREADS, 0, h->stream>>>(a);
+    else k_scatter_ops<2><<<grid, SC_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     BOSS_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->ev_valid[0] = true;
@@ -590,7 +603,7 @@ struct TextRead {
 
 static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* contig, const int64_t* tstart,
                             const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
-                            const std::vector<TextRead>& all_reads, int n_threads) {
+                            const std::vector<TextRead>& all_reads, int n_threads, const int64_t* batch_cov_add = nullptr) {
     // The caller hands every shard the WHOLE batch. A shard holds one contiguous range of the genome axis, so
     // at most one of its segments belongs to any contig: reads are routed to that segment when they overlap
     // it (the scatter kernel clips at the segment edges, so a read spanning a shard edge lands in both
@@ -620,6 +633,8 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         if (t1 <= S.start || t0 >= S.start + S.len) continue;
         sel.push_back(i);
     }
+    if (batch_cov_add)                // routed batch: the caller hands the reference span of the WHOLE batch per contig
+        for (int k = 0; k < h->n_contigs_total; ++k) cov_add[k] = (unsigned long long)batch_cov_add[k];
     TRY(spec_order_totals(h));
     if (h->prescore_state == 1)       // is this the batch that was announced? Same reads, same intervals -> its tile marks hold
         h->prescore_state = (n_all == h->pre_n_reads && batch_hash(n_all, contig, tstart, tend) == h->pre_hash) ? 2 : -1;
@@ -860,6 +875,25 @@ extern "C" int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads, co
     return ingest_text_impl(h, n_reads, contig, tstart, tend, barcode, rev, reads, n_threads);
 }
 
+extern "C" int bossgpu_ingest_records_routed(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart,
+                                             const int64_t* tend, const int32_t* barcode, const uint8_t* rev,
+                                             const uint64_t* cigar_ptr, const int64_t* cigar_len, const uint64_t* seq_ptr,
+                                             const int64_t* seq_from, const int64_t* seq_to, const int64_t* batch_cov_add,
+                                             int n_threads) {
+    H_CHECK(h);
+    if (n_reads < 0 || !batch_cov_add) return fail(BOSSGPU_EINVAL, "bad routed batch");
+    if (n_reads > 0 && (!contig || !tstart || !tend || !barcode || !rev || !cigar_ptr || !cigar_len || !seq_ptr || !seq_from || !seq_to))
+        return fail(BOSSGPU_EINVAL, "null batch array");
+    std::vector<TextRead> reads((size_t)n_reads);
+    for (int64_t i = 0; i < n_reads; ++i) {
+        if (seq_to[i] < seq_from[i] || seq_from[i] < 0 || cigar_len[i] < 0)
+            return fail(BOSSGPU_EINVAL, "read %lld: bad slice bounds", (long long)i);
+        reads[i] = TextRead{(const char*)(uintptr_t)cigar_ptr[i], cigar_len[i],
+                            (const char*)(uintptr_t)seq_ptr[i] + seq_from[i], seq_to[i] - seq_from[i]};
+    }
+    return ingest_text_impl(h, n_reads, contig, tstart, tend, barcode, rev, reads, n_threads, batch_cov_add);
+}
+
 // ------------------------------------------------------------------------------------------------
 // update
 // ------------------------------------------------------------------------------------------------
@@ -869,7 +903,8 @@ static int validate_params(const bossgpu_update_params* p) {
         // bn.move_sum raises for window < 1 (reference.py:259-260 with approx_ccl < 100)
         if (p->w[i] < 1) return fail(BOSSGPU_EINVAL, "staircase window %d is %d bins; Bottleneck's move_sum rejects windows < 1", i, p->w[i]);
         if (i > 0 && p->w[i] < p->w[i - 1]) return fail(BOSSGPU_EINVAL, "staircase windows must be non-decreasing");
-        if (p->w[i] > 20000) return fail(BOSSGPU_EINVAL, "staircase window %d exceeds the supported 20000 bins", i);
+        // the smoothing tile (1024 bins + a halo of w - 1 on both sides) has to fit 200 KB of shared memory
+        if (p->w[i] > 12000) return fail(BOSSGPU_EINVAL, "staircase window %d exceeds the supported 12000 bins (1.2 Mb reads)", i);
     }
     return 0;
 }
@@ -924,10 +959,21 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
         BOSS_KERNEL_CHECK();
         a.tile_list = h->d_touched_list;
         a.list_n = reinterpret_cast<const unsigned*>(h->d_pre_misc);
-        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
-        k_score_bin_tma<false, 2, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+        if (h->multi_fused) {
+            dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+            k_score_bin_multi<2><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), h->stream>>>(a, h->n_tiles);
+        } else {
+            dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+            k_score_bin_tma<false, 2, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), h->stream>>>(a, h->n_tiles);
+        }
         BOSS_KERNEL_CHECK();
         h->launches += 2;
+    } else if (h->multi_fused) {
+        // barcodes: one CTA takes a tile through every barcode (row rules Q6/Q8), each counter read once
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+        k_score_bin_multi<0><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), h->stream>>>(a, h->n_tiles);
+        BOSS_KERNEL_CHECK();
+        h->launches++;
     } else {
         if (h->nb > 1) {
             k_rowflags<<<(unsigned)ceil_div(h->P / 4, 256), 256, 0, h->stream>>>(h->P / 4, h->nb, h->P, h->d_cov, h->d_rowflag);
@@ -989,8 +1035,13 @@ extern "C" int bossgpu_prescore_begin(bossgpu_handle* h) {
     BOSS_CUDA(cudaEventRecord(h->ev_pre_thr, st));       // the ingest may add to the totals after this point
     ScoreArgs a = score_args(h);
     a.drop_thr = h->d_drop_thr_spec;
-    dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
-    k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), st>>>(a, h->n_tiles);
+    if (h->multi_fused) {
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+        k_score_bin_multi<0><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), st>>>(a, h->n_tiles);
+    } else {
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
+        k_score_bin_tma<false, 2><<<grid, SBT_THREADS, sbt_smem_bytes(false, 2), st>>>(a, h->n_tiles);
+    }
     BOSS_KERNEL_CHECK();
     BOSS_CUDA(cudaEventRecord(h->ev_pre_done, st));
     h->launches += 2;
@@ -1120,7 +1171,7 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
     BOSS_CUDA(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned long long) * (3 * HBINS + 4), h->stream));
     HistArgs a;
     a.benefit = h->d_benefit; a.n_rows = h->n_rows; a.nb = h->nb; a.R0 = h->R0; a.M = h->M_rows; a.target = h->target_rows;
-    a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.hist = h->d_hist; a.upd = h->d_upd; a.codes = h->d_codes;
+    a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.ushift = h->ubar_shift; a.hist = h->d_hist; a.upd = h->d_upd; a.codes = h->d_codes;
     const int64_t n_groups = (h->R0 + h->n_rows - 1) / HIST_GROUP - h->R0 / HIST_GROUP + 1;     // groups of the global row axis
     unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_groups, HIST_THREADS), (int64_t)h->n_sm * 10));
     k_hist<<<dim3(gx, (unsigned)h->nb), HIST_THREADS, 0, h->stream>>>(a);
@@ -1132,7 +1183,7 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
 
 static int phase3_threshold(bossgpu_handle* h, const bossgpu_update_params* p) {
     EV_BEGIN(5);
-    k_threshold<<<1, THR_THREADS, 0, h->stream>>>(h->d_hist, h->fhat_shift, p->tc, h->d_upd);
+    k_threshold<<<1, THR_THREADS, 0, h->stream>>>(h->d_hist, h->fhat_shift, h->ubar_shift, p->tc, h->d_upd);
     BOSS_KERNEL_CHECK();
     h->launches++;
     EV_END(5);
@@ -1442,7 +1493,7 @@ static int preload_update_kernels() {
     PRELOAD(k_drop_thresholds); PRELOAD(k_rowflags); PRELOAD(k_buckets);
     PRELOAD(k_score_bin<false>); PRELOAD(k_score_bin<true>);
     PRELOAD(k_score_bin_tma<false, 2>); PRELOAD(k_score_bin_tma<false, 4>); PRELOAD(k_score_bin_tma<true, 2>);
-    PRELOAD(k_score_bin_tma<false, 2, 2>); PRELOAD(k_mark_tiles); PRELOAD(k_mark_changed); PRELOAD(k_tile_reduce);
+    PRELOAD(k_score_bin_tma<false, 2, 2>); PRELOAD(k_score_bin_multi<0>); PRELOAD(k_score_bin_multi<2>); PRELOAD(k_mark_tiles); PRELOAD(k_mark_changed); PRELOAD(k_tile_reduce);
     PRELOAD(k_fhat_from_counts); PRELOAD(k_fhat_sum); PRELOAD(k_fhat_finish);
     PRELOAD(k_smooth); PRELOAD(k_smooth_direct); PRELOAD(k_hist); PRELOAD(k_threshold); PRELOAD(k_pack_mask);
     PRELOAD(k_distribute<true>); PRELOAD(k_distribute<false>);
@@ -1500,6 +1551,12 @@ extern "C" int bossgpu_update_fused_begin(bossgpu_handle* h, const bossgpu_updat
     if (!h->fabric_attached) return fail(BOSSGPU_ESTATE, "bossgpu_fabric_attach has not been called");
     if (h->fused_open) return fail(BOSSGPU_ESTATE, "previous bossgpu_update_fused_begin has no matching _end");
     if (!p->fhat_from_counts && !p->fhat_windows && !h->have_fhat) return fail(BOSSGPU_ESTATE, "no F-hat uploaded yet");
+    // Everything that can fail without the GPU's help happens BEFORE the first exchange kernel is enqueued: a shard that
+    // gave up half-way would leave its peers spinning at the next exchange until the fabric timeout. validate_params has
+    // bounded the smoothing tile; the buffers the phases may want are allocated here.
+    if (p->write_debug) TRY(ensure_debug(h));
+    if (p->fhat_windows) TRY(ensure_stage(h, sizeof(double) * 2 * h->n_windows_total));
+    TRY(ensure_scratch(h, 256));
     h->fabric_epoch++;
     const FabricArgs fa = fabric_args(h);
     EV_BEGIN(7);

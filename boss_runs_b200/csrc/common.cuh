@@ -115,7 +115,8 @@ struct bossgpu_handle {
     int64_t Tf_rows = 0;       // sum(L) // 100                    (readstartdist.py:29)
     int64_t R0 = 0;            // first merged row of this shard
     int64_t D0 = 0;            // first strategy row (distribution axis) of this shard
-    int fhat_shift = 55;
+    int fhat_shift = 50;       // exact F-hat sums: terms are fhat * 2^fhat_shift (strategy.cuh)
+    int ubar_shift = 61;       // exact ubar0 sum: terms are fhat * benefit * 2^(ubar_shift - exponent of the normaliser)
     // shard totals
     int64_t P = 0;             // padded sites
     int64_t n_tiles = 0;
@@ -214,6 +215,7 @@ struct bossgpu_handle {
     int32_t*  d_drop_thr_spec = nullptr;     // [n_contigs_total] thresholds the early pass used
     uint32_t* d_tile_cov = nullptr;          // [n_tiles][nb] per-tile depth totals (score_pass.cuh)
     uint32_t* d_tile_drop = nullptr;         // [n_tiles]
+    bool multi_fused = false;                // barcodes: k_score_bin_multi takes a tile through every barcode (no row-summary pass)
     bool prescore_ok = false;                // geometry allows it (one segment per contig, no barcodes, staged kernel)
     int64_t pre_n_reads = 0;
     uint64_t pre_hash = 0;

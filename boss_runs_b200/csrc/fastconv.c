@@ -27,20 +27,35 @@ static int attr_i64(PyObject* o, PyObject* name, long long* out) {
 
 static long long clampll(long long x, long long lo, long long hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-/* convert(paf_dict, seqs, contig_index, best_record, bufs, keep) -> (n_used, n_skipped)
+/* convert(paf_dict, seqs, contig_index, best_record, bufs, keep[, route]) -> (n_used, n_skipped[, n_tracked])
  * bufs: tuple of 10 writable buffers sized for len(paf_dict) entries:
  *   contig i32, tstart i64, tend i64, barcode i32, rev u8, cigar_ptr u64, cigar_len i64, seq_ptr u64, seq_from i64, seq_to i64
- * keep: list that receives the str objects the pointers refer to */
+ * keep: list that receives the str objects the pointers refer to
+ * route (one process per GPU, each holding a range of the genome): tuple (ranges i64[n_contigs][2], contig_all i32, tstart_all i64,
+ *   tend_all i64, rev_all u8). Every read on a tracked contig is listed in the *_all buffers (depth totals and read starts need
+ *   the whole batch); only reads whose interval overlaps [ranges[k][0], ranges[k][1]) of their contig k are converted. */
 static PyObject* convert(PyObject* self, PyObject* args) {
-    PyObject *paf_dict, *seqs, *contig_index, *best_record, *bufs, *keep;
-    if (!PyArg_ParseTuple(args, "O!O!O!OO!O!", &PyDict_Type, &paf_dict, &PyDict_Type, &seqs, &PyDict_Type, &contig_index,
-                          &best_record, &PyTuple_Type, &bufs, &PyList_Type, &keep))
+    PyObject *paf_dict, *seqs, *contig_index, *best_record, *bufs, *keep, *route = NULL;
+    if (!PyArg_ParseTuple(args, "O!O!O!OO!O!|O!", &PyDict_Type, &paf_dict, &PyDict_Type, &seqs, &PyDict_Type, &contig_index,
+                          &best_record, &PyTuple_Type, &bufs, &PyList_Type, &keep, &PyTuple_Type, &route))
         return NULL;
     if (PyTuple_GET_SIZE(bufs) != 10) { PyErr_SetString(PyExc_ValueError, "expected 10 output buffers"); return NULL; }
-    Py_buffer vb[10];
+    if (route && PyTuple_GET_SIZE(route) != 5) { PyErr_SetString(PyExc_ValueError, "route: expected 5 buffers"); return NULL; }
+    Py_buffer vb[10], rb[5];
     static const Py_ssize_t item[10] = {4, 8, 8, 4, 1, 8, 8, 8, 8, 8};
+    static const Py_ssize_t ritem[5] = {0, 4, 8, 8, 1};
     const Py_ssize_t n_max = PyDict_Size(paf_dict);
-    int got = 0;
+    int got = 0, rgot = 0;
+    if (route) {
+        for (; rgot < 5; ++rgot) {
+            if (PyObject_GetBuffer(PyTuple_GET_ITEM(route, rgot), &rb[rgot], (rgot ? PyBUF_WRITABLE : 0) | PyBUF_C_CONTIGUOUS) < 0) goto fail;
+            if (rb[rgot].len < n_max * ritem[rgot]) {
+                ++rgot;
+                PyErr_SetString(PyExc_ValueError, "route buffer too small");
+                goto fail;
+            }
+        }
+    }
     for (; got < 10; ++got) {
         if (PyObject_GetBuffer(PyTuple_GET_ITEM(bufs, got), &vb[got], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) goto fail;
         if (vb[got].len < n_max * item[got]) {
@@ -54,7 +69,11 @@ static PyObject* convert(PyObject* self, PyObject* args) {
         int32_t* o_bc = (int32_t*)vb[3].buf;       uint8_t* o_rev = (uint8_t*)vb[4].buf;     uint64_t* o_cp = (uint64_t*)vb[5].buf;
         int64_t* o_cl = (int64_t*)vb[6].buf;       uint64_t* o_sp = (uint64_t*)vb[7].buf;    int64_t* o_sf = (int64_t*)vb[8].buf;
         int64_t* o_st = (int64_t*)vb[9].buf;
-        Py_ssize_t pos = 0, n = 0, skipped = 0;
+        Py_ssize_t pos = 0, n = 0, skipped = 0, m = 0;
+        const int64_t* ranges = route ? (const int64_t*)rb[0].buf : NULL;
+        const Py_ssize_t n_ranges = route ? rb[0].len / 16 : 0;
+        int32_t* a_contig = route ? (int32_t*)rb[1].buf : NULL;  int64_t* a_tstart = route ? (int64_t*)rb[2].buf : NULL;
+        int64_t* a_tend = route ? (int64_t*)rb[3].buf : NULL;    uint8_t* a_rev = route ? (uint8_t*)rb[4].buf : NULL;
         PyObject *key, *recs;
         while (PyDict_Next(paf_dict, &pos, &key, &recs)) {
             PyObject* rec;
@@ -77,6 +96,23 @@ static PyObject* convert(PyObject* self, PyObject* args) {
                 continue;
             }
             long long ki = PyLong_AsLongLong(k), tstart, tend, qlen, qstart, qend;
+            if (route) {
+                /* routed batch: list the read, convert it only if this process' range of its contig sees it */
+                PyObject* rv = PyObject_GetAttr(rec, s_rev);
+                int r01 = rv ? PyObject_IsTrue(rv) : -1;
+                Py_XDECREF(rv);
+                if (r01 < 0 || attr_i64(rec, s_tstart, &tstart) < 0 || attr_i64(rec, s_tend, &tend) < 0 || ki < 0 || ki >= n_ranges) {
+                    if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "contig index outside the routing table");
+                    if (owned) Py_DECREF(rec);
+                    goto fail;
+                }
+                a_contig[m] = (int32_t)ki; a_tstart[m] = tstart; a_tend[m] = tend; a_rev[m] = (uint8_t)r01; ++m;
+                const long long t0 = tstart < tend ? tstart : tend, t1 = tstart < tend ? tend : tstart;
+                if (t1 <= ranges[2 * ki] || t0 >= ranges[2 * ki + 1]) {
+                    if (owned) Py_DECREF(rec);
+                    continue;
+                }
+            }
             PyObject* qname = PyObject_GetAttr(rec, s_qname);
             PyObject* revo = qname ? PyObject_GetAttr(rec, s_rev) : NULL;
             PyObject* cig = revo ? PyObject_GetAttr(rec, s_cigar) : NULL;
@@ -136,10 +172,12 @@ static PyObject* convert(PyObject* self, PyObject* args) {
             if (!ok) goto fail;
         }
         for (int i = 0; i < 10; ++i) PyBuffer_Release(&vb[i]);
-        return Py_BuildValue("nn", n, skipped);
+        for (int i = 0; i < rgot; ++i) PyBuffer_Release(&rb[i]);
+        return route ? Py_BuildValue("nnn", n, skipped, m) : Py_BuildValue("nn", n, skipped);
     }
 fail:
     for (int i = 0; i < got; ++i) PyBuffer_Release(&vb[i]);
+    for (int i = 0; i < rgot; ++i) PyBuffer_Release(&rb[i]);
     return NULL;
 }
 

@@ -276,6 +276,8 @@ struct ScatterArgs {
     int32_t* err;
 };
 
+// MODE 0: bases packed 2 bits each (text ingest), 1: ASCII bytes, 2: code bytes 0..4
+template <int MODE>
 __global__ void __launch_bounds__(SC_THREADS)
 k_scatter_ops(ScatterArgs a) {
     using Scan = cub::BlockScan<int, SC_THREADS>;
@@ -326,6 +328,8 @@ k_scatter_ops(ScatterArgs a) {
             }
             int before;
             Scan(scan_tmp).ExclusiveScan(run, before, -1, cub::Max());
+            // a warp whose eight-position strips all lie behind the block's last position has nothing to expand
+            if (win0 + (t & ~31) * SC_PER >= total) continue;
             // all of the thread's positions first (registers only, no data-dependent indexing), then its atomics
             unsigned long long widx[SC_PER];
             unsigned add[SC_PER];
@@ -340,7 +344,7 @@ k_scatter_ops(ScatterArgs a) {
                 unsigned code = 4;                            // deletion column (sequences.py:792-793)
                 if (live && (qi.y & 3) != 2) {
                     const int64_t o = rev ? (int64_t)qi.x - p : (int64_t)qi.x + p;    // slice index, sequencing orientation
-                    if (a.pk.data) {
+                    if (MODE == 0) {
                         // 2 bits per base, 4 per byte, every read's slice starting on its own byte
                         unsigned ch = (a.pk.data[s_boff[i] + (o >> 2)] >> (2 * (o & 3))) & 3u;       // raw: A C T G = 0 1 2 3
                         ch ^= ch >> 1;                                                                // A C G T = 0 1 2 3
@@ -352,10 +356,15 @@ k_scatter_ops(ScatterArgs a) {
                         }
                         code = ch;
                     } else {
-                        unsigned ch = a.bases[s_boff[i] + o];
-                        if (a.base_is_ascii) {
-                            if (rev) ch = ch == 'A' ? 'T' : ch == 'T' ? 'A' : ch == 'G' ? 'C' : ch == 'C' ? 'G' : ch;
-                            code = base_code_ascii(ch);
+                        const unsigned ch = a.bases[s_boff[i] + o];
+                        if (MODE == 1) {
+                            // branch-free: (ch >> 1) & 3 sends A C T G to 0 1 2 3, ^= >> 1 makes that A C G T; the reverse
+                            // complement of a base is 3 - code; any other character is ord - 48, never complemented
+                            const bool acgt = ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
+                            unsigned c = (ch >> 1) & 3u;
+                            c ^= c >> 1;
+                            if (rev) c = 3u - c;
+                            code = acgt ? c : ((ch - 48u) & 0xFFu);
                         } else {
                             code = (rev && ch < 4u) ? 3u - ch : ch;
                         }

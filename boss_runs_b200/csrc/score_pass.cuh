@@ -446,6 +446,199 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Barcoded runs (nb > 1): the whole-row rules couple the barcodes of a site — a row observed in ANY barcode is scored
+// from the table in all of them (Q6), a row whose depth is at or below the dropout threshold in SOME barcode is zeroed in
+// all of them (Q8) — so a site's scores need its counters in every barcode. One CTA takes a tile through ALL barcodes,
+// half a tile (1000 sites, 4 per thread) at a time, in two sweeps:
+//   sweep 1  every barcode's five counter planes come through the TMA ring once; each thread turns its sites' counters into
+//            table rows (19 bits, parked in shared memory: 3 bytes per site and barcode) and keeps the row-wide minimum
+//            depth and "ever observed" flag in registers;
+//   sweep 2  per barcode: rows back from shared memory (the thread's own), row rules applied, one table gather per site,
+//            100-site bin sums in position order.
+// Every counter is read from HBM exactly once (10 B per site and barcode + 1 B reference base per site); the separate
+// row-summary pass (k_rowflags: all counters a second time) is only kept for more barcodes than fit in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int SBM_CONSUMERS = 256;                 // 250 active: 4 sites each = 1000 sites
+constexpr int SBM_THREADS = SBM_CONSUMERS + 32;
+constexpr int SBM_HALF = TILE / 2;
+constexpr int SBM_SITES = 4;
+constexpr int SBM_PLANE_BYTES = SBM_HALF * 2;      // 2000
+constexpr int SBM_REF_OFF = 5 * SBM_PLANE_BYTES;   // 10000
+constexpr int SBM_STAGE_BYTES = 11136;             // 5 planes + 1000 reference bases, padded to a multiple of 128
+constexpr int SBM_STAGES = 3;
+constexpr int SBM_MAX_NB = 24;
+
+constexpr size_t sbm_smem_bytes(int nb) {
+    return (size_t)SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 2 * (SBM_HALF / SBM_SITES) * sizeof(double) +
+           4 * FREEZE * sizeof(uint32_t) + 2 * SBM_STAGES * sizeof(unsigned long long) + (size_t)nb * sizeof(unsigned) + 64 + 128;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SBM_THREADS, 2)
+k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int nb = a.nb;
+    unsigned char* s_stage = s_raw;
+    uint16_t* s_rlo = reinterpret_cast<uint16_t*>(s_raw + SBM_STAGES * SBM_STAGE_BYTES);             // [nb][SBM_HALF]
+    uint8_t* s_rhi = reinterpret_cast<uint8_t*>(s_rlo + (size_t)nb * SBM_HALF);                       // [nb][SBM_HALF]
+    double* s_part = reinterpret_cast<double*>(s_raw + ((SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 15) & ~(size_t)15));
+    uint32_t (*s_T)[FREEZE] = reinterpret_cast<uint32_t (*)[FREEZE]>(s_part + 2 * (SBM_HALF / SBM_SITES));
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_T + 4);                        // full[], empty[]
+    unsigned* s_cov = reinterpret_cast<unsigned*>(s_bar + 2 * SBM_STAGES);                             // [nb]
+    unsigned* s_drop = s_cov + nb;
+
+    const int t = threadIdx.x;
+    if (t < 4 * FREEZE) {
+        const int k = t / FREEZE, p = t - k * FREEZE;
+        const int64_t q = p + k + 1;
+        s_T[k][p] = (uint32_t)(k == 0 ? binom2(q) : k == 1 ? binom3(q) : k == 2 ? binom4(q) : binom5(q));
+    }
+    if (t == 0) {
+        for (int s = 0; s < SBM_STAGES; ++s) {
+            mbar_init(smem_u32(&s_bar[s]), 1);
+            mbar_init(smem_u32(&s_bar[SBM_STAGES + s]), SBM_CONSUMERS / 32);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n_iter = MODE == 2 ? (int64_t)*a.list_n : n_tiles;
+
+    if (t >= SBM_CONSUMERS) {
+        // ------------------------------- producer warp -------------------------------
+        if (t == SBM_CONSUMERS) {
+            int it = 0;
+            for (int64_t idx = blockIdx.x; idx < n_iter; idx += gridDim.x) {
+                const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
+                const int64_t site_off = a.tiles[tile].site_off;
+                for (int half = 0; half < 2; ++half) {
+                    for (int b = 0; b < nb; ++b, ++it) {
+                        const int stage = it % SBM_STAGES;
+                        const uint32_t full = smem_u32(&s_bar[stage]), empty = smem_u32(&s_bar[SBM_STAGES + stage]);
+                        if (it >= SBM_STAGES) mbar_wait(empty, ((it / SBM_STAGES) - 1) & 1);
+                        const uint32_t dst = smem_u32(s_stage + (size_t)stage * SBM_STAGE_BYTES);
+                        mbar_expect_tx(full, 5 * SBM_PLANE_BYTES + (b == 0 ? SBM_HALF : 0));
+                        const uint16_t* plane0 = a.cov + (size_t)b * 5 * a.P + site_off + half * SBM_HALF;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) bulk_g2s(dst + k * SBM_PLANE_BYTES, plane0 + (size_t)k * a.P, SBM_PLANE_BYTES, full);
+                        if (b == 0) bulk_g2s(dst + SBM_REF_OFF, a.ref + site_off + half * SBM_HALF, SBM_HALF, full);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ----------------------------------- consumers -----------------------------------
+    int it = 0, buf = 0;
+    const bool active = t < SBM_HALF / SBM_SITES;                      // 250 of the 256 consumer threads hold sites
+    if (t < nb) s_cov[t] = 0u;
+    if (t == 0) *s_drop = 0u;
+    consumer_bar();
+    for (int64_t idx = blockIdx.x; idx < n_iter; idx += gridDim.x) {
+        const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
+        const TileDesc td = a.tiles[tile];
+        const int32_t thr_i = a.drop_thr[td.contig];                   // -1 while the depth rule is inactive
+        for (int half = 0; half < 2; ++half) {
+            const int l0 = half * SBM_HALF + SBM_SITES * t;            // first site of this thread within the tile
+            uint32_t refw = 0, mn[SBM_SITES], any = 0;
+#pragma unroll
+            for (int i = 0; i < SBM_SITES; ++i) mn[i] = 0xFFFFFFFFu;
+            // ---- sweep 1: counters -> table rows, row-wide minimum depth / observed flag ----
+            for (int b = 0; b < nb; ++b, ++it) {
+                const int stage = it % SBM_STAGES;
+                mbar_wait(smem_u32(&s_bar[stage]), (it / SBM_STAGES) & 1);
+                const unsigned char* sb = s_stage + (size_t)stage * SBM_STAGE_BYTES;
+                uint2 v[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) v[k] = make_uint2(0, 0);
+                if (active) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) v[k] = reinterpret_cast<const uint2*>(sb + k * SBM_PLANE_BYTES)[t];
+                    if (b == 0) refw = reinterpret_cast<const uint32_t*>(sb + SBM_REF_OFF)[t];
+                }
+                {
+                    // the arrival must not overtake the loads: fold every loaded word into a value the arriving lane needs
+                    const unsigned seen = v[0].x ^ v[0].y ^ v[1].x ^ v[1].y ^ v[2].x ^ v[2].y ^ v[3].x ^ v[3].y ^ v[4].x ^ v[4].y ^ refw;
+                    const unsigned all_seen = __reduce_or_sync(0xFFFFFFFFu, seen);
+                    if ((t & 31) == 0) {
+                        asm volatile("" ::"r"(all_seen) : "memory");
+                        mbar_arrive(smem_u32(&s_bar[SBM_STAGES + stage]));
+                    }
+                }
+                unsigned covsum = 0;
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < SBM_SITES; ++i) {
+                        uint32_t c[5];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const uint32_t w = (i < 2) ? v[k].x : v[k].y;
+                            c[k] = (i & 1) ? (w >> 16) : (w & 0xFFFFu);
+                        }
+                        const uint32_t p2 = c[0] + c[1], p3 = p2 + c[2], p4 = p3 + c[3], cs = p4 + c[4];
+                        const uint32_t rank = min(c[0], 29u) + s_T[0][min(p2, 29u)] + s_T[1][min(p3, 29u)] + s_T[2][min(p4, 29u)] +
+                                              s_T[3][min(cs, 29u)];
+                        const uint32_t row = cs < (uint32_t)FREEZE ? rank : (uint32_t)ROW_TINY;
+                        const int site = SBM_SITES * t + i;
+                        s_rlo[(size_t)b * SBM_HALF + site] = (uint16_t)(row & 0xFFFFu);
+                        s_rhi[(size_t)b * SBM_HALF + site] = (uint8_t)(row >> 16);
+                        const bool valid = l0 + i < td.n_sites;
+                        mn[i] = min(mn[i], cs);
+                        any |= (cs != 0u ? 1u : 0u) << i;
+                        covsum += valid ? cs : 0u;
+                    }
+                }
+                covsum = __reduce_add_sync(0xFFFFFFFFu, covsum);
+                if ((t & 31) == 0 && covsum) atomicAdd(&s_cov[b], covsum);
+            }
+            // ---- sweep 2: row rules, table gather, 100-site bins, barcode by barcode ----
+            bool drop[SBM_SITES];
+            unsigned ndrop = 0;
+#pragma unroll
+            for (int i = 0; i < SBM_SITES; ++i) {
+                const bool valid = active && l0 + i < td.n_sites;
+                drop[i] = valid && (int32_t)mn[i] <= thr_i;
+                ndrop += drop[i] ? 1u : 0u;
+            }
+            ndrop = __reduce_add_sync(0xFFFFFFFFu, ndrop);
+            if ((t & 31) == 0 && ndrop) atomicAdd(s_drop, ndrop);
+            for (int b = 0; b < nb; ++b) {
+                double* part = s_part + buf * (SBM_HALF / SBM_SITES);
+                if (active) {
+                    double sv[SBM_SITES];
+#pragma unroll
+                    for (int i = 0; i < SBM_SITES; ++i) {
+                        const int site = SBM_SITES * t + i;
+                        uint32_t row = (uint32_t)s_rlo[(size_t)b * SBM_HALF + site] | ((uint32_t)s_rhi[(size_t)b * SBM_HALF + site] << 16);
+                        row = ((any >> i) & 1u) ? row : (uint32_t)ROW_SCORE0;      // Q5/Q6: row never observed in any barcode
+                        if (drop[i] || l0 + i >= td.n_sites) row = ROW_ZERO;        // Q8 / whatever follows the contig end
+                        const uint32_t refb = (refw >> (8 * i)) & 3u;
+                        sv[i] = __ldg(a.table + (size_t)(row * 4 + refb));
+                    }
+                    part[t] = ((sv[0] + sv[1]) + sv[2]) + sv[3];                    // position order within a thread
+                }
+                consumer_bar();
+                if (t < SBM_HALF / BIN) {
+                    // bin j of the half = 25 consecutive 4-site partials, added in position order
+                    const int bin = half * (SBM_HALF / BIN) + t;
+                    if (bin < td.n_bins) {
+                        double acc = 0.0;
+#pragma unroll 5
+                        for (int k = 0; k < 25; ++k) acc += part[25 * t + k];
+                        a.ds[(size_t)b * a.ds_len + td.ds_index + bin] = acc;
+                    }
+                }
+                buf ^= 1;
+            }
+        }
+        consumer_bar();                                              // every warp's depth sums and drop counts are in
+        if (t < nb) { a.tile_cov[(size_t)tile * nb + t] = s_cov[t]; s_cov[t] = 0u; }
+        if (t == 32) { a.tile_drop[tile] = *s_drop; *s_drop = 0u; }
+        consumer_bar();                                              // ... and reset, before the next tile adds to them
+    }
+}
+
 // per-tile depth totals -> bucket sums (reference.py:196-198 sums whole 20 kb buckets; a tile is a tenth of one), and
 // the number of dropped rows for the log line. Integer sums: order-free.
 __global__ void k_tile_reduce(int64_t n_tiles, int nb, const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ tile_cov,

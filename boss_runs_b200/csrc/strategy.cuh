@@ -326,6 +326,7 @@ struct HistArgs {
     FhatGeom fg;
     const double* fw;             // [W][2]
     int shift;                    // limbs hold fhat * 2^shift
+    int ushift;                   // ubar0 is summed as integers of fhat * benefit * 2^(ushift - exponent of the normaliser)
     unsigned long long* hist;     // [3*HBINS + 4]: counts | hi | lo | ubar_hi, ubar_lo, n_nonzero, -
     uint8_t* codes;               // [nb][n_rows][2] exponent-bin code of every entry (see k_hist), or NULL
     UpdateDev* upd;
@@ -389,7 +390,7 @@ __device__ __forceinline__ void warp_hist_add(int e, unsigned cnt, unsigned long
 // four register slots, and groups that straddle a window edge (only in the tail-fixed part of F-hat), take the direct
 // path. Also leaves the bin of every entry behind as a one-byte code (hist.codes) for the distribution kernel:
 // 0 = the maximum itself, c = entry in [norm 2^-c, norm 2^-(c-1)), 254 = anything smaller, 255 = zero / cut row.
-__global__ void __launch_bounds__(HIST_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS, 6)
 k_hist(HistArgs a) {
     __shared__ unsigned s_cnt[HBINS];
     __shared__ unsigned long long s_hi[HBINS];
@@ -406,12 +407,12 @@ k_hist(HistArgs a) {
     int norm_e;
     frexp(norm, &norm_e);                       // norm < 2^norm_e  =>  fhat*b*2^(shift-norm_e) < fhat*2^shift
     const double two_shift = ldexp(1.0, a.shift);
-    const int ue = a.shift - norm_e;
+    const int ue = a.ushift - norm_e;          // fhat * benefit * 2^(ushift - norm_e) < fhat * 2^ushift <= 2^ushift
     const bool ue_ok = ue > -1000 && ue < 1000;
     const double two_ue = ue_ok ? ldexp(1.0, ue) : 0.0;
     const int b = blockIdx.y;
     const int64_t extra = a.target > a.M ? a.target - a.M : 0;    // rows duplicated at the tail (adjust_length pads)
-    unsigned long long u_hi = 0, u_lo = 0, nnz = 0;
+    unsigned long long u_sum = 0, nnz = 0;
     const double2* ben = a.benefit + (size_t)b * a.n_rows;
     uint16_t* codes = a.codes ? reinterpret_cast<uint16_t*>(a.codes) + (size_t)b * a.n_rows : nullptr;
 
@@ -424,24 +425,32 @@ k_hist(HistArgs a) {
     double f[2] = {0.0, 0.0};
     unsigned long long fh[2] = {0, 0}, fl[2] = {0, 0};
     int ebase[2] = {-1, -1};
-    unsigned cnt[2][HIST_SLOTS] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    unsigned cnt[2] = {0u, 0u};                 // HIST_SLOTS counters of 8 bits each (a group holds at most 2 x 20 rows)
     auto direct = [&](int e, unsigned n, unsigned long long h, unsigned long long l) {
         atomicAdd(&s_cnt[e], n);
         atomicAdd(&s_hi[e], h * n);
         atomicAdd(&s_lo[e], l * n);
     };
-    auto spill = [&]() {                        // window changes inside the group: empty the register slots
+    auto enter_window = [&](int64_t win) {      // empties the register slots and loads the window's F-hat
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 2; ++s) {
 #pragma unroll
-            for (int j = 0; j < HIST_SLOTS; ++j)
-                if (cnt[s][j]) { direct(ebase[s] + j, cnt[s][j], fh[s], fl[s]); cnt[s][j] = 0; }
+            for (int j = 0; j < HIST_SLOTS; ++j) {
+                const unsigned n = (cnt[s] >> (8 * j)) & 0xFFu;
+                if (n) direct(ebase[s] + j, n, fh[s], fl[s]);
+            }
+            cnt[s] = 0u;
+            f[s] = a.fw[2 * win + s] * scale;   // np.multiply(fhat_exp, normalizer)
+            to_limbs_small(f[s] * two_shift, fh[s], fl[s]);
+        }
+        cur_win = win;
     };
     // pass 0: every row below `target`; pass 1 (only when adjust_length pads, core.py:179-181 with reject refs):
     // the last `extra` merged rows once more, at their appended positions
     const int n_pass = (extra > 0 && r_hi > a.M - extra) ? 2 : 1;
-    // in the plain part of F-hat (before either tail fix) the whole group lies in window G
-    const bool plain = (G + 1) * HIST_GROUP <= min(min(20 * a.fg.W, a.fg.Tf), a.target);
+    // in the plain part of F-hat (before either tail fix) the whole group lies in window G: nothing to look up per row
+    const bool plain = n_pass == 1 && (G + 1) * HIST_GROUP <= min(min(20 * a.fg.W, a.fg.Tf), a.target);
+    if (plain && r_lo < r_hi) enter_window(G);
     for (int pass = 0; pass < n_pass; ++pass) {
         for (int64_t r4 = r_lo; r4 < r_hi; r4 += 4) {
         double2 v4[4];
@@ -455,39 +464,30 @@ k_hist(HistArgs a) {
         for (int j = 0; j < 4; ++j) {
             const int64_t r = r4 + j;
             const double2 v = v4[j];
-            unsigned code2 = 0xFFFFu;
-            if (!(v.x == 0.0 && v.y == 0.0)) {                // np.nonzero (sequences.py:585); rows that are cut read 0
-                const int64_t win = (plain && pass == 0) ? G : fhat_window_of_row(a.fg, pass == 0 ? r : r + extra);
-                if (win != cur_win) {
-                    spill();
-                    cur_win = win;
+            // np.nonzero (sequences.py:585): zero entries (and rows that are cut, which read 0) count nowhere
+            if (!plain && !(v.x == 0.0 && v.y == 0.0)) {
+                const int64_t win = fhat_window_of_row(a.fg, pass == 0 ? r : r + extra);
+                if (win != cur_win) enter_window(win);
+            }
+            unsigned code2 = 0u;
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        f[s] = a.fw[2 * win + s] * scale;     // np.multiply(fhat_exp, normalizer)
-                        to_limbs_small(f[s] * two_shift, fh[s], fl[s]);
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const double x = s == 0 ? v.x : v.y;
-                    if (x == 0.0) continue;
-                    const int e = abs_exponent_of_ratio(x, norm, nbits);
-                    // one-byte bin code: the maximum (the only entry whose ratio has exponent +1, Q3) gets 0
-                    const unsigned c = (x == norm) ? 0u : (unsigned)min(e + 1, 254);
-                    code2 = s == 0 ? ((code2 & 0xFF00u) | c) : ((code2 & 0x00FFu) | (c << 8));
-                    if (ebase[s] < 0) ebase[s] = max(e - 1, 0);
-                    const int rel = e - ebase[s];
-                    if ((unsigned)rel < (unsigned)HIST_SLOTS) {
-#pragma unroll
-                        for (int j = 0; j < HIST_SLOTS; ++j) cnt[s][j] += (rel == j) ? 1u : 0u;
-                    } else {
-                        direct(e, 1u, fh[s], fl[s]);
-                    }
-                    const double t = f[s] * x;                // term of ubar0 = sum(fhat*smu), smu := benefit (Q1)
-                    unsigned long long uh, ul;
-                    to_limbs_small(ue_ok ? t * two_ue : ldexp(t, ue), uh, ul);
-                    u_hi += uh; u_lo += ul; nnz++;
-                }
+            for (int s = 0; s < 2; ++s) {
+                const double x = s == 0 ? v.x : v.y;
+                const bool nz = x != 0.0;
+                const int e = abs_exponent_of_ratio(nz ? x : norm, norm, nbits);
+                // one-byte bin code: the maximum (the only entry whose ratio has exponent +1, Q3) gets 0
+                const unsigned c = !nz ? 255u : (x == norm ? 0u : (unsigned)min(e + 1, 254));
+                code2 |= c << (8 * s);
+                ebase[s] = (ebase[s] < 0 && nz) ? max(e - 1, 0) : ebase[s];
+                const int rel = e - ebase[s];
+                const bool slot = nz && (unsigned)rel < (unsigned)HIST_SLOTS;
+                cnt[s] += slot ? (1u << (8 * (rel & 3))) : 0u;
+                if (nz && !slot) direct(e, 1u, fh[s], fl[s]);
+                // term of ubar0 = sum(fhat * smu), smu := benefit (Q1): rounded once to 2^-ushift of the normaliser's
+                // binade and summed as an integer (order-free, the same whatever the grid or the number of shards)
+                const double t = f[s] * x;
+                u_sum += (unsigned long long)__double2ll_rn(ue_ok ? t * two_ue : ldexp(t, ue));
+                nnz += nz ? 1ull : 0ull;
             }
             if (pass == 0 && codes && r < r_hi) codes[r - a.R0] = (uint16_t)code2;
         }
@@ -498,16 +498,15 @@ k_hist(HistArgs a) {
     for (int s = 0; s < 2; ++s)
 #pragma unroll
         for (int j = 0; j < HIST_SLOTS; ++j) {
-            const unsigned n = cnt[s][j];
+            const unsigned n = (cnt[s] >> (8 * j)) & 0xFFu;
             warp_hist_add(n ? ebase[s] + j : -1, n, fh[s] * n, fl[s] * n, s_cnt, s_hi, s_lo);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
-        u_hi += __shfl_down_sync(0xFFFFFFFFu, u_hi, o);
-        u_lo += __shfl_down_sync(0xFFFFFFFFu, u_lo, o);
+        u_sum += __shfl_down_sync(0xFFFFFFFFu, u_sum, o);
         nnz += __shfl_down_sync(0xFFFFFFFFu, nnz, o);
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_u[0], u_hi); atomicAdd(&s_u[1], u_lo); atomicAdd(&s_u[2], nnz); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_u[0], u_sum); atomicAdd(&s_u[2], nnz); }
     __syncthreads();
     for (int i = threadIdx.x; i < HBINS; i += blockDim.x) {
         if (s_cnt[i]) {
@@ -525,7 +524,7 @@ k_hist(HistArgs a) {
 // the ratios are again formed by all threads and the first maximum is picked like np.argmax does.
 constexpr int THR_THREADS = 256;
 __global__ void __launch_bounds__(THR_THREADS)
-k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, UpdateDev* upd) {
+k_threshold(const unsigned long long* __restrict__ hist, int shift, int ushift, double tc, UpdateDev* upd) {
     __shared__ double s_u[HBINS], s_t[HBINS];        // per-bin terms, then (compacted) cumulative sums, then s_u = ratio
     __shared__ int s_exp[HBINS];
     __shared__ int s_nocc;
@@ -548,7 +547,7 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, double tc, U
     }
     int norm_e;
     frexp(norm, &norm_e);
-    const double ubar0 = from_limbs(hist[3 * HBINS], hist[3 * HBINS + 1], shift - norm_e);
+    const double ubar0 = ldexp((double)(long long)hist[3 * HBINS], norm_e - ushift);
     const double tbar0 = 3.0 + 3.0 + 4.0;                               // alpha + rho + mu in bins (sequences.py:578-580,630)
     for (int e = threadIdx.x; e < HBINS; e += THR_THREADS) {
         const unsigned long long cnt = hist[e];

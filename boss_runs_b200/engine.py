@@ -173,6 +173,19 @@ class Engine:
                                                   ptr(rev), ptr(cigar_ptr), ptr(cigar_len), ptr(seq_ptr), ptr(seq_from),
                                                   ptr(seq_to), int(n_threads)))
 
+    def ingest_records_routed(self, contig, tstart, tend, barcode, rev, cigar_ptr, cigar_len, seq_ptr, seq_from, seq_to,
+                              batch_cov_add, n_threads: int = 0) -> None:
+        """Text ingest of the reads this shard sees; `batch_cov_add` = reference span of the whole batch per global contig."""
+        contig = as_c(contig, np.int32); tstart = as_c(tstart, np.int64); tend = as_c(tend, np.int64)
+        barcode = as_c(barcode, np.int32); rev = as_c(rev, np.uint8)
+        cigar_ptr = as_c(cigar_ptr, np.uint64); cigar_len = as_c(cigar_len, np.int64)
+        seq_ptr = as_c(seq_ptr, np.uint64); seq_from = as_c(seq_from, np.int64); seq_to = as_c(seq_to, np.int64)
+        add = as_c(batch_cov_add, np.int64)
+        assert add.shape == (len(self.contig_lengths),)
+        check(self.lib.bossgpu_ingest_records_routed(self.h, len(contig), ptr(contig), ptr(tstart), ptr(tend), ptr(barcode),
+                                                     ptr(rev), ptr(cigar_ptr), ptr(cigar_len), ptr(seq_ptr), ptr(seq_from),
+                                                     ptr(seq_to), ptr(add), int(n_threads)))
+
     def prescore_begin(self) -> None:
         """A batch has arrived: score every tile now, on a second stream, while the host prepares the batch
         (`bossgpu_prescore_begin`); results do not depend on it."""

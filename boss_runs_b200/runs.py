@@ -13,7 +13,8 @@ Standalone use (no upstream checkout needed)::
     run.process_batch_runs(paf_dict, seqs)                # convert -> scatter -> read starts -> update
     run.contigs["chr1"].strat                             # bool (L//100, 2, nb), refreshed by the update
 
-`boss_runs_b200.dropin` wires the same engine underneath the upstream `BossRuns` / `BossRunsSim` classes.
+`boss_runs_b200.dropin` puts the same engine underneath upstream's own `BossRuns` / `BossRunsSim` classes (a mixin that
+overrides `init`, `_effect_increments` and `update_wrapper`; unchanged TOML plus an optional `[gpu]` table).
 """
 from __future__ import annotations
 
@@ -55,6 +56,18 @@ class PackedBatch:
     seq_to: np.ndarray
     keep: list              # the str objects the pointers refer to
     n_skipped: int = 0      # reads whose target is not a tracked contig
+    # routed batches (one process per GPU): the arrays above hold only the reads this process' range of the genome sees;
+    # these list EVERY read of the batch on a tracked contig (depth totals and read starts need the whole batch)
+    all_contig: np.ndarray | None = None
+    all_tstart: np.ndarray | None = None
+    all_tend: np.ndarray | None = None
+    all_rev: np.ndarray | None = None
+
+    def whole_batch(self):
+        """(contig, tstart, tend, rev) of every tracked read of the batch, routed or not."""
+        if self.all_contig is None:
+            return self.contig, self.tstart, self.tend, self.rev
+        return self.all_contig, self.all_tstart, self.all_tend, self.all_rev
 
     def __len__(self) -> int:
         return int(self.contig.shape[0])
@@ -92,22 +105,33 @@ class CoverageConverter:
         self.qt = qt
 
     def convert_records(self, paf_dict, seqs: dict[str, str], quals: dict[str, str] | None = None,
-                        barcodes: dict[str, int] | None = None) -> PackedBatch:
+                        barcodes: dict[str, int] | None = None, ranges: np.ndarray | None = None) -> PackedBatch:
         """Same walk as upstream's loop (sequences.py:694-738). Runs in the `_fastconv` C helper when it has been
         built (`__graft_entry__.build()` / `python -m boss_runs_b200.build`), else in `_convert_records_py`; both
-        produce identical batches (tests/test_hostmodel.py)."""
+        produce identical batches (tests/test_hostmodel.py).
+
+        `ranges` (int64 [n tracked contigs][2], one process per GPU): only reads overlapping [ranges[k][0], ranges[k][1]) of
+        their contig k are converted — the others are merely listed in the batch's `all_*` arrays."""
         fc = _fastconv()
         if fc is None:
-            return self._convert_records_py(paf_dict, seqs)
+            return self._convert_records_py(paf_dict, seqs, ranges)
         n = len(paf_dict)
         contig, bc = np.empty(n, np.int32), np.empty(n, np.int32)
         tstart, tend, cl, sf, st = (np.empty(n, np.int64) for _ in range(5))
         rev = np.empty(n, np.uint8)
         cp, sp = np.empty(n, np.uint64), np.empty(n, np.uint64)
         keep: list = []
-        used, skipped = fc.convert(paf_dict, seqs, self.contig_index, best_record, (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st), keep)
+        bufs = (contig, tstart, tend, bc, rev, cp, cl, sp, sf, st)
+        if ranges is None:
+            used, skipped = fc.convert(paf_dict, seqs, self.contig_index, best_record, bufs, keep)
+            return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
+                               sf[:used], st[:used], keep, skipped)
+        ranges = np.ascontiguousarray(ranges, dtype=np.int64)
+        assert ranges.shape == (len(self.contig_index), 2)
+        ac, ats, ate, arv = np.empty(n, np.int32), np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.uint8)
+        used, skipped, m = fc.convert(paf_dict, seqs, self.contig_index, best_record, bufs, keep, (ranges, ac, ats, ate, arv))
         return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
-                           sf[:used], st[:used], keep, skipped)
+                           sf[:used], st[:used], keep, skipped, ac[:m], ats[:m], ate[:m], arv[:m])
 
     def convert_text(self, paf_raw: str, seqs: dict[str, str], min_len: int = 200,
                      barcodes: dict[str, int] | None = None) -> PackedBatch:
@@ -135,8 +159,9 @@ class CoverageConverter:
         return PackedBatch(contig[:used], tstart[:used], tend[:used], bc[:used], rev[:used], cp[:used], cl[:used], sp[:used],
                            sf[:used], st[:used], keep, skipped)
 
-    def _convert_records_py(self, paf_dict, seqs: dict[str, str]) -> PackedBatch:
+    def _convert_records_py(self, paf_dict, seqs: dict[str, str], ranges=None) -> PackedBatch:
         contig, tstart, tend, bc, rev, cp, cl, sp, sf, st, keep = [], [], [], [], [], [], [], [], [], [], []
+        everyone = [] if ranges is not None else None
         skipped = 0
         index = self.contig_index
         for recs in paf_dict.values():
@@ -145,6 +170,11 @@ class CoverageConverter:
             if k is None:
                 skipped += 1          # upstream collects these under a key nobody reads (core.py:83-86)
                 continue
+            if ranges is not None:
+                everyone.append((k, rec.tstart, rec.tend, 1 if rec.rev else 0))
+                t0, t1 = min(rec.tstart, rec.tend), max(rec.tstart, rec.tend)
+                if t1 <= ranges[k][0] or t0 >= ranges[k][1]:
+                    continue
             s = seqs[rec.qname]
             if rec.rev:
                 # upstream slices the reverse complement of the WHOLE string with qlen-based coordinates
@@ -173,11 +203,16 @@ class CoverageConverter:
             st.append(max(hi, lo))
             keep.append(cig)
             keep.append(s)
-        return PackedBatch(np.asarray(contig, dtype=np.int32), np.asarray(tstart, dtype=np.int64),
-                           np.asarray(tend, dtype=np.int64), np.asarray(bc, dtype=np.int32),
-                           np.asarray(rev, dtype=np.uint8), np.asarray(cp, dtype=np.uint64), np.asarray(cl, dtype=np.int64),
-                           np.asarray(sp, dtype=np.uint64), np.asarray(sf, dtype=np.int64), np.asarray(st, dtype=np.int64),
-                           keep, skipped)
+        b = PackedBatch(np.asarray(contig, dtype=np.int32), np.asarray(tstart, dtype=np.int64),
+                        np.asarray(tend, dtype=np.int64), np.asarray(bc, dtype=np.int32),
+                        np.asarray(rev, dtype=np.uint8), np.asarray(cp, dtype=np.uint64), np.asarray(cl, dtype=np.int64),
+                        np.asarray(sp, dtype=np.uint64), np.asarray(sf, dtype=np.int64), np.asarray(st, dtype=np.int64),
+                        keep, skipped)
+        if everyone is not None:
+            cols = list(zip(*everyone)) if everyone else [[], [], [], []]
+            b.all_contig, b.all_tstart = np.asarray(cols[0], dtype=np.int32), np.asarray(cols[1], dtype=np.int64)
+            b.all_tend, b.all_rev = np.asarray(cols[2], dtype=np.int64), np.asarray(cols[3], dtype=np.uint8)
+        return b
 
 
 def _best_index(keys: list) -> int:
@@ -479,13 +514,32 @@ class BossRuns:
         """`paf_dict` = mappings of the batch ({read id: [PafLine]}); `paf_dict_starts` (default: the same)
         is the subset that feeds the read-start distribution — the simulator passes accepted reads only
         (simulation.py:171)."""
+        import time as _t
+        t0 = _t.perf_counter()
         self._prescore_begin()
-        increments = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
+        increments = self._convert(paf_dict, seqs, quals, barcodes)
+        t1 = _t.perf_counter()
         self._prescore(increments)
+        t2 = _t.perf_counter()
         self._effect_increments(increments=increments)
-        self.count_read_starts(paf_dict if paf_dict_starts is None else paf_dict_starts)
+        t3 = _t.perf_counter()
+        if paf_dict_starts is None:
+            # the winning record of every read is already in the batch arrays: same windows, same drops as
+            # ReadStartDist.count_read_starts(paf_dict) without walking the PafLine objects a second time
+            wins, strands = self.read_starts.count_read_starts_arrays(*increments.whole_batch())
+            self._read_starts_to_device(wins, strands)
+        else:
+            self.count_read_starts(paf_dict_starts)
+        t4 = _t.perf_counter()
         self.update_wrapper()
+        t5 = _t.perf_counter()
+        self.last_batch_ms = {"convert_records": (t1 - t0) * 1e3, "announce": (t2 - t1) * 1e3, "ingest": (t3 - t2) * 1e3,
+                              "count_read_starts": (t4 - t3) * 1e3, "update_wrapper": (t5 - t4) * 1e3}
         self.batch += 1
+
+    def _convert(self, paf_dict, seqs, quals=None, barcodes=None) -> PackedBatch:
+        """`self.cc.convert_records`; `sharding.ShardedRun` routes the batch here (each process converts only its reads)."""
+        return self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes)
 
     def process_batch_text(self, paf_raw: str, seqs: dict[str, str], quals: dict[str, str] | None = None,
                            barcodes: dict[str, int] | None = None, min_len: int = 200) -> None:

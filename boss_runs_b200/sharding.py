@@ -469,6 +469,12 @@ class ShardedRun(BossRuns):
             if self._exchange == "fabric" and not self._fabric:
                 raise RuntimeError("exchange='fabric' was asked for but the shards cannot map each other's memory")
         logging.info("sharded update over %d shard(s): %s", n, "peer-memory fabric" if self._fabric else "phase protocol")
+        # one process per GPU: this process' range of every contig; convert_records skips the reads outside it
+        self._ranges = None
+        if self._n_virtual is None and n > 1 and self.route_batches:
+            self._ranges = np.zeros((len(lens), 2), dtype=np.int64)
+            for s in self.plan[mine[0]]:
+                self._ranges[s.contig] = (s.start, s.start + s.length)
 
     @property
     def exchange_mode(self) -> str:
@@ -488,13 +494,35 @@ class ShardedRun(BossRuns):
         self.sync_depth_totals()
 
     # -- coverage ---------------------------------------------------------------------------------------
+    route_batches = True        # one process per GPU: convert only the reads this process' range of the genome sees
+
+    def _convert(self, paf_dict, seqs, quals=None, barcodes=None) -> PackedBatch:
+        if self._ranges is None:
+            return super()._convert(paf_dict, seqs, quals, barcodes)
+        err, b = None, None
+        try:
+            b = self.cc.convert_records(paf_dict=paf_dict, seqs=seqs, quals=quals, barcodes=barcodes, ranges=self._ranges)
+        except Exception as ex:             # noqa: BLE001 - a bad record is seen by the rank that owns it only: agree before raising
+            err = ex
+        if not self.group.agree(err is None):
+            raise err if err is not None else RuntimeError("another shard found a bad record while converting the batch")
+        return b
+
     def _effect_increments(self, increments: PackedBatch) -> None:
         b = increments
         err = None
         try:
-            for e in self.engines:
-                e.ingest_records_ptr(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
-                                     b.seq_ptr, b.seq_from, b.seq_to)
+            if b.all_contig is not None:
+                # routed batch: own reads + the whole batch's reference span per contig (dropout rule, reference.py:157-158)
+                cov_add = np.zeros(len(self.contigs_filt), dtype=np.int64)
+                np.add.at(cov_add, b.all_contig, np.abs(b.all_tend - b.all_tstart))
+                for e in self.engines:
+                    e.ingest_records_routed(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
+                                            b.seq_ptr, b.seq_from, b.seq_to, cov_add)
+            else:
+                for e in self.engines:
+                    e.ingest_records_ptr(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
+                                         b.seq_ptr, b.seq_from, b.seq_to)
         except (IndexError, AssertionError, ValueError) as ex:        # what upstream raises for a bad record
             err = ex
         if not self.group.agree(err is None):

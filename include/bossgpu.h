@@ -156,6 +156,17 @@ int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads,
                                const uint64_t* seq_ptr, const int64_t* seq_from, const int64_t* seq_to,
                                int n_threads);
 
+/* ingest_records_routed: one process per GPU, each holding a range of the genome. The caller has already routed the batch:
+ * it hands over only the reads whose interval overlaps this shard's range of their contig (converting the others would be
+ * wasted host work, N times over), plus batch_cov_add[k] = reference span of the WHOLE batch on global contig k — the
+ * dropout rule (reference.py:157-158,175-177) needs contig-wide depth on every shard. An empty read list is fine. */
+int bossgpu_ingest_records_routed(bossgpu_handle* h, int64_t n_reads,
+                                  const int32_t* contig, const int64_t* tstart, const int64_t* tend,
+                                  const int32_t* barcode, const uint8_t* rev,
+                                  const uint64_t* cigar_ptr, const int64_t* cigar_len,
+                                  const uint64_t* seq_ptr, const int64_t* seq_from, const int64_t* seq_to,
+                                  const int64_t* batch_cov_add, int n_threads);
+
 /* Multi-shard geometry and halo staging (see bossgpu_update_phase) */
 /* Split score/bin pass (optional; results are identical with and without it).
  *   bossgpu_prescore_begin  when a batch arrives, before anything is known about it: every 2000-site tile is scored at
@@ -170,7 +181,7 @@ int bossgpu_ingest_records_ptr(bossgpu_handle* h, int64_t n_reads,
  * would compute (same counters, same threshold). Every tile is scored from its counters in every update — nothing is
  * carried over from one update to the next. If the batch that is ingested differs from the announced one (or is
  * rejected, or arrives by another ingest route, or was never announced) the update scores every tile again.
- * No-op with barcodes (the row rules Q6/Q8 need the pre-pass over all planes). */
+ * Works with up to 24 barcodes (one CTA takes a tile through every barcode: the row rules Q6/Q8 couple them); a no-op beyond. */
 int bossgpu_prescore_begin(bossgpu_handle* h);
 int bossgpu_prescore(bossgpu_handle* h, int64_t n_reads, const int32_t* contig, const int64_t* tstart, const int64_t* tend);
 

@@ -156,6 +156,12 @@ class NumpyShardEngine:
             b = int(barcode[r]) if 0 <= int(barcode[r]) < self.nb else 0
             np.add.at(self.cov[i], (pos[ok], q[ok], b), 1)
 
+    def ingest_records_routed(self, contig, tstart, tend, barcode, rev, cigar_ptr, cigar_len, seq_ptr, seq_from, seq_to, batch_cov_add,
+                              n_threads=0):
+        before = self.cov_total.copy()
+        self.ingest_records_ptr(contig, tstart, tend, barcode, rev, cigar_ptr, cigar_len, seq_ptr, seq_from, seq_to)
+        self.cov_total[:] = before + np.asarray(batch_cov_add, dtype=self.cov_total.dtype)
+
     def read_starts_add(self, wins, strands):
         np.add.at(self.rs_counts, (np.asarray(wins), np.asarray(strands)), 1)
 

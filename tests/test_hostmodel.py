@@ -63,6 +63,36 @@ def test_fastconv_equals_python_loop(fc):
         k += 1
 
 
+def test_routed_conversion_is_the_filtered_conversion(fc):
+    """One process per GPU: `convert_records(..., ranges=...)` converts the reads overlapping this process' range of their
+    contig — exactly the sub-batch the library would have selected from the whole batch — and lists every tracked read in
+    the `all_*` arrays (depth totals, read starts). C helper and Python loop agree."""
+    contigs = synth.random_contigs({"a": 300_000, "b": 200_000, "c": 120_000}, seed=2)
+    rb = synth.read_batch(contigs, n_reads=500, seed=19, mean_len=3000.0, n_barcodes=2)
+    pd = parse_PAF(io.StringIO(rb.paf_text))
+    for rid, recs in pd.items():
+        for r in recs:
+            r.barcode = rb.barcodes[rid]
+    cc = CoverageConverter({"a": 0, "b": 1})                 # "c" is unknown to the converter
+    whole = cc.convert_records(pd, rb.seqs)
+    for ranges in ([[0, 140_000], [0, 0]], [[140_000, 300_000], [0, 60_000]], [[0, 0], [60_000, 200_000]], [[0, 0], [0, 0]]):
+        ranges = np.array(ranges, dtype=np.int64)
+        a = cc.convert_records(pd, rb.seqs, ranges=ranges)
+        b = cc._convert_records_py(pd, rb.seqs, ranges)
+        same(a, b)
+        t0, t1 = np.minimum(whole.tstart, whole.tend), np.maximum(whole.tstart, whole.tend)
+        lo, hi = ranges[whole.contig, 0], ranges[whole.contig, 1]
+        mine = (t1 > lo) & (t0 < hi)
+        for f in FIELDS:
+            assert np.array_equal(getattr(a, f), getattr(whole, f)[mine]), f
+        for got, got_py, want in ((a.all_contig, b.all_contig, whole.contig), (a.all_tstart, b.all_tstart, whole.tstart),
+                                  (a.all_tend, b.all_tend, whole.tend), (a.all_rev, b.all_rev, whole.rev)):
+            assert np.array_equal(got, want) and np.array_equal(got_py, want)
+        assert all(np.array_equal(x, y) for x, y in zip(a.whole_batch(), whole.whole_batch()))
+    # the three ranges above partition the genome: every read is converted by at least one process, spanning reads by two
+    assert whole.all_contig is None
+
+
 def test_fastconv_errors(fc):
     contigs = synth.random_contigs({"a": 150_000}, seed=3)
     rb = synth.read_batch(contigs, n_reads=5, seed=1, mean_len=2000.0)

@@ -58,7 +58,7 @@ def test_accepted_read_without_full_mapping_raises_like_upstream():
 import hashlib  # noqa: E402
 
 import helpers as H  # noqa: E402
-from golden_io import load_case  # noqa: E402
+from golden_io import GOLDEN, load_case, unpack2bit  # noqa: E402
 
 FLOW = dict(np.load(Path(__file__).resolve().parent / "golden" / "sim_flow_zymo.npz", allow_pickle=False))
 
@@ -175,3 +175,70 @@ def test_text_decisions_errors_like_object_path():
         pd, *_rest, a, r = make_decisions(cont, {"r1": "A" * 900}, full900, wrap, {"r1": 0})
         got = decide_text(cc.contig_index, cont, {"r1": "A" * 900}, full900, wrap, {"r1": 0})
         assert (a, got[6]) == (want_acc, want_acc)
+
+
+# ---- BASELINE config 1 at its stated size: upstream's own simulator run recorded by oracle/make_golden_c1.py ---------------
+def _c1_full():
+    path = GOLDEN / "c1_full.npz"
+    if not path.exists():
+        pytest.skip("tests/golden/c1_full.npz not generated (python -m oracle.make_golden_c1)")
+    z = np.load(path, allow_pickle=False)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    records = []
+    for name, L in zip(z["ref_names"], z["ref_lengths"]):
+        records.append((str(name), acgt[unpack2bit(z[f"ref_{name}"], int(L))].tobytes().decode()))
+    lens = z["pool_len"]
+    allb = acgt[unpack2bit(z["pool_2bit"], int(lens.sum()))].tobytes().decode()
+    off = np.concatenate(([0], np.cumsum(lens)))
+    pool = {str(r): allb[off[i]: off[i + 1]] for i, r in enumerate(z["pool_rids"])}
+    return z, records, pool
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_c1_full_size_against_upstream_simulator(tag, lib):
+    """The whole of data/BOSS_test_data (zymo.fa: 9 tracked contigs, 31 012 581 sites; ERR3152366 reads with their full-length
+    and mu-truncated minimap2 records) through `BossRunsSim.process_batch_runs_sim`, batch for batch what upstream's sampler
+    handed out, against what upstream's `BossRunsSim` computed: run A = batchsize 4000, maxb 1 (BASELINE.json configs[0]),
+    run B = 1000 x 8. Decision counts, read-length staircase, counters (digest), dropout zeros, score sums, threshold and
+    every mask bit; run A additionally state by state against the oracle."""
+    from boss_runs_b200.simulation import BossRunsSim
+    z, records, pool = _c1_full()
+    assert int(z[f"{tag}_n_sites"]) == 31_012_581 and len([1 for _, s in records if len(s) >= 100_000]) == 9   # test_reference.py:51-67
+    sim = BossRunsSim(contigs=records, ploidy=1, bucket_threshold=0, write_debug=(tag == "A"))
+    assert int(sim.ref.n_sites) == int(z[f"{tag}_n_sites"]) and list(sim.contigs) == [str(x) for x in z[f"{tag}_contigs"]]
+    orc = H.oracle_run(records, 1, [], None, 0) if tag == "A" else None
+    for bi in range(int(z[f"{tag}_maxb"])):
+        p = f"{tag}{bi}_"
+        seqs = {str(r): pool[str(r)] for r in z[p + "rids"]}
+        assert len(seqs) == int(z[f"{tag}_batchsize"])
+        paf_f, paf_t = z[p + "paf_full"].tobytes().decode(), z[p + "paf_trunc"].tobytes().decode()
+        if orc is not None:
+            updated, counts, acc, dec_o = H.oracle_sim_step(orc, seqs, paf_f, paf_t, {r: 0 for r in seqs}, set(seqs))
+        dec_p = sim.process_batch_runs_sim(seqs, None, {r: "" for r in seqs}, paf_f, paf_t)
+        n_mapped, n_unmapped, n_acc, n_rej = (int(x) for x in z[p + "counts"])
+        assert (sim.n_accepted, sim.n_rejected) == (n_acc, n_rej), f"{p}: decisions differ from upstream's"
+        assert sum(len(s) for s in dec_p.values()) > 0
+        assert np.array_equal(sim.rl_dist.approx_ccl, z[p + "approx_ccl"]) and sim.rl_dist.time_cost == float(z[p + "time_cost"])
+        assert bool(sim.last.switched_on) == bool(z[p + "updated"])
+        if sim.last.switched_on:
+            thr = float(z[p + "threshold"])
+            assert abs(sim.threshold - thr) <= H.tol.THRESHOLD_RTOL * thr, f"{p}: threshold {sim.threshold!r} vs upstream {thr!r}"
+            assert abs(sim.last.normaliser - float(z[p + "normaliser"])) <= H.tol.NORM_RTOL * float(z[p + "normaliser"])
+        n_drop = 0
+        for name, c in sim.contigs_filt.items():
+            q = f"{p}{name}_"
+            cov = c.coverage
+            assert hashlib.sha256(np.ascontiguousarray(cov).tobytes()).hexdigest() == str(z[q + "coverage_sha"]), f"{q}: counters"
+            assert int(cov.sum(dtype=np.int64)) == int(z[q + "depth_total"])
+            s = c.scores
+            assert int(np.count_nonzero(s == 0.0)) == int(z[q + "n_dropout"]), f"{q}: dropout zeros"
+            n_drop += int(z[q + "n_dropout"])
+            assert abs(float(s.sum()) - float(z[q + "scores_sum"])) <= 1e-9 * abs(float(z[q + "scores_sum"])), f"{q}: scores"
+            assert np.array_equal(np.packbits(np.asarray(c.bucket_switches).ravel()), z[q + "switches"]), f"{q}: bucket switches"
+            got, want = np.packbits(np.asarray(c.strat).ravel()), z[q + "strat"]
+            assert np.array_equal(got, want), f"{q}: {int(np.unpackbits(got ^ want).sum())} mask bits differ from upstream's"
+        assert sim.last.n_dropout == n_drop
+        if orc is not None:
+            assert counts == (n_mapped, n_unmapped, n_acc, n_rej) and dec_p == dec_o and updated
+            H.compare_state(sim, orc, updated, f"c1/{p}")
