@@ -8,8 +8,11 @@ Layout:
   priors.py        host constants of the scoring model (mirror of upstream `Priors`)
   hostmodel.py     host mirrors: PafLine/parse_PAF, ReadlengthDist, ReadStartDist
   runs.py          reference-facing API: Contig, Reference, CoverageConverter, BossRuns
-  dropin.py        the same engine underneath the upstream `BossRuns` / `BossRunsSim` classes
-  sharding.py      multi-GPU: genome-axis partition + NCCL exchange steps
+  dropin.py        upstream's own `BossRuns` / `BossRunsSim` with the array half replaced (mixin; `[gpu]` TOML table; main())
+  simulation.py    the simulator's decision step on the GPU-backed update
+  sharding.py      multi-GPU: genome-axis partition, peer-memory fabric / NCCL exchange steps, routed batches
+  aeons.py         BOSS-AEONS' Benefit / pool threshold / masks (stateless C-ABI call)
+  stratfile.py     optional packed strategy file boss.bits + consumer lookup
   synth.py         synthetic references / read batches of BASELINE.json's shapes (tests, bench)
 
 Importing the package never touches CUDA; the first `Engine` loads libbossgpu.so and fails loudly if it

@@ -60,6 +60,16 @@ class UpdateResult(C.Structure):
                 ("n_nonzero", C.c_int64), ("n_dropout", C.c_int64), ("n_accept", C.c_int64 * 2), ("mirror_bytes", C.c_int64)]
 
 
+class AeonsParams(C.Structure):
+    _fields_ = [("mu_ds", C.c_int32), ("ccl_ds", C.c_int32 * 10), ("perc", C.c_double * 10), ("tc", C.c_double),
+                ("tbar0", C.c_double), ("want_strategy", C.c_int32), ("reserved", C.c_int32)]
+
+
+class AeonsResult(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("normaliser", C.c_double), ("ubar0", C.c_double), ("n_nonzero", C.c_int64),
+                ("strat_size", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/bossgpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -114,6 +124,7 @@ SYMBOLS = {
     "bossgpu_timing": (C.c_int, [_P, _P]),
     "bossgpu_launch_count": (C.c_int64, [_P]),
     "bossgpu_ingest_bytes": (C.c_int64, [_P]),
+    "bossgpu_aeons_update": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, _P, C.POINTER(AeonsParams), _P, _P, _P, _P, C.POINTER(AeonsResult)]),
     "bossgpu_synth_coverage": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
 }
 

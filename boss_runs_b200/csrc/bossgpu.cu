@@ -14,6 +14,7 @@
 #include "strategy.cuh"
 #include "fabric.cuh"
 #include "synth.cuh"
+#include "aeons.cuh"
 #include "tokenizer.h"
 
 namespace boss {
@@ -1946,4 +1947,97 @@ extern "C" int bossgpu_get_read_starts(bossgpu_handle* h, int64_t* out, int64_t 
     BOSS_CUDA(cudaMemcpyAsync(out, h->d_rs_counts, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// BOSS-AEONS benefit / threshold step (aeons.cuh); stateless
+// ------------------------------------------------------------------------------------------------
+extern "C" int bossgpu_aeons_update(int device, int64_t n_seq, const int64_t* node_off, const double* scores, const uint8_t* e1,
+                                    const uint8_t* e2, const bossgpu_aeons_params* p, double* benefit, double* smu_sum,
+                                    uint8_t* strat, int64_t* counts, bossgpu_aeons_result* r) {
+    if (!p || !node_off || n_seq <= 0 || !scores || !e1 || !e2 || !benefit || !smu_sum)
+        return fail(BOSSGPU_EINVAL, "null argument");
+    if (p->want_strategy && (!strat || !r)) return fail(BOSSGPU_EINVAL, "strategy outputs missing");
+    if (p->mu_ds < 1) return fail(BOSSGPU_EINVAL, "anchor window of %d nodes; Bottleneck's move_sum rejects windows < 1", p->mu_ds);
+    for (int i = 0; i < NSTEPS; ++i) {
+        if (p->ccl_ds[i] < 1) return fail(BOSSGPU_EINVAL, "staircase window %d is %d nodes; Bottleneck's move_sum rejects windows < 1", i, p->ccl_ds[i]);
+        if (i > 0 && p->ccl_ds[i] < p->ccl_ds[i - 1]) return fail(BOSSGPU_EINVAL, "staircase windows must be non-decreasing");
+        if (p->ccl_ds[i] > 12000) return fail(BOSSGPU_EINVAL, "staircase window %d exceeds the supported 12000 nodes", i);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(BOSSGPU_ECUDA, "no usable CUDA device; libbossgpu has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BOSSGPU_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    BOSS_CUDA(cudaSetDevice(device));
+    const int64_t total = node_off[n_seq];
+    if (node_off[0] != 0 || total <= 0) return fail(BOSSGPU_EINVAL, "node offsets must start at 0 and hold at least one node");
+    std::vector<int32_t> tseq, tj0;
+    for (int64_t i = 0; i < n_seq; ++i) {
+        const int64_t n = node_off[i + 1] - node_off[i];
+        if (n <= 0) return fail(BOSSGPU_EINVAL, "contig %lld has no nodes", (long long)i);
+        for (int64_t j = 0; j < n; j += AE_TILE) { tseq.push_back((int32_t)i); tj0.push_back((int32_t)j); }
+    }
+    const size_t n_tiles = tseq.size();
+    // one device blob: [off | scores | e1 | e2 | tile_seq | tile_j0 | benefit | smu_sum | strat | counts | norm, nnz | out]
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (size_t)round_up((int64_t)bytes, 256); return at; };
+    const size_t o_off = take(sizeof(int64_t) * (n_seq + 1)), o_sc = take(sizeof(double) * total), o_e1 = take((size_t)n_seq),
+                 o_e2 = take((size_t)n_seq), o_ts = take(sizeof(int32_t) * n_tiles), o_tj = take(sizeof(int32_t) * n_tiles);
+    const size_t in_bytes = o;
+    const size_t o_ben = take(sizeof(double) * 2 * total), o_ss = take(sizeof(double) * n_seq), o_st = take((size_t)2 * total),
+                 o_cnt = take(sizeof(unsigned long long) * HBINS), o_misc = take(sizeof(unsigned long long) * 2), o_out = take(sizeof(AeonsOut));
+    char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, o);
+    if (e != cudaSuccess) return fail(BOSSGPU_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", o, cudaGetErrorString(e));
+    std::vector<char> hs(in_bytes, 0);
+    memcpy(hs.data() + o_off, node_off, sizeof(int64_t) * (n_seq + 1));
+    memcpy(hs.data() + o_sc, scores, sizeof(double) * total);
+    memcpy(hs.data() + o_e1, e1, (size_t)n_seq);
+    memcpy(hs.data() + o_e2, e2, (size_t)n_seq);
+    memcpy(hs.data() + o_ts, tseq.data(), sizeof(int32_t) * n_tiles);
+    memcpy(hs.data() + o_tj, tj0.data(), sizeof(int32_t) * n_tiles);
+    int rc = 0;
+    auto finish = [&](int code) { cudaFree(d); return code; };
+#define AE_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = fail(BOSSGPU_ECUDA, "%s failed: %s", #x, cudaGetErrorString(_e)); return finish(rc); } } while (0)
+    AE_CUDA(cudaMemcpy(d, hs.data(), in_bytes, cudaMemcpyHostToDevice));
+    AE_CUDA(cudaMemset(d + o_cnt, 0, o - o_cnt));
+    AeonsArgs a;
+    a.n_seq = n_seq; a.off = (const int64_t*)(d + o_off); a.scores = (const double*)(d + o_sc); a.e1 = (const uint8_t*)(d + o_e1);
+    a.e2 = (const uint8_t*)(d + o_e2); a.tile_seq = (const int32_t*)(d + o_ts); a.tile_j0 = (const int32_t*)(d + o_tj);
+    a.mu = p->mu_ds;
+    for (int i = 0; i < NSTEPS; ++i) { a.w[i] = p->ccl_ds[i]; a.perc[i] = p->perc[i]; }
+    a.benefit = (double*)(d + o_ben); a.norm_bits = (unsigned long long*)(d + o_misc);
+    const int wmax = std::max(p->ccl_ds[NSTEPS - 1], p->mu_ds);
+    const size_t smem = sizeof(double) * (AE_TILE + 2 * (size_t)wmax);
+    if (smem > 200 * 1024) return finish(fail(BOSSGPU_EINVAL, "window of %d nodes needs %zu B of shared memory", wmax, smem));
+    AE_CUDA(cudaFuncSetAttribute(k_aeons_benefit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_aeons_benefit<<<(unsigned)n_tiles, AE_TILE, smem>>>(a);
+    AE_CUDA(cudaGetLastError());
+    k_aeons_smu_sum<<<(unsigned)n_seq, 256>>>(n_seq, a.off, a.scores, a.e1, a.e2, p->mu_ds, (int64_t)p->ccl_ds[NSTEPS - 1], (double*)(d + o_ss));
+    AE_CUDA(cudaGetLastError());
+    if (p->want_strategy) {
+        k_aeons_hist<<<(unsigned)std::min<int64_t>(ceil_div(2 * total, 256), 148 * 8), 256>>>(
+            2 * total, a.benefit, a.norm_bits, (unsigned long long*)(d + o_cnt), (unsigned long long*)(d + o_misc) + 1);
+        AE_CUDA(cudaGetLastError());
+        k_aeons_threshold<<<1, 32>>>(n_seq, (const double*)(d + o_ss), (const unsigned long long*)(d + o_cnt), a.norm_bits,
+                                     (const unsigned long long*)(d + o_misc) + 1, p->tc, p->tbar0, (AeonsOut*)(d + o_out));
+        AE_CUDA(cudaGetLastError());
+        k_aeons_mask<<<(unsigned)n_tiles, AE_TILE>>>(n_seq, a.off, a.benefit, (const AeonsOut*)(d + o_out), a.tile_seq, a.tile_j0,
+                                                     (uint8_t*)(d + o_st));
+        AE_CUDA(cudaGetLastError());
+    }
+    AE_CUDA(cudaMemcpy(benefit, d + o_ben, sizeof(double) * 2 * total, cudaMemcpyDeviceToHost));
+    AE_CUDA(cudaMemcpy(smu_sum, d + o_ss, sizeof(double) * n_seq, cudaMemcpyDeviceToHost));
+    if (p->want_strategy) {
+        AeonsOut out;
+        AE_CUDA(cudaMemcpy(&out, d + o_out, sizeof out, cudaMemcpyDeviceToHost));
+        r->threshold = out.threshold; r->normaliser = out.normaliser; r->ubar0 = out.ubar0; r->n_nonzero = (int64_t)out.n_nonzero;
+        r->strat_size = out.strat_size; r->reserved = 0;
+        if (counts) AE_CUDA(cudaMemcpy(counts, d + o_cnt, sizeof(unsigned long long) * HBINS, cudaMemcpyDeviceToHost));
+        if (out.empty) return finish(fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError"));
+        AE_CUDA(cudaMemcpy(strat, d + o_st, (size_t)2 * total, cudaMemcpyDeviceToHost));
+    }
+#undef AE_CUDA
+    return finish(0);
 }

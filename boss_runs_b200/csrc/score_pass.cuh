@@ -465,7 +465,10 @@ constexpr int SBM_HALF = TILE / 2;
 constexpr int SBM_SITES = 4;
 constexpr int SBM_PLANE_BYTES = SBM_HALF * 2;      // 2000
 constexpr int SBM_REF_OFF = 5 * SBM_PLANE_BYTES;   // 10000
-constexpr int SBM_STAGE_BYTES = 11136;             // 5 planes + 1000 reference bases, padded to a multiple of 128
+constexpr int SBM_STAGE_BYTES = 11136;             // 5 planes + a 1024-byte window of reference bases, padded to a multiple of 128
+// bulk copies move multiples of 16 bytes from 16-byte aligned addresses: the first half's 1000 reference bases come as bytes
+// [0, 1024) of the tile, the second half's as bytes [992, 2000) (so they start 8 bytes into the window)
+constexpr int SBM_REF_BYTES_H0 = 1024, SBM_REF_SRC_H1 = 992, SBM_REF_BYTES_H1 = TILE - SBM_REF_SRC_H1, SBM_REF_SKIP_H1 = SBM_HALF - SBM_REF_SRC_H1;
 constexpr int SBM_STAGES = 3;
 constexpr int SBM_MAX_NB = 24;
 
@@ -517,11 +520,12 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
                         const uint32_t full = smem_u32(&s_bar[stage]), empty = smem_u32(&s_bar[SBM_STAGES + stage]);
                         if (it >= SBM_STAGES) mbar_wait(empty, ((it / SBM_STAGES) - 1) & 1);
                         const uint32_t dst = smem_u32(s_stage + (size_t)stage * SBM_STAGE_BYTES);
-                        mbar_expect_tx(full, 5 * SBM_PLANE_BYTES + (b == 0 ? SBM_HALF : 0));
+                        mbar_expect_tx(full, 5 * SBM_PLANE_BYTES + (b == 0 ? (half ? SBM_REF_BYTES_H1 : SBM_REF_BYTES_H0) : 0));
                         const uint16_t* plane0 = a.cov + (size_t)b * 5 * a.P + site_off + half * SBM_HALF;
 #pragma unroll
                         for (int k = 0; k < 5; ++k) bulk_g2s(dst + k * SBM_PLANE_BYTES, plane0 + (size_t)k * a.P, SBM_PLANE_BYTES, full);
-                        if (b == 0) bulk_g2s(dst + SBM_REF_OFF, a.ref + site_off + half * SBM_HALF, SBM_HALF, full);
+                        if (b == 0) bulk_g2s(dst + SBM_REF_OFF, a.ref + site_off + (half ? SBM_REF_SRC_H1 : 0),
+                                             half ? SBM_REF_BYTES_H1 : SBM_REF_BYTES_H0, full);
                     }
                 }
             }
@@ -555,7 +559,7 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
                 if (active) {
 #pragma unroll
                     for (int k = 0; k < 5; ++k) v[k] = reinterpret_cast<const uint2*>(sb + k * SBM_PLANE_BYTES)[t];
-                    if (b == 0) refw = reinterpret_cast<const uint32_t*>(sb + SBM_REF_OFF)[t];
+                    if (b == 0) refw = reinterpret_cast<const uint32_t*>(sb + SBM_REF_OFF + (half ? SBM_REF_SKIP_H1 : 0))[t];
                 }
                 {
                     // the arrival must not overtake the loads: fold every loaded word into a value the arriving lane needs

@@ -368,6 +368,41 @@ int64_t bossgpu_ingest_bytes(bossgpu_handle* h);
 int bossgpu_synth_coverage(bossgpu_handle* h, uint64_t seed, double mean_depth, double p_ref,
                            double p_del, double frac_dropout, double frac_deep);
 
+/* ---------------------------------------------------------------------------------------------
+ * BOSS-AEONS (no reference genome: the "contigs" are the current assembly and change with every batch, so this entry
+ * point is stateless — no handle). Replaces, for a pool of contigs given as per-node scores (one per 100-bp node):
+ *   Benefit.calc_fragment_benefit + helpers (boss/aeons/sequences.py:1555-1641), Benefit.benefit_bins (:1644-1682),
+ *   ContigPool.find_threshold (:1059-1094) and Sequence.find_strat_m0 (:398-406).
+ * node_off[n_seq + 1]: offsets of the contigs in `scores`; e1 / e2: left / right end markers (Sequence.noi[0], noi[-1]).
+ * Outputs (host, caller-owned): benefit — contig i's forward row at 2 * node_off[i], its reverse row right behind it
+ * (upstream's (2, n_i) array, flattened); smu_sum[n_seq]; strat — bool [total nodes][2]; counts[BOSSGPU_HIST_BINS] — the
+ * exponent histogram. With want_strategy == 0 only benefit and smu_sum are produced (calc_fragment_benefit alone).
+ * Errors: BOSSGPU_EEMPTY when every benefit is zero (np.max of an empty array upstream), BOSSGPU_EINVAL for windows < 1
+ * (bn.move_sum) or decreasing windows.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bossgpu_aeons_params {
+    int32_t mu_ds;                    /* mu // node_size */
+    int32_t ccl_ds[BOSSGPU_N_STEPS];  /* approx_ccl // node_size */
+    double  perc[BOSSGPU_N_STEPS];    /* np.arange(0.1, 1.1, 0.1)[::-1] (sequences.py:1634) */
+    double  tc;                       /* (lam - mu - 300) // node_size (sequences.py:1074) */
+    double  tbar0;                    /* alpha + rho + mu // node_size = 2 + 3 + 4 (sequences.py:1072-1073,1079) */
+    int32_t want_strategy;
+    int32_t reserved;
+} bossgpu_aeons_params;
+
+typedef struct bossgpu_aeons_result {
+    double  threshold;
+    double  normaliser;
+    double  ubar0;                    /* sum of the contigs' smu_sum */
+    int64_t n_nonzero;
+    int32_t strat_size;
+    int32_t reserved;
+} bossgpu_aeons_result;
+
+int bossgpu_aeons_update(int device, int64_t n_seq, const int64_t* node_off, const double* scores, const uint8_t* e1,
+                         const uint8_t* e2, const bossgpu_aeons_params* p, double* benefit, double* smu_sum, uint8_t* strat,
+                         int64_t* counts, bossgpu_aeons_result* r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,7 @@ def test_header_constants_match_binding():
     assert (const("BOSSGPU_N_PATTERNS"), const("BOSSGPU_N_STEPS"), const("BOSSGPU_HIST_BINS"), const("BOSSGPU_N_TIMERS")) == \
         (_lib.N_PATTERNS, _lib.N_STEPS, _lib.HIST_BINS, _lib.N_TIMERS)
     for name, val in (("OK", 0), ("EINVAL", -1), ("ECUDA", -2), ("ENOMEM", -3), ("EBASE", -4), ("ESHAPE", -5), ("ESTATE", -6),
-                      ("EEMPTY", -7)):
+                      ("EEMPTY", -7), ("EPEER", -8), ("ENOTC", -9)):
         assert const(f"BOSSGPU_{name}") == getattr(_lib, name) == val
 
 
@@ -53,6 +53,8 @@ def test_struct_layouts(tmp_path):
                                   "rs_alpha", "rs_denom", "rs_zero_value"],
         "bossgpu_update_result": ["switched_on", "strat_size", "threshold", "normaliser", "ubar0", "fhat_sum", "n_nonzero",
                                   "n_dropout", "n_accept", "mirror_bytes"],
+        "bossgpu_aeons_params": ["mu_ds", "ccl_ds", "perc", "tc", "tbar0", "want_strategy"],
+        "bossgpu_aeons_result": ["threshold", "normaliser", "ubar0", "n_nonzero", "strat_size"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{REPO}/include/bossgpu.h"', "int main(void){"]
     for st, fs in fields.items():
@@ -65,7 +67,8 @@ def test_struct_layouts(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)     # also: the header is plain C
     got = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
     mirror = {"bossgpu_segment": _lib.Segment, "bossgpu_config": _lib.Config, "bossgpu_update_params": _lib.UpdateParams,
-              "bossgpu_update_result": _lib.UpdateResult}
+              "bossgpu_update_result": _lib.UpdateResult, "bossgpu_aeons_params": _lib.AeonsParams,
+              "bossgpu_aeons_result": _lib.AeonsResult}
     for st, fs in fields.items():
         assert int(got[st]) == C.sizeof(mirror[st]), st
         for f in fs:
