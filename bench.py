@@ -409,6 +409,10 @@ def run_b200(args, spec):
     barrier()
     launches = eng.launch_count() - l0
     ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    # the state after every leg: the same sequence of batches on every N -> the same strategies (taken before the untimed
+    # updates below, whose number depends on the measured time)
+    run._pull_strategies()
+    check = checksum_of(run)
     # A timed region of a few milliseconds is shorter than nvidia-smi's 100 ms sampling period: keep the same workload
     # running (untimed; the same number of extra updates on every rank, derived from the agreed ms) until the sampler has
     # seen ~0.5 s of it, so that the clocks line always describes the GPU under this load.
@@ -420,9 +424,6 @@ def run_b200(args, spec):
         barrier()
     clocks = sampler.stop()
     clocks["sampled_over"] = f"warm-up + timed updates + {n_extra} untimed updates of the same workload"
-    # the state after every leg: the same sequence of batches on every N -> the same strategies
-    run._pull_strategies()
-    check = checksum_of(run)
 
     if rank != 0:
         return

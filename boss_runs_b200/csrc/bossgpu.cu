@@ -1218,6 +1218,7 @@ static int fetch_result(bossgpu_handle* h, bossgpu_update_result* r) {
     BOSS_CUDA(cudaMemcpyAsync(h->h_bucket_sw, h->d_bucket_sw, (size_t)h->n_sw * h->nb, cudaMemcpyDeviceToHost, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     h->last = *h->h_upd;
+    if (h->last.switched_on) h->sticky_on = true;
     for (int i = 0; i < BOSSGPU_N_TIMERS; ++i)
         if (h->ev_valid[i]) cudaEventElapsedTime(&h->ms[i], h->ev[2 * i], h->ev[2 * i + 1]);
     if (r) {
@@ -1247,6 +1248,23 @@ extern "C" int bossgpu_update(bossgpu_handle* h, const bossgpu_update_params* p,
         if (S.start != 0 || !S.is_tail) return fail(BOSSGPU_ESTATE, "bossgpu_update needs whole-contig segments; use the phase API");
     EV_BEGIN(7);
     TRY(phase0_scores(h, p));
+    if (h->sticky_on) {
+        // Bucket switches are sticky (reference.py:199-211): once an update has seen one on, every later update does. The
+        // whole update is enqueued without a host round trip; the kernels of the strategy half look at the device-side flags
+        // themselves (all-zero benefit, missing time_cost: the masks stay as they are) and the host checks them at the end.
+        TRY(upload_fhat(h, p));
+        TRY(phase1_smooth(h, p));
+        TRY(phase2_hist(h, p));
+        TRY(phase3_threshold(h, p));
+        TRY(phase4_distribute(h, nullptr));
+        EV_END(7);
+        TRY(fetch_result(h, r));
+        if (h->last.switched_on && h->last.empty == 2)
+            return fail(BOSSGPU_ENOTC, "a bucket is on but there is no time_cost yet (no read length has been observed)");
+        if (h->last.switched_on && h->last.empty)
+            return fail(BOSSGPU_EEMPTY, "all benefits are zero: upstream np.max of an empty array raises ValueError");
+        return 0;
+    }
     // The strategy half only runs once some bucket is on (core.py:172). The switch lives on the device;
     // reading it costs one small sync, which also bounds how much work is queued behind an idle update.
     BOSS_CUDA(cudaMemcpyAsync(&h->h_upd->switched_on, &h->d_upd->switched_on, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1759,6 +1777,7 @@ extern "C" int bossgpu_set_buckets(bossgpu_handle* h, int32_t seg, const uint8_t
     BOSS_CUDA(cudaMemcpyAsync(h->d_bucket_sw + (size_t)S.sw_off * h->nb, switches, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     BOSS_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(h->h_bucket_sw + (size_t)S.sw_off * h->nb, switches, (size_t)n);
+    h->sticky_on = false;                 // the caller may have switched buckets off: look at the device flag again
     return 0;
 }
 

@@ -205,6 +205,7 @@ struct bossgpu_handle {
     int64_t* d_shard_row_start = nullptr;    // [n_shards+1]
     double*  d_halo = nullptr;               // [send L | send R | recv L | recv R] x halo_bins x nb
     bool have_fhat = false;
+    bool sticky_on = false;                  // an earlier update saw a bucket on (switches never go off again)
     bool debug_bufs = false;
     // split score/bin pass (bossgpu_prescore): tiles the coming batch does not touch are scored on `stream2` while the
     // host is still packing the batch; the update then only scores the touched tiles

@@ -226,12 +226,16 @@ class ReadStartDist:
         w = np.minimum(pos // self.window_size, nw - 1)
         return (self._win_base[contig] + w)[ok].astype(np.int64), rev[ok].astype(np.uint8)
 
-    def count_read_starts_arrays(self, contig, tstart, tend, rev) -> tuple[np.ndarray, np.ndarray]:
-        """`count_read_starts` from arrays (the text path never builds PafLine objects)."""
-        wins, strands = self.window_events_arrays(contig, tstart, tend, rev)
+    def add_events(self, wins, strands) -> None:
+        """Add (global window, strand) events to the host mirror of the counts."""
         if len(wins):
             np.add.at(self._merged_rows(), (wins, strands), 1.0)
             self.csum = getattr(self, "csum", 0.0) + float(len(wins))
+
+    def count_read_starts_arrays(self, contig, tstart, tend, rev) -> tuple[np.ndarray, np.ndarray]:
+        """`count_read_starts` from arrays (the text path never builds PafLine objects)."""
+        wins, strands = self.window_events_arrays(contig, tstart, tend, rev)
+        self.add_events(wins, strands)
         return wins, strands
 
     def pointmass_scalars(self, csum: float | None = None) -> tuple[float, float, float]:

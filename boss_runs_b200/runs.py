@@ -520,14 +520,19 @@ class BossRuns:
         increments = self._convert(paf_dict, seqs, quals, barcodes)
         t1 = _t.perf_counter()
         self._prescore(increments)
+        events = None
+        if paf_dict_starts is None:
+            # the winning record of every read is already in the batch arrays: same windows, same drops as
+            # ReadStartDist.count_read_starts(paf_dict) without walking the PafLine objects a second time. Worked out while
+            # the GPU is still busy with the early pass, applied only once the ingest has accepted the batch (upstream
+            # counts read starts after _effect_increments, core.py:219-222)
+            events = self.read_starts.window_events_arrays(*increments.whole_batch())
         t2 = _t.perf_counter()
         self._effect_increments(increments=increments)
         t3 = _t.perf_counter()
-        if paf_dict_starts is None:
-            # the winning record of every read is already in the batch arrays: same windows, same drops as
-            # ReadStartDist.count_read_starts(paf_dict) without walking the PafLine objects a second time
-            wins, strands = self.read_starts.count_read_starts_arrays(*increments.whole_batch())
-            self._read_starts_to_device(wins, strands)
+        if events is not None:
+            self.read_starts.add_events(*events)
+            self._read_starts_to_device(*events)
         else:
             self.count_read_starts(paf_dict_starts)
         t4 = _t.perf_counter()
