@@ -347,6 +347,7 @@ class Engine:
         raw = (C.c_uint8 * max(n.value, 1)).from_address(p.value)
         raw._owner = self
         flat = np.frombuffer(raw, dtype=np.bool_)[: n.value].reshape(-1, self.nb)
+        self.buckets_flat = flat               # all segments back to back (the views below are slices of it)
         out, row = [], 0
         for i in range(len(self.segments)):
             k = self.seg_switches(i)

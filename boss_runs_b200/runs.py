@@ -476,14 +476,33 @@ class BossRuns:
 
     def _pull_switches(self) -> None:
         """`Contig.bucket_switches` are views of the library's pinned image (refreshed by the update);
-        `switched_on` follows reference.py:203-207: any switch of any barcode flags the whole contig."""
+        `switched_on` follows reference.py:203-207: any switch of any barcode flags the whole contig. With thousands of
+        contigs the per-contig test is one segmented reduction over the flat image, and contigs already flagged are done."""
         if self._switch_views is None:
             self._switch_views = self.engine.buckets_host()
+            starts, row = [], 0
             for c, v in zip(self.contigs_filt.values(), self._switch_views):
                 c.bucket_switches = v
-        for c, v in zip(self.contigs_filt.values(), self._switch_views):
-            if not c.switched_on.all() and v.any():
-                c.switched_on[...] = True
+                starts.append(row)
+                row += v.shape[0]
+            flat = getattr(self.engine, "buckets_flat", None)
+            self._switch_flat = None
+            if flat is not None and flat.shape[0] == row and all(v.shape[0] > 0 for v in self._switch_views):
+                self._switch_flat = flat
+                self._switch_starts = np.asarray(starts, dtype=np.intp)
+            self._flagged = np.zeros(len(self._switch_views), dtype=bool)
+        if self._flagged.all():
+            return
+        if self._switch_flat is not None:
+            on = np.logical_or.reduceat(self._switch_flat.any(axis=1), self._switch_starts)
+            todo = np.flatnonzero(on & ~self._flagged)
+        else:
+            todo = [i for i, v in enumerate(self._switch_views) if not self._flagged[i] and v.any()]
+        if len(todo):
+            contigs = list(self.contigs_filt.values())
+            for i in todo:
+                contigs[i].switched_on[...] = True
+                self._flagged[i] = True
 
     def _pull_strategies(self) -> None:
         """`Contig.strat` of every contig is a view into the library's pinned host mirror, which the update has
@@ -497,11 +516,14 @@ class BossRuns:
                 n = c.length // BIN
                 self._strat_views.append(flat[row: row + n])
                 row += n
-        acc = self.engine.seg_accept()
-        for i, c in enumerate(self.contigs_filt.values()):
-            c.strat = self._strat_views[i]
-            rows = max(c.strat.shape[0], 1)
-            logging.info(f"{c.name}: {acc[i, 0] / rows}, {acc[i, 1] / rows}")
+        for c, v in zip(self.contigs_filt.values(), self._strat_views):
+            if c.strat is not v:
+                c.strat = v
+        if logging.getLogger().isEnabledFor(logging.INFO):
+            acc = self.engine.seg_accept()
+            for i, c in enumerate(self.contigs_filt.values()):
+                rows = max(c.strat.shape[0], 1)
+                logging.info(f"{c.name}: {acc[i, 0] / rows}, {acc[i, 1] / rows}")
 
     def count_read_starts(self, paf_dict) -> None:
         """`ReadStartDist.count_read_starts` on the host mirror AND on the GPU-side counter."""
