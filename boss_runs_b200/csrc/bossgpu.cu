@@ -334,6 +334,7 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         h->multi_fused = h->nb > 1 && h->nb <= SBM_MAX_NB && getenv("BOSSGPU_NO_FUSED_BARCODES") == nullptr;
         h->prescore_ok = one_each && (h->nb == 1 || h->multi_fused) && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
         if (h->multi_fused) {
+            h->multi_ctas = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(227 * 1024) / (sbm_smem_bytes(h->nb) + 1024)));
             BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
             BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
         }
@@ -961,7 +962,7 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
         a.tile_list = h->d_touched_list;
         a.list_n = reinterpret_cast<const unsigned*>(h->d_pre_misc);
         if (h->multi_fused) {
-            dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+            dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->multi_ctas), 1u);
             k_score_bin_multi<2><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), h->stream>>>(a, h->n_tiles);
         } else {
             dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);
@@ -971,7 +972,7 @@ static int phase0_scores(bossgpu_handle* h, const bossgpu_update_params* p) {
         h->launches += 2;
     } else if (h->multi_fused) {
         // barcodes: one CTA takes a tile through every barcode (row rules Q6/Q8), each counter read once
-        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->multi_ctas), 1u);
         k_score_bin_multi<0><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), h->stream>>>(a, h->n_tiles);
         BOSS_KERNEL_CHECK();
         h->launches++;
@@ -1037,7 +1038,7 @@ extern "C" int bossgpu_prescore_begin(bossgpu_handle* h) {
     ScoreArgs a = score_args(h);
     a.drop_thr = h->d_drop_thr_spec;
     if (h->multi_fused) {
-        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * 2), 1u);
+        dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->multi_ctas), 1u);
         k_score_bin_multi<0><<<grid, SBM_THREADS, sbm_smem_bytes(h->nb), st>>>(a, h->n_tiles);
     } else {
         dim3 grid((unsigned)std::min<int64_t>(h->n_tiles, (int64_t)h->n_sm * h->score_ctas_per_sm), 1u);

@@ -217,6 +217,7 @@ struct bossgpu_handle {
     uint32_t* d_tile_cov = nullptr;          // [n_tiles][nb] per-tile depth totals (score_pass.cuh)
     uint32_t* d_tile_drop = nullptr;         // [n_tiles]
     bool multi_fused = false;                // barcodes: k_score_bin_multi takes a tile through every barcode (no row-summary pass)
+    int multi_ctas = 2;                  // resident CTAs per SM of k_score_bin_multi (shared memory per CTA grows with the barcodes)
     bool prescore_ok = false;                // geometry allows it (one segment per contig, no barcodes, staged kernel)
     int64_t pre_n_reads = 0;
     uint64_t pre_hash = 0;

@@ -549,8 +549,13 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, int ushift, 
     frexp(norm, &norm_e);
     const double ubar0 = ldexp((double)(long long)hist[3 * HBINS], norm_e - ushift);
     const double tbar0 = 3.0 + 3.0 + 4.0;                               // alpha + rho + mu in bins (sequences.py:578-580,630)
-    for (int e = threadIdx.x; e < HBINS; e += THR_THREADS) {
-        const unsigned long long cnt = hist[e];
+    // per-bin terms by all threads, compacted to the occupied bins (np.nonzero(bincounts), sequences.py:607) in bin order:
+    // a chunk of THR_THREADS bins at a time, positions from warp ballots
+    __shared__ int s_warp_n[THR_THREADS / 32];
+    int base = 0;
+    for (int e0 = 0; e0 < HBINS; e0 += THR_THREADS) {
+        const int e = e0 + threadIdx.x;
+        const unsigned long long cnt = e < HBINS ? hist[e] : 0ull;
         double tu = 0.0, tt = 0.0;
         if (cnt) {
             const double counts = (double)(long long)cnt;
@@ -560,20 +565,28 @@ k_threshold(const unsigned long long* __restrict__ hist, int shift, int ushift, 
             tu = (bin * f_mean) * counts;                               // benefit_bin * f_grid_mean * counts
             tt = (tc * counts) * f_mean;                                // tc * counts * f_grid_mean
         }
-        s_u[e] = tu; s_t[e] = tt;
+        const unsigned occ = __ballot_sync(0xFFFFFFFFu, cnt != 0ull);
+        if ((threadIdx.x & 31) == 0) s_warp_n[threadIdx.x >> 5] = __popc(occ);
+        __syncthreads();
+        int pos = base;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pos += s_warp_n[w];
+        int total = 0;
+        for (int w = 0; w < THR_THREADS / 32; ++w) total += s_warp_n[w];
+        if (cnt) {
+            pos += __popc(occ & ((1u << (threadIdx.x & 31)) - 1u));
+            s_u[pos] = tu; s_t[pos] = tt; s_exp[pos] = e;
+        }
+        base += total;
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         double cs_u = 0.0, cs_t = 0.0;
-        int n_occ = 0;
-        for (int e = 0; e < HBINS; ++e) {
-            if (!hist[e]) continue;                                     // np.nonzero(bincounts) (sequences.py:607)
-            cs_u += s_u[e];                                             // np.cumsum: sequential, in bin order
-            cs_t += s_t[e];
-            s_u[n_occ] = cs_u; s_t[n_occ] = cs_t; s_exp[n_occ] = e;     // n_occ <= e: never overtakes the reads
-            ++n_occ;
+        for (int i = 0; i < base; ++i) {
+            cs_u += s_u[i];                                             // np.cumsum: sequential, in bin order
+            cs_t += s_t[i];
+            s_u[i] = cs_u; s_t[i] = cs_t;
         }
-        s_nocc = n_occ;
+        s_nocc = base;
     }
     __syncthreads();
     const int n_occ = s_nocc;
