@@ -334,9 +334,11 @@ extern "C" int bossgpu_create(const bossgpu_config* cfg, bossgpu_handle** out) {
         h->multi_fused = h->nb > 1 && h->nb <= SBM_MAX_NB && getenv("BOSSGPU_NO_FUSED_BARCODES") == nullptr;
         h->prescore_ok = one_each && (h->nb == 1 || h->multi_fused) && getenv("BOSSGPU_NO_PRESCORE") == nullptr;
         if (h->multi_fused) {
-            h->multi_ctas = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(227 * 1024) / (sbm_smem_bytes(h->nb) + 1024)));
             BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
             BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_multi<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbm_smem_bytes(h->nb)));
+            int resident = 0;                    // persistent grid = what the SMs hold at once (registers and shared memory decide)
+            BOSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_score_bin_multi<0>, SBM_THREADS, sbm_smem_bytes(h->nb)));
+            h->multi_ctas = std::max(1, resident);
         }
         BOSS_CUDA(cudaFuncSetAttribute(k_score_bin_tma<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbt_smem_bytes(false, 2)));
     }

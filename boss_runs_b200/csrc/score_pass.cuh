@@ -450,23 +450,19 @@ k_score_bin_tma(ScoreArgs a, int64_t n_tiles) {
 // Barcoded runs (nb > 1): the whole-row rules couple the barcodes of a site — a row observed in ANY barcode is scored
 // from the table in all of them (Q6), a row whose depth is at or below the dropout threshold in SOME barcode is zeroed in
 // all of them (Q8) — so a site's scores need its counters in every barcode. One CTA takes a tile through ALL barcodes,
-// half a tile (1000 sites) at a time, one consumer warp per 100-site bin (25 lanes x 4 sites), in two sweeps:
+// half a tile (1000 sites, 4 per thread) at a time, in two sweeps:
 //   sweep 1  every barcode's five counter planes come through the TMA ring once; each thread turns its sites' counters into
 //            table rows (19 bits, parked in shared memory: 3 bytes per site and barcode) and keeps the row-wide minimum
 //            depth and "ever observed" flag in registers;
 //   sweep 2  per barcode: rows back from shared memory (the thread's own), row rules applied, one table gather per site,
-//            the warp's 25 partial sums folded by a fixed shuffle tree into the bin sum — no block barrier, the warps run
-//            free of each other (the first version summed bins through shared memory behind a barrier per barcode and spent
-//            a third of its time waiting there).
+//            100-site bin sums in position order.
 // Every counter is read from HBM exactly once (10 B per site and barcode + 1 B reference base per site); the separate
 // row-summary pass (k_rowflags: all counters a second time) is only kept for more barcodes than fit in shared memory.
 // ------------------------------------------------------------------------------------------------
+constexpr int SBM_CONSUMERS = 256;                 // 250 active: 4 sites each = 1000 sites
+constexpr int SBM_THREADS = SBM_CONSUMERS + 32;
 constexpr int SBM_HALF = TILE / 2;
 constexpr int SBM_SITES = 4;
-constexpr int SBM_WARPS = SBM_HALF / BIN;          // 10 consumer warps, one per bin of the half tile
-constexpr int SBM_LANES = BIN / SBM_SITES;         // 25 lanes of a warp hold sites
-constexpr int SBM_CONSUMERS = SBM_WARPS * 32;
-constexpr int SBM_THREADS = SBM_CONSUMERS + 32;
 constexpr int SBM_PLANE_BYTES = SBM_HALF * 2;      // 2000
 constexpr int SBM_REF_OFF = 5 * SBM_PLANE_BYTES;   // 10000
 constexpr int SBM_STAGE_BYTES = 11136;             // 5 planes + a 1024-byte window of reference bases, padded to a multiple of 128
@@ -477,10 +473,9 @@ constexpr int SBM_STAGES = 3;
 constexpr int SBM_MAX_NB = 24;
 
 constexpr size_t sbm_smem_bytes(int nb) {
-    return (size_t)SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 16 +
+    return (size_t)SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 2 * (SBM_HALF / SBM_SITES) * sizeof(double) +
            4 * FREEZE * sizeof(uint32_t) + 2 * SBM_STAGES * sizeof(unsigned long long) + (size_t)nb * sizeof(unsigned) + 64 + 128;
 }
-__device__ __forceinline__ void sbm_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SBM_CONSUMERS) : "memory"); }
 
 template <int MODE>
 __global__ void __launch_bounds__(SBM_THREADS, 2)
@@ -490,8 +485,8 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
     unsigned char* s_stage = s_raw;
     uint16_t* s_rlo = reinterpret_cast<uint16_t*>(s_raw + SBM_STAGES * SBM_STAGE_BYTES);             // [nb][SBM_HALF]
     uint8_t* s_rhi = reinterpret_cast<uint8_t*>(s_rlo + (size_t)nb * SBM_HALF);                       // [nb][SBM_HALF]
-    uint32_t (*s_T)[FREEZE] = reinterpret_cast<uint32_t (*)[FREEZE]>(
-        s_raw + ((SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 15) & ~(size_t)15));
+    double* s_part = reinterpret_cast<double*>(s_raw + ((SBM_STAGES * SBM_STAGE_BYTES + (size_t)nb * SBM_HALF * 3 + 15) & ~(size_t)15));
+    uint32_t (*s_T)[FREEZE] = reinterpret_cast<uint32_t (*)[FREEZE]>(s_part + 2 * (SBM_HALF / SBM_SITES));
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_T + 4);                        // full[], empty[]
     unsigned* s_cov = reinterpret_cast<unsigned*>(s_bar + 2 * SBM_STAGES);                             // [nb]
     unsigned* s_drop = s_cov + nb;
@@ -539,19 +534,17 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
     }
 
     // ----------------------------------- consumers -----------------------------------
-    int it = 0;
-    const int lane = t & 31, wp = t >> 5;
-    const bool active = lane < SBM_LANES;                              // 25 of a warp's lanes hold 4 sites each: one bin
-    const int u = active ? SBM_LANES * wp + lane : 0;                  // this thread's 4-site group within the half tile
+    int it = 0, buf = 0;
+    const bool active = t < SBM_HALF / SBM_SITES;                      // 250 of the 256 consumer threads hold sites
     if (t < nb) s_cov[t] = 0u;
     if (t == 0) *s_drop = 0u;
-    sbm_bar();
+    consumer_bar();
     for (int64_t idx = blockIdx.x; idx < n_iter; idx += gridDim.x) {
         const int64_t tile = MODE == 2 ? (int64_t)a.tile_list[idx] : idx;
         const TileDesc td = a.tiles[tile];
         const int32_t thr_i = a.drop_thr[td.contig];                   // -1 while the depth rule is inactive
         for (int half = 0; half < 2; ++half) {
-            const int l0 = half * SBM_HALF + SBM_SITES * u;            // first site of this thread within the tile
+            const int l0 = half * SBM_HALF + SBM_SITES * t;            // first site of this thread within the tile
             uint32_t refw = 0, mn[SBM_SITES], any = 0;
 #pragma unroll
             for (int i = 0; i < SBM_SITES; ++i) mn[i] = 0xFFFFFFFFu;
@@ -565,22 +558,20 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
                 for (int k = 0; k < 5; ++k) v[k] = make_uint2(0, 0);
                 if (active) {
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) v[k] = reinterpret_cast<const uint2*>(sb + k * SBM_PLANE_BYTES)[u];
-                    if (b == 0) refw = reinterpret_cast<const uint32_t*>(sb + SBM_REF_OFF + (half ? SBM_REF_SKIP_H1 : 0))[u];
+                    for (int k = 0; k < 5; ++k) v[k] = reinterpret_cast<const uint2*>(sb + k * SBM_PLANE_BYTES)[t];
+                    if (b == 0) refw = reinterpret_cast<const uint32_t*>(sb + SBM_REF_OFF + (half ? SBM_REF_SKIP_H1 : 0))[t];
                 }
                 {
                     // the arrival must not overtake the loads: fold every loaded word into a value the arriving lane needs
                     const unsigned seen = v[0].x ^ v[0].y ^ v[1].x ^ v[1].y ^ v[2].x ^ v[2].y ^ v[3].x ^ v[3].y ^ v[4].x ^ v[4].y ^ refw;
                     const unsigned all_seen = __reduce_or_sync(0xFFFFFFFFu, seen);
-                    if (lane == 0) {
+                    if ((t & 31) == 0) {
                         asm volatile("" ::"r"(all_seen) : "memory");
                         mbar_arrive(smem_u32(&s_bar[SBM_STAGES + stage]));
                     }
                 }
                 unsigned covsum = 0;
                 if (active) {
-                    uint2 rl = make_uint2(0u, 0u);
-                    uint32_t rh = 0u;
 #pragma unroll
                     for (int i = 0; i < SBM_SITES; ++i) {
                         uint32_t c[5];
@@ -593,21 +584,19 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
                         const uint32_t rank = min(c[0], 29u) + s_T[0][min(p2, 29u)] + s_T[1][min(p3, 29u)] + s_T[2][min(p4, 29u)] +
                                               s_T[3][min(cs, 29u)];
                         const uint32_t row = cs < (uint32_t)FREEZE ? rank : (uint32_t)ROW_TINY;
-                        // rows of the thread's four sites: low halves in one 8-byte word, high bytes in one 4-byte word
-                        if (i < 2) rl.x |= (row & 0xFFFFu) << (16 * i); else rl.y |= (row & 0xFFFFu) << (16 * (i - 2));
-                        rh |= (row >> 16) << (8 * i);
+                        const int site = SBM_SITES * t + i;
+                        s_rlo[(size_t)b * SBM_HALF + site] = (uint16_t)(row & 0xFFFFu);
+                        s_rhi[(size_t)b * SBM_HALF + site] = (uint8_t)(row >> 16);
                         const bool valid = l0 + i < td.n_sites;
                         mn[i] = min(mn[i], cs);
                         any |= (cs != 0u ? 1u : 0u) << i;
                         covsum += valid ? cs : 0u;
                     }
-                    reinterpret_cast<uint2*>(s_rlo + (size_t)b * SBM_HALF)[u] = rl;
-                    reinterpret_cast<uint32_t*>(s_rhi + (size_t)b * SBM_HALF)[u] = rh;
                 }
                 covsum = __reduce_add_sync(0xFFFFFFFFu, covsum);
-                if (lane == 0 && covsum) atomicAdd(&s_cov[b], covsum);
+                if ((t & 31) == 0 && covsum) atomicAdd(&s_cov[b], covsum);
             }
-            // ---- sweep 2: row rules, table gather, the warp's bin sum, barcode by barcode ----
+            // ---- sweep 2: row rules, table gather, 100-site bins, barcode by barcode ----
             bool drop[SBM_SITES];
             unsigned ndrop = 0;
 #pragma unroll
@@ -617,36 +606,40 @@ k_score_bin_multi(ScoreArgs a, int64_t n_tiles) {
                 ndrop += drop[i] ? 1u : 0u;
             }
             ndrop = __reduce_add_sync(0xFFFFFFFFu, ndrop);
-            if (lane == 0 && ndrop) atomicAdd(s_drop, ndrop);
-            const int bin = half * SBM_WARPS + wp;
-#pragma unroll 2
+            if ((t & 31) == 0 && ndrop) atomicAdd(s_drop, ndrop);
             for (int b = 0; b < nb; ++b) {
-                double p = 0.0;
+                double* part = s_part + buf * (SBM_HALF / SBM_SITES);
                 if (active) {
                     double sv[SBM_SITES];
-                    const uint2 rl = reinterpret_cast<const uint2*>(s_rlo + (size_t)b * SBM_HALF)[u];
-                    const uint32_t rh = reinterpret_cast<const uint32_t*>(s_rhi + (size_t)b * SBM_HALF)[u];
 #pragma unroll
                     for (int i = 0; i < SBM_SITES; ++i) {
-                        uint32_t row = (((i < 2 ? rl.x : rl.y) >> (16 * (i & 1))) & 0xFFFFu) | (((rh >> (8 * i)) & 0xFFu) << 16);
+                        const int site = SBM_SITES * t + i;
+                        uint32_t row = (uint32_t)s_rlo[(size_t)b * SBM_HALF + site] | ((uint32_t)s_rhi[(size_t)b * SBM_HALF + site] << 16);
                         row = ((any >> i) & 1u) ? row : (uint32_t)ROW_SCORE0;      // Q5/Q6: row never observed in any barcode
                         if (drop[i] || l0 + i >= td.n_sites) row = ROW_ZERO;        // Q8 / whatever follows the contig end
                         const uint32_t refb = (refw >> (8 * i)) & 3u;
                         sv[i] = __ldg(a.table + (size_t)(row * 4 + refb));
                     }
-                    p = ((sv[0] + sv[1]) + sv[2]) + sv[3];                          // position order within a thread
+                    part[t] = ((sv[0] + sv[1]) + sv[2]) + sv[3];                    // position order within a thread
                 }
-                // the bin = 25 four-site partials (lanes 25..31 hold 0): the same butterfly in every launch, so the sum is
-                // reproducible; every lane ends up with it
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
-                if (lane == 0 && bin < td.n_bins) a.ds[(size_t)b * a.ds_len + td.ds_index + bin] = p;
+                consumer_bar();
+                if (t < SBM_HALF / BIN) {
+                    // bin j of the half = 25 consecutive 4-site partials, added in position order
+                    const int bin = half * (SBM_HALF / BIN) + t;
+                    if (bin < td.n_bins) {
+                        double acc = 0.0;
+#pragma unroll 5
+                        for (int k = 0; k < 25; ++k) acc += part[25 * t + k];
+                        a.ds[(size_t)b * a.ds_len + td.ds_index + bin] = acc;
+                    }
+                }
+                buf ^= 1;
             }
         }
-        sbm_bar();                                                   // every warp's depth sums and drop counts are in
+        consumer_bar();                                              // every warp's depth sums and drop counts are in
         if (t < nb) { a.tile_cov[(size_t)tile * nb + t] = s_cov[t]; s_cov[t] = 0u; }
         if (t == 32) { a.tile_drop[tile] = *s_drop; *s_drop = 0u; }
-        sbm_bar();                                                   // ... and reset, before the next tile adds to them
+        consumer_bar();                                              // ... and reset, before the next tile adds to them
     }
 }
 

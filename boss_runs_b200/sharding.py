@@ -514,8 +514,9 @@ class ShardedRun(BossRuns):
         try:
             if b.all_contig is not None:
                 # routed batch: own reads + the whole batch's reference span per contig (dropout rule, reference.py:157-158)
-                cov_add = np.zeros(len(self.contigs_filt), dtype=np.int64)
-                np.add.at(cov_add, b.all_contig, np.abs(b.all_tend - b.all_tstart))
+                # (spans sum far below 2^53: the float64 weights of bincount are exact)
+                cov_add = np.bincount(b.all_contig, weights=np.abs(b.all_tend - b.all_tstart),
+                                      minlength=len(self.contigs_filt)).astype(np.int64)
                 for e in self.engines:
                     e.ingest_records_routed(b.contig, b.tstart, b.tend, b.barcode, b.rev, b.cigar_ptr, b.cigar_len,
                                             b.seq_ptr, b.seq_from, b.seq_to, cov_add)
