@@ -1177,7 +1177,14 @@ static int phase2_hist(bossgpu_handle* h, const bossgpu_update_params* p) {
     a.benefit = h->d_benefit; a.n_rows = h->n_rows; a.nb = h->nb; a.R0 = h->R0; a.M = h->M_rows; a.target = h->target_rows;
     a.fg = fg; a.fw = h->d_fhat_w; a.shift = h->fhat_shift; a.ushift = h->ubar_shift; a.hist = h->d_hist; a.upd = h->d_upd; a.codes = h->d_codes;
     const int64_t n_groups = (h->R0 + h->n_rows - 1) / HIST_GROUP - h->R0 / HIST_GROUP + 1;     // groups of the global row axis
-    unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_groups, HIST_THREADS), (int64_t)h->n_sm * 10));
+    // persistent grid: exactly what the SMs hold at once (a grid of 10 CTAs per SM ran as 1.7 waves with 6 resident)
+    static int hist_resident = 0;
+    if (hist_resident == 0) {
+        BOSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_resident, k_hist, HIST_THREADS, 0));
+        hist_resident = std::max(1, hist_resident);
+    }
+    const int64_t hist_ctas = std::max<int64_t>(1, (int64_t)h->n_sm * hist_resident / h->nb);
+    unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_groups, HIST_THREADS), hist_ctas));
     k_hist<<<dim3(gx, (unsigned)h->nb), HIST_THREADS, 0, h->stream>>>(a);
     BOSS_KERNEL_CHECK();
     h->launches += 3;
