@@ -683,8 +683,10 @@ k_distribute(DistArgs a) {
         uint32_t w[4] = {0, 0, 0, 0};
         bool changed = false;
         bool fast = false;
-        if (NB1 && whole && by_code && a.mask_ptrs == nullptr) {
-            // eight strategy rows of one barcode-less contig inside one bucket: sixteen code bytes against the threshold bin
+        if (NB1 && whole && by_code) {
+            // eight strategy rows of one barcode-less contig: sixteen code bytes against the threshold bin. With several shards
+            // the codes of this shard serve every strategy row whose merged row lies here — all but the few rows at a shard
+            // edge (Q2 shifts contig k by k rows), which read the gathered masks below
             const int64_t dl0 = i0 >> 1, dl1 = dl0 + 7;
             if (dl0 >= row_hi || dl0 < row_lo) {
                 sg = find_segment(a.srow_start, a.n_seg, dl0);
@@ -692,8 +694,10 @@ k_distribute(DistArgs a) {
             }
             const int64_t j0 = dl0 - row_lo;                               // row within the segment
             const int64_t bk = j0 / (BUCKET / BIN);
-            const int64_t c0 = 2 * (a.D0 + dl0 - a.R0);                  // Q2: strategy row d reads merged row d
-            if (dl1 < row_hi && ((reinterpret_cast<uintptr_t>(a.codes) + c0) & 3) == 0) {
+            const int64_t m0 = a.D0 + dl0 - a.R0;                        // Q2: strategy row d reads merged row d
+            const int64_t c0 = 2 * m0;
+            const bool local = a.mask_ptrs == nullptr || (m0 >= 0 && m0 + 8 <= a.n_rows);
+            if (local && dl1 < row_hi && ((reinterpret_cast<uintptr_t>(a.codes) + c0) & 3) == 0) {
                 fast = true;
                 const uint4 ov = *reinterpret_cast<const uint4*>(a.strat + i0);
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
