@@ -16,6 +16,7 @@
 #include "synth.cuh"
 #include "aeons.cuh"
 #include "tokenizer.h"
+#include "workerpool.h"
 
 namespace boss {
 thread_local std::string g_last_error;
@@ -769,14 +770,19 @@ static int ingest_text_impl(bossgpu_handle* h, int64_t n_all, const int32_t* con
         work(0);
         for (int g = 0; g < G; ++g) TRY(ship(g));
     } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+        WorkerPool& wp = WorkerPool::instance();
+        std::unique_lock<std::mutex> own(wp.owner, std::try_to_lock);
+        const std::function<void(int)> job = work;
+        std::vector<std::thread> spawned;
+        if (own.owns_lock()) wp.start(T, job);
+        else for (int t = 0; t < T; ++t) spawned.emplace_back(work, t);
         int rc_ship = 0;
         for (int g = 0; g < G; ++g) {
             while (done[g].load(std::memory_order_acquire) < T) std::this_thread::yield();
             if (rc_ship == 0) rc_ship = ship(g);
         }
-        for (auto& th : pool) th.join();
+        if (own.owns_lock()) wp.wait();
+        for (auto& th : spawned) th.join();
         if (rc_ship != 0) return rc_ship;
     }
     const double ms_pass2 = ms_since(t_begin);

@@ -3,6 +3,7 @@ its struct layouts match the ctypes mirrors, its pure-host entry points work, an
 (instead of falling back to anything) when there is no CUDA device."""
 import ctypes as C
 import re
+import subprocess
 from pathlib import Path
 
 import numpy as np
@@ -143,3 +144,47 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libbossgpu.so")
     with pytest.raises(_lib.BossGpuError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_worker_pool_runs_every_task_and_survives_reuse(tmp_path):
+    """csrc/workerpool.h (the ingest path's persistent host threads) on its own: every worker index runs exactly once per
+    start(), pools of different sizes follow each other, a forked child gets fresh workers."""
+    src = tmp_path / "pool.cpp"
+    src.write_text(r'''
+#include "workerpool.h"
+#include <atomic>
+#include <cstdio>
+#include <sys/wait.h>
+int main() {
+    boss::WorkerPool& p = boss::WorkerPool::instance();
+    const int sizes[] = {3, 15, 1, 8, 15, 2};
+    for (int rep = 0; rep < 200; ++rep) {
+        const int n = sizes[rep % 6];
+        std::atomic<int> hits[16];
+        for (auto& h : hits) h = 0;
+        const std::function<void(int)> job = [&](int t) { hits[t].fetch_add(1); };
+        std::unique_lock<std::mutex> own(p.owner, std::try_to_lock);
+        if (!own.owns_lock()) return 2;
+        p.start(n, job);
+        p.wait();
+        for (int t = 0; t < 16; ++t) if (hits[t] != (t < n ? 1 : 0)) { std::printf("rep %d worker %d ran %d times\n", rep, t, (int)hits[t]); return 1; }
+    }
+    const pid_t c = fork();
+    if (c == 0) {
+        std::atomic<int> sum{0};
+        const std::function<void(int)> job = [&](int t) { sum.fetch_add(t + 1); };
+        p.start(4, job);
+        p.wait();
+        _exit(sum == 10 ? 0 : 3);
+    }
+    int st = 0;
+    waitpid(c, &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::printf("child status %d\n", st); return 4; }
+    std::puts("ok");
+    return 0;
+}
+''')
+    exe = tmp_path / "pool"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", str(REPO / "boss_runs_b200" / "csrc"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
