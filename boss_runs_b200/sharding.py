@@ -172,9 +172,14 @@ class LocalGroup:
                 recv[s][h:].copy_(send[s + 1][:h])          # right neighbour's first bins
 
     def shared_mirror(self, nbytes: int) -> np.ndarray:
-        """Host array every shard's distribution kernel writes its slice of (here: ordinary process memory,
-        page-locked by each engine)."""
-        self._mirror = np.ones(nbytes, dtype=np.uint8)
+        """Host array every shard's distribution kernel writes its slice of (here: an anonymous mapping of this process,
+        page-locked once for all engines). It owns whole pages: page-locking works on pages, and a heap array would share
+        its first and last page with unrelated small arrays — a later pageable copy into one of those (half inside a
+        locked page, half outside) is refused by the driver with "invalid argument"."""
+        import mmap
+        self._mirror_map = mmap.mmap(-1, (max(nbytes, 1) + mmap.PAGESIZE - 1) // mmap.PAGESIZE * mmap.PAGESIZE)
+        self._mirror = np.frombuffer(self._mirror_map, dtype=np.uint8)[:nbytes]
+        self._mirror[:] = 1
         return self._mirror
 
     def setup_fabric(self, timeout_s: float = 0.0) -> bool:

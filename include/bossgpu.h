@@ -307,7 +307,9 @@ int bossgpu_strat_host(bossgpu_handle* h, uint8_t** ptr, int64_t* bytes);
  * outlive the handle. */
 int bossgpu_set_strat_mirror(bossgpu_handle* h, void* host_ptr, int64_t bytes, int registered);
 /* cudaHostRegister (mapped, portable) / cudaHostUnregister of the pages around a host range, for callers without
- * a CUDA binding of their own */
+ * a CUDA binding of their own. Page-locking works on whole pages: hand in memory that owns its pages (a shared-memory
+ * segment, an anonymous mapping). A heap array shares its first and last page with unrelated allocations, and a later
+ * pageable cudaMemcpy into such a neighbour (half inside a locked page) is refused by the driver. */
 int bossgpu_host_register(void* host_ptr, int64_t bytes);
 int bossgpu_host_unregister(void* host_ptr);
 /* accepted entries per segment and strand after the last update, int64 [n_segments][2]
