@@ -269,35 +269,110 @@ static void table_free(paf_table_t* T) {
     memset(T, 0, sizeof *T);
 }
 
+/* Separators of one line. The bulk of a PAF line is its cg:Z: value (kilobytes); splitting it with one memchr per question
+ * (where does the line end? the field? is there a third colon?) walks that value four times. One pass over the line with
+ * 16/32-byte compares records the offsets of every tab and colon up to the newline; fields and tag parts follow from those. */
+typedef struct { Py_ssize_t* off; Py_ssize_t n, cap; } seps_t;
+
+static int seps_push(seps_t* S, Py_ssize_t o) {
+    if (S->n == S->cap) {
+        const Py_ssize_t cap = S->cap ? 2 * S->cap : 64;
+        Py_ssize_t* q = (Py_ssize_t*)PyMem_Realloc(S->off, sizeof(Py_ssize_t) * (size_t)cap);
+        if (!q) { PyErr_NoMemory(); return -1; }
+        S->off = q; S->cap = cap;
+    }
+    S->off[S->n++] = o;
+    return 0;
+}
+
+/* offsets of the tabs and colons of tp[pos, e) into S, e = offset of the first newline at or after pos (tlen if none);
+ * returns e, or -1 with a Python error set */
+static Py_ssize_t scan_line_scalar(const char* tp, Py_ssize_t pos, Py_ssize_t tlen, seps_t* S) {
+    for (; pos < tlen; ++pos) {
+        const char c = tp[pos];
+        if (c == '\n') return pos;
+        if ((c == '\t' || c == ':') && seps_push(S, pos) < 0) return -1;
+    }
+    return tlen;
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static Py_ssize_t scan_line_avx2(const char* tp, Py_ssize_t pos, Py_ssize_t tlen, seps_t* S) {
+    const __m256i vt = _mm256_set1_epi8('\t'), vc = _mm256_set1_epi8(':'), vn = _mm256_set1_epi8('\n');
+    while (pos + 32 <= tlen) {
+        const __m256i x = _mm256_loadu_si256((const __m256i*)(tp + pos));
+        unsigned m = (unsigned)_mm256_movemask_epi8(
+            _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, vt), _mm256_cmpeq_epi8(x, vc)), _mm256_cmpeq_epi8(x, vn)));
+        while (m) {
+            const int k = __builtin_ctz(m);
+            m &= m - 1;
+            if (tp[pos + k] == '\n') return pos + k;
+            if (seps_push(S, pos + k) < 0) return -1;
+        }
+        pos += 32;
+    }
+    return scan_line_scalar(tp, pos, tlen, S);
+}
+static Py_ssize_t scan_line_sse2(const char* tp, Py_ssize_t pos, Py_ssize_t tlen, seps_t* S) {
+    const __m128i vt = _mm_set1_epi8('\t'), vc = _mm_set1_epi8(':'), vn = _mm_set1_epi8('\n');
+    while (pos + 16 <= tlen) {
+        const __m128i x = _mm_loadu_si128((const __m128i*)(tp + pos));
+        unsigned m = (unsigned)_mm_movemask_epi8(_mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, vt), _mm_cmpeq_epi8(x, vc)), _mm_cmpeq_epi8(x, vn)));
+        while (m) {
+            const int k = __builtin_ctz(m);
+            m &= m - 1;
+            if (tp[pos + k] == '\n') return pos + k;
+            if (seps_push(S, pos + k) < 0) return -1;
+        }
+        pos += 16;
+    }
+    return scan_line_scalar(tp, pos, tlen, S);
+}
+#endif
+
+static Py_ssize_t scan_line(const char* tp, Py_ssize_t pos, Py_ssize_t tlen, seps_t* S) {
+#if defined(__x86_64__)
+    static int avx2 = -1;
+    if (avx2 < 0) avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+    return avx2 ? scan_line_avx2(tp, pos, tlen, S) : scan_line_sse2(tp, pos, tlen, S);
+#else
+    return scan_line_scalar(tp, pos, tlen, S);
+#endif
+}
+
 /* pass 1: tokenise every line, filter, group by read. 0 = ok, -1 = Python error set (the caller frees the table). */
+static int tokenise_paf_lines(const char* tp, Py_ssize_t tlen, long long min_len, paf_table_t* T, seps_t* S);
+
 static int tokenise_paf(PyObject* text, long long min_len, paf_table_t* T) {
     memset(T, 0, sizeof *T);
     Py_ssize_t tlen = 0;
     const char* tp = PyUnicode_AsUTF8AndSize(text, &tlen);
     if (!tp) return -1;
     if (tlen != PyUnicode_GET_LENGTH(text)) { PyErr_SetString(PyExc_ValueError, "PAF text must be ASCII"); return -1; }
-    Py_ssize_t n_lines = 0;
-    for (const char* q = tp; (q = (const char*)memchr(q, '\n', (size_t)(tp + tlen - q))) != NULL; ++q) ++n_lines;
-    if (tlen > 0 && tp[tlen - 1] != '\n') ++n_lines;
-    T->recs = (rec_t*)PyMem_Malloc(sizeof(rec_t) * (size_t)(n_lines ? n_lines : 1));
-    T->grps = (grp_t*)PyMem_Malloc(sizeof(grp_t) * (size_t)(n_lines ? n_lines : 1));
     T->gindex = PyDict_New();
-    if (!T->recs || !T->grps || !T->gindex) { PyErr_NoMemory(); return -1; }
-    rec_t* const recs = T->recs;
-    grp_t* const grps = T->grps;
+    if (!T->gindex) return -1;
+    seps_t S = {NULL, 0, 0};
+    const int rc = tokenise_paf_lines(tp, tlen, min_len, T, &S);
+    PyMem_Free(S.off);
+    return rc;
+}
+
+static int tokenise_paf_lines(const char* tp, Py_ssize_t tlen, long long min_len, paf_table_t* T, seps_t* S) {
+    Py_ssize_t cap_rec = 0, cap_grp = 0;
     PyObject* const gindex = T->gindex;
 #define n_rec (T->n_rec)
 #define n_grp (T->n_grp)
-    /* ---- pass 1: tokenise every line, filter, group by read ---- */
     for (Py_ssize_t pos = 0; pos < tlen;) {
-        const char* nl = (const char*)memchr(tp + pos, '\n', (size_t)(tlen - pos));
-        const Py_ssize_t e = nl ? (Py_ssize_t)(nl - tp) : tlen;
+        S->n = 0;
+        const Py_ssize_t e = scan_line(tp, pos, tlen, S);
+        if (e < 0) return -1;
         span_t line = {tp + pos, e - pos};
         pos = e + 1;
         line = strip_span(line);
+        const Py_ssize_t la = (Py_ssize_t)(line.p - tp), lb = la + line.n;     /* the stripped line as offsets into the text */
         span_t col[12];
         int nc = 0;
-        Py_ssize_t i = 0, c0 = 0;
         rec_t r;
         memset(&r, 0, sizeof r);
         r.next = -1;
@@ -305,48 +380,46 @@ static int tokenise_paf(PyObject* text, long long min_len, paf_table_t* T) {
         int primary = 0, has_as = 0;
         char as_typ = 'i';
         span_t as_val = {NULL, 0};
+        Py_ssize_t si = 0, fs = la;
+        while (si < S->n && S->off[si] < la) ++si;                               /* separators inside the stripped-off head */
         for (;;) {
-            {
-                const char* tb = (const char*)memchr(line.p + c0, '\t', (size_t)(line.n - c0));
-                i = tb ? (Py_ssize_t)(tb - line.p) : line.n;
-                span_t f = {line.p + c0, i - c0};
-                if (nc < 12) {
-                    col[nc] = f;
-                } else {
-                    /* key:type:value */
-                    Py_ssize_t a = -1, b = -1, colons = 0;
-                    const char* c1 = (const char*)memchr(f.p, ':', (size_t)f.n);
-                    if (c1) {
-                        a = c1 - f.p; colons = 1;
-                        const char* c2 = (const char*)memchr(c1 + 1, ':', (size_t)(f.n - a - 1));
-                        if (c2) {
-                            b = c2 - f.p; colons = 2;
-                            if (memchr(c2 + 1, ':', (size_t)(f.n - b - 1))) colons = 3;
-                        }
-                    }
-                    if (colons != 2) {
-                        PyErr_SetString(PyExc_ValueError, colons < 2 ? "not enough values to unpack (expected 3)" : "too many values to unpack (expected 3)");
-                        return -1;
-                    }
-                    span_t key = {f.p, a}, typ = {f.p + a + 1, b - a - 1}, val = {f.p + b + 1, f.n - b - 1};
-                    if (typ.n != 1 || !(typ.p[0] == 'i' || typ.p[0] == 'A' || typ.p[0] == 'f' || typ.p[0] == 'Z')) {
-                        PyObject* ko = PyUnicode_FromStringAndSize(typ.p, typ.n);
-                        if (ko) { PyErr_SetObject(PyExc_KeyError, ko); Py_DECREF(ko); }
-                        return -1;
-                    }
-                    if (key.n == 2 && key.p[0] == 'A' && key.p[1] == 'S') {
-                        as_val = val; as_typ = typ.p[0]; has_as = 1;      /* a repeated key keeps its LAST value (dict) */
-                    } else if (key.n == 2 && key.p[0] == 't' && key.p[1] == 'p') {
-                        primary = val.n == 1 && val.p[0] == 'P';
-                    } else if (key.n == 2 && key.p[0] == 'c' && key.p[1] == 'g') {
-                        r.cigar = val;
-                        r.has_cigar = 1;
-                    }
-                }
-                ++nc;
-                c0 = i + 1;
-                if (i == line.n) break;
+            /* the field runs to the next tab inside the stripped line; its colons come first in the separator list */
+            Py_ssize_t c1 = -1, c2 = -1, colons = 0;
+            while (si < S->n && S->off[si] < lb && tp[S->off[si]] == ':') {
+                if (colons == 0) c1 = S->off[si]; else if (colons == 1) c2 = S->off[si];
+                ++colons; ++si;
             }
+            const int last = !(si < S->n && S->off[si] < lb);
+            const Py_ssize_t fe = last ? lb : S->off[si];
+            span_t f = {tp + fs, fe - fs};
+            if (nc < 12) {
+                col[nc] = f;
+            } else {
+                /* key:type:value */
+                if (colons != 2) {
+                    PyErr_SetString(PyExc_ValueError, colons < 2 ? "not enough values to unpack (expected 3)" : "too many values to unpack (expected 3)");
+                    return -1;
+                }
+                const Py_ssize_t a = c1 - fs, b = c2 - fs;
+                span_t key = {f.p, a}, typ = {f.p + a + 1, b - a - 1}, val = {f.p + b + 1, f.n - b - 1};
+                if (typ.n != 1 || !(typ.p[0] == 'i' || typ.p[0] == 'A' || typ.p[0] == 'f' || typ.p[0] == 'Z')) {
+                    PyObject* ko = PyUnicode_FromStringAndSize(typ.p, typ.n);
+                    if (ko) { PyErr_SetObject(PyExc_KeyError, ko); Py_DECREF(ko); }
+                    return -1;
+                }
+                if (key.n == 2 && key.p[0] == 'A' && key.p[1] == 'S') {
+                    as_val = val; as_typ = typ.p[0]; has_as = 1;      /* a repeated key keeps its LAST value (dict) */
+                } else if (key.n == 2 && key.p[0] == 't' && key.p[1] == 'p') {
+                    primary = val.n == 1 && val.p[0] == 'P';
+                } else if (key.n == 2 && key.p[0] == 'c' && key.p[1] == 'g') {
+                    r.cigar = val;
+                    r.has_cigar = 1;
+                }
+            }
+            ++nc;
+            if (last) break;
+            fs = fe + 1;
+            ++si;
         }
         if (nc < 12) { PyErr_SetString(PyExc_IndexError, "list index out of range (PAF line with fewer than 12 columns)"); return -1; }
         if (has_as) {
@@ -393,23 +466,35 @@ static int tokenise_paf(PyObject* text, long long min_len, paf_table_t* T) {
         if (!qn) return -1;
         PyObject* gi = PyDict_GetItemWithError(gindex, qn);         /* borrowed */
         if (!gi && PyErr_Occurred()) { Py_DECREF(qn); return -1; }
+        if (n_rec == cap_rec) {
+            const Py_ssize_t cap = cap_rec ? 2 * cap_rec : 1024;
+            rec_t* q = (rec_t*)PyMem_Realloc(T->recs, sizeof(rec_t) * (size_t)cap);
+            if (!q) { Py_DECREF(qn); PyErr_NoMemory(); return -1; }
+            T->recs = q; cap_rec = cap;
+        }
         Py_ssize_t g;
         if (gi) {
             g = PyLong_AsSsize_t(gi);
             Py_DECREF(qn);
-            recs[grps[g].last].next = n_rec;
-            grps[g].last = n_rec;
-            grps[g].count++;
+            T->recs[T->grps[g].last].next = n_rec;
+            T->grps[g].last = n_rec;
+            T->grps[g].count++;
         } else {
+            if (n_grp == cap_grp) {
+                const Py_ssize_t cap = cap_grp ? 2 * cap_grp : 1024;
+                grp_t* q = (grp_t*)PyMem_Realloc(T->grps, sizeof(grp_t) * (size_t)cap);
+                if (!q) { Py_DECREF(qn); PyErr_NoMemory(); return -1; }
+                T->grps = q; cap_grp = cap;
+            }
             g = n_grp++;
             PyObject* go = PyLong_FromSsize_t(g);
             if (!go || PyDict_SetItem(gindex, qn, go) < 0) { Py_XDECREF(go); Py_DECREF(qn); --n_grp; return -1; }
             Py_DECREF(go);
-            grps[g].first = grps[g].last = n_rec;
-            grps[g].count = 1;
-            grps[g].qname = qn;                                      /* owned until `done` */
+            T->grps[g].first = T->grps[g].last = n_rec;
+            T->grps[g].count = 1;
+            T->grps[g].qname = qn;                                   /* owned until `done` */
         }
-        recs[n_rec++] = r;
+        T->recs[n_rec++] = r;
     }
 
 #undef n_rec
