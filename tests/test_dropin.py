@@ -79,6 +79,39 @@ class StubEngine:
     def seg_accept(self): return np.ones((len(self.lens), 2), dtype=np.int64)
     def coverage(self, seg): return np.zeros((self.lens[seg], 5, self.nb), dtype=np.uint16)
 
+def model_engine():
+    """The NumPy model of the library (tests/shard_model.py: oracle scoring + the kernels' phase structure) behind the engine
+    interface the mixin talks to: upstream's classes + mixin + this must reproduce what upstream alone computes."""
+    from shard_model import NumpyShardEngine
+    from boss_runs_b200._lib import BUF_SWITCH
+    from boss_runs_b200.sharding import plan_shards
+
+    class ModelEngine(NumpyShardEngine):
+        def __init__(self, contig_lengths, ref_codes, n_barcodes, ploidy, n_sites_total, device):
+            plan = plan_shards([int(x) for x in contig_lengths], 1)
+            super().__init__(contig_lengths, ref_codes, n_barcodes=n_barcodes, ploidy=ploidy, n_sites_total=n_sites_total,
+                             segments=plan[0], halo_bins=0)
+            self.set_shards(1, 0, [0, self.M_rows])
+            self.thresholds = []
+        def prescore_begin(self): pass
+        def prescore(self, contig, tstart, tend): pass
+        def update(self, approx_ccl, time_cost, bucket_threshold, fhat_scalars, debug=False):
+            p = self.params(approx_ccl, time_cost, bucket_threshold, fhat_scalars=fhat_scalars)
+            self.update_phase(0, p)
+            if self.buf[BUF_SWITCH][0]:
+                for ph in (1, 2, 3):
+                    self.update_phase(ph, p)
+            out = self.update_phase(4, p)
+            self.thresholds.append(out.threshold)
+            return out
+        def seg_accept(self):
+            acc, row = [], 0
+            for n in self.n_srows:
+                acc.append([int(self._strat[row: row + n, 0].sum()), int(self._strat[row: row + n, 1].sum())])
+                row += n
+            return np.asarray(acc, dtype=np.int64)
+    return ModelEngine
+
 mode, toml = sys.argv[1], sys.argv[2]
 sys.argv = ["boss", "--toml", toml]
 import boss.config
@@ -114,6 +147,29 @@ if mode == "live":
         assert c.switched_on.all()
         row += n
     out["npz_false"] = int(sum((~npz[k]).sum() for k in npz.files if npz[k].ndim == 3))
+elif mode == "simmodel":
+    cls = dropin.BossRunsSimGPU
+    cls.engine_factory = model_engine()
+    cls.gpu = opts
+    exp = cls(args=conf.args)
+    exp.init_sim()
+    counts = {}
+    decisions = exp.make_decisions
+    def spy(**kw):
+        res = decisions(**kw)
+        counts["c"] = [int(x) for x in res[2:]]
+        return res
+    exp.make_decisions = spy
+    while exp.batch < conf.args.simulation.maxb:
+        exp.process_batch_sim(exp.process_batch_runs_sim)
+    out["batches"] = exp.batch
+    out["counts"] = counts["c"]
+    out["threshold"] = float(exp.engine.thresholds[-1]).hex()
+    out["approx_ccl"] = [int(x) for x in exp.rl_dist.approx_ccl]
+    npz = np.load(Path(exp.out_dir) / "masks" / "boss.npz")
+    out["strat"] = {n: np.packbits(npz[n].ravel()).tobytes().hex() for n in exp.contigs_filt}
+    out["shares"] = all(np.shares_memory(c.strat, exp.engine._strat) for c in exp.contigs_filt.values())
+    exp.cleanup()
 else:
     cls = dropin.BossRunsSimGPU
     cls.engine_factory = StubEngine
@@ -131,9 +187,9 @@ print("RESULT " + json.dumps(out))
 
 def _run_driver(mode, toml, cwd):
     env = dict(os.environ)
-    env["PYTHONPATH"] = os.pathsep.join([str(REPO), str(REPO / "oracle" / "shims"), str(REFERENCE)])
+    env["PYTHONPATH"] = os.pathsep.join([str(REPO), str(REPO / "tests"), str(REPO / "oracle" / "shims"), str(REFERENCE)])
     env["PYTHONDONTWRITEBYTECODE"] = "1"
-    r = subprocess.run([sys.executable, "-c", _DRIVER, mode, str(toml)], cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", _DRIVER, mode, str(toml)], cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     import json
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
@@ -202,6 +258,57 @@ def test_mixin_on_upstream_simulation(tmp_path):
     ingested = [e[1] for e in res["log"] if e[0] == "ingest"]
     starts = [e[1] for e in res["log"] if e[0] == "read_starts"]
     assert all(0 < s <= n <= 600 for s, n in zip(starts, ingested))          # read starts: accepted reads only (simulation.py:171)
+
+
+@needs_reference
+def test_dropin_with_model_engine_reproduces_upstream_simulation(tmp_path):
+    """Numbers, not only call order: upstream's own `BossRunsSim` classes + the mixin + a NumPy model of the library (oracle
+    scoring behind the engine interface) run BASELINE config 1 (whole `data/BOSS_test_data`, `batchsize = 4000, maxb = 1`)
+    and must arrive where upstream ALONE arrived — decisions, read-length staircase, threshold, every mask bit of every
+    contig, as recorded from upstream in tests/golden/c1_full.npz (run A)."""
+    import numpy as np
+    gold = np.load(REPO / "tests" / "golden" / "c1_full.npz")
+    data = REFERENCE / "data" / "BOSS_test_data"
+    for f in ("zymo.fa", "ERR3152366_10k.fq", "ERR3152366_10k.paf", "ERR3152366_10k_trunc.paf"):
+        if not (data / f).exists():
+            pytest.skip(f"{f} not in the reference's test data")
+        os.symlink(data / f, tmp_path / f)
+    (tmp_path / "zymo.mmi").touch()
+    toml = tmp_path / "c1.toml"
+    toml.write_text(textwrap.dedent(f'''
+        [general]
+        name = "c1model"
+        ref = "{tmp_path / "zymo.fa"}"
+        mmi = "{tmp_path / "zymo.mmi"}"
+        [optional]
+        ploidy = 1
+        bucket_threshold = 0
+        [simulation]
+        fq = "{tmp_path / "ERR3152366_10k.fq"}"
+        paf_full = "{tmp_path / "ERR3152366_10k.paf"}"
+        paf_trunc = "{tmp_path / "ERR3152366_10k_trunc.paf"}"
+        batchsize = 4000
+        maxb = 1
+        '''))
+    res = _run_driver("simmodel", toml, tmp_path)
+    assert res["batches"] == 1 and res["shares"]
+    assert res["counts"] == [int(x) for x in gold["A0_counts"]]
+    assert res["approx_ccl"] == [int(x) for x in gold["A0_approx_ccl"]]
+    want_thr = float(gold["A0_threshold"])
+    assert abs(float.fromhex(res["threshold"]) - want_thr) <= 1e-12 * want_thr
+    names = [str(n) for n in gold["A_contigs"]]
+    assert sorted(res["strat"]) == sorted(names)
+    differing = total = 0
+    for n in names:
+        got = np.unpackbits(np.frombuffer(bytes.fromhex(res["strat"][n]), dtype=np.uint8))
+        want = np.unpackbits(gold[f"A0_{n}_strat"])
+        assert got.shape == want.shape, n
+        differing += int((got != want).sum())
+        total += want.size
+    # the model sums every window directly (like the CUDA kernels), upstream carries a running accumulator: entries whose
+    # benefit sits within rounding of the threshold may fall either side (tests/tolerances.py MASK_REL)
+    print('mask entries differing from upstream:', differing, 'of', total)
+    assert differing <= max(2, total // 100_000), (differing, total)
 
 
 # ------------------------------------------------------------------------------------------------------
