@@ -224,3 +224,47 @@ def test_text_path_names_and_errors(fc):
     pd, want = _via_objects(cc, odd, {"7": read, "r2": read}, 1)
     same_text(got, want)
     assert list(got.rev) == [0, 1]
+
+
+def test_switch_pull_flags_whole_contigs_from_the_flat_image():
+    """`BossRuns._pull_switches` with thousands of contigs: one segmented reduction over the library's flat switch image
+    (reference.py:203-207: any switch of any barcode flags the whole contig), contigs flagged once stay flagged, and the
+    image is read again on every call (the library rewrites it in place)."""
+    from types import SimpleNamespace
+    from boss_runs_b200.runs import BossRuns
+    nb, sizes = 2, [3, 1, 5, 2]
+    flat = np.zeros((sum(sizes), nb), dtype=bool)
+    views, row = [], 0
+    for k in sizes:
+        views.append(flat[row: row + k])
+        row += k
+
+    class Eng:
+        buckets_flat = flat
+        def buckets_host(self):
+            return views
+    run = BossRuns.__new__(BossRuns)
+    run.engine = Eng()
+    run._switch_views = None
+    run.contigs_filt = {f"c{i}": SimpleNamespace(switched_on=np.zeros(nb, dtype=bool), bucket_switches=None) for i in range(len(sizes))}
+    run._pull_switches()
+    assert not any(c.switched_on.any() for c in run.contigs_filt.values())
+    assert all(c.bucket_switches is v for c, v in zip(run.contigs_filt.values(), views))
+    flat[3, 1] = True                       # contig 1 (one row), barcode 1
+    flat[8, 0] = True                       # contig 2, last row
+    run._pull_switches()
+    assert [bool(c.switched_on.all()) for c in run.contigs_filt.values()] == [False, True, True, False]
+    flat[0, 0] = True
+    flat[10, 1] = True
+    run._pull_switches()
+    assert all(c.switched_on.all() for c in run.contigs_filt.values())
+    run._pull_switches()                    # everything flagged: nothing left to do
+    # without a flat image (another engine type) the per-contig test gives the same answer
+    run2 = BossRuns.__new__(BossRuns)
+    run2.engine = SimpleNamespace(buckets_host=lambda: views)
+    run2._switch_views = None
+    run2.contigs_filt = {f"c{i}": SimpleNamespace(switched_on=np.zeros(nb, dtype=bool), bucket_switches=None) for i in range(len(sizes))}
+    flat[:] = False
+    flat[4, 0] = True
+    run2._pull_switches()
+    assert [bool(c.switched_on.all()) for c in run2.contigs_filt.values()] == [False, False, True, False]
